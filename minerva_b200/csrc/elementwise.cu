@@ -1,0 +1,352 @@
+// elementwise.cu -- a1 Arithmetic, a2/a3 ArithmeticConst, a4 Elewise, a10/a11 Activation,
+// a20 copy, a21 Fill / Philox generators, 8(f) fused SGD.  All HBM-bound streaming kernels:
+// 128-bit coalesced accesses, 4 independent vectors in flight per thread, grid = one wave of
+// 148 SMs x 8 CTAs.  Replaces K1-K3, K10, K11 and the cuBLAS copy+axpy / copy+scal two-pass
+// paths L2-L4, L6 and cuDNN activations L12.
+//
+// Bit-exactness vs minerva/op/impl/basic.cpp: every arithmetic step is an explicit IEEE
+// round-to-nearest intrinsic (no FMA contraction, true division), so +,-,*,/,neg,relu,fill,copy
+// match the CPU reference bit for bit.  exp/ln/tanh use CUDA's expf/logf/tanhf (<= 2 ulp from
+// glibc; the reference's own tests allow 4 ulp, tests/unittest_elewise.cpp:17).
+#include "common.cuh"
+
+namespace mnv {
+
+std::atomic<uint64_t> g_launches{0};
+
+constexpr int kUnroll = 4;
+
+template <int NIN, class Op>
+__global__ void __launch_bounds__(kBlock) ew_vec4_kernel(const float4* __restrict__ a,
+                                                         const float4* __restrict__ b,
+                                                         const float4* __restrict__ c,
+                                                         float4* __restrict__ out, size_t n4, Op op) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; base < n4;
+       base += stride * kUnroll) {
+    float4 va[kUnroll], vb[kUnroll], vc[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      size_t i = base + u * stride;
+      if (i < n4) {
+        va[u] = __ldg(a + i);
+        if (NIN > 1) vb[u] = __ldg(b + i);
+        if (NIN > 2) vc[u] = __ldg(c + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      size_t i = base + u * stride;
+      if (i < n4) {
+        float4 r;
+        r.x = op(va[u].x, vb[u].x, vc[u].x);
+        r.y = op(va[u].y, vb[u].y, vc[u].y);
+        r.z = op(va[u].z, vb[u].z, vc[u].z);
+        r.w = op(va[u].w, vb[u].w, vc[u].w);
+        out[i] = r;
+      }
+    }
+  }
+}
+
+template <int NIN, class Op>
+__global__ void __launch_bounds__(kBlock) ew_scalar_kernel(const float* __restrict__ a,
+                                                           const float* __restrict__ b,
+                                                           const float* __restrict__ c,
+                                                           float* __restrict__ out, size_t begin,
+                                                           size_t n, Op op) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = begin + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float x = a[i];
+    float y = NIN > 1 ? b[i] : 0.f;
+    float z = NIN > 2 ? c[i] : 0.f;
+    out[i] = op(x, y, z);
+  }
+}
+
+// One entry for every elementwise op: vector body + scalar tail (or all-scalar when a pointer is
+// not 16-byte aligned, e.g. a sliced view).
+template <int NIN, class Op>
+int launch_ew(const float* a, const float* b, const float* c, float* out, size_t n, Op op, cudaStream_t s) {
+  if (n == 0) return MNV_OK;
+  if (!a || !out || (NIN > 1 && !b) || (NIN > 2 && !c)) return MNV_EINVAL;
+  bool vec = aligned16(a) && aligned16(out) && (NIN < 2 || aligned16(b)) && (NIN < 3 || aligned16(c));
+  size_t n4 = vec ? n / 4 : 0;
+  if (n4) {
+    int grid = stream_grid((n4 + kUnroll - 1) / kUnroll);
+    ew_vec4_kernel<NIN, Op><<<grid, kBlock, 0, s>>>(reinterpret_cast<const float4*>(a),
+                                                     reinterpret_cast<const float4*>(b),
+                                                     reinterpret_cast<const float4*>(c),
+                                                     reinterpret_cast<float4*>(out), n4, op);
+    int rc = finish_launch();
+    if (rc) return rc;
+  }
+  if (n4 * 4 < n) {
+    size_t rest = n - n4 * 4;
+    ew_scalar_kernel<NIN, Op><<<stream_grid(rest), kBlock, 0, s>>>(a, b, c, out, n4 * 4, n, op);
+    return finish_launch();
+  }
+  return MNV_OK;
+}
+
+// ---- functors (x, y, z) -> result; unused operands are ignored ------------------------------
+struct AddOp { __device__ float operator()(float x, float y, float) const { return __fadd_rn(x, y); } };
+struct SubOp { __device__ float operator()(float x, float y, float) const { return __fsub_rn(x, y); } };
+struct MulOp { __device__ float operator()(float x, float y, float) const { return __fmul_rn(x, y); } };
+struct DivOp { __device__ float operator()(float x, float y, float) const { return __fdiv_rn(x, y); } };
+struct ConstAddOp { float v; __device__ float operator()(float x, float, float) const { return __fadd_rn(x, v); } };
+struct LeftConstSubOp { float v; __device__ float operator()(float x, float, float) const { return __fsub_rn(v, x); } };
+struct LeftConstDivOp { float v; __device__ float operator()(float x, float, float) const { return __fdiv_rn(v, x); } };
+struct ScaleOp { float v; __device__ float operator()(float x, float, float) const { return __fmul_rn(x, v); } };
+struct ConstDivOp { float v; __device__ float operator()(float x, float, float) const { return __fdiv_rn(x, v); } };
+struct ExpOp { __device__ float operator()(float x, float, float) const { return expf(x); } };
+struct LnOp { __device__ float operator()(float x, float, float) const { return logf(x); } };
+struct NegOp { __device__ float operator()(float x, float, float) const { return -x; } };
+struct CopyOp { __device__ float operator()(float x, float, float) const { return x; } };
+// basic.cpp:416 -- float expf, then the reciprocal in double, rounded once to float
+struct SigmoidOp {
+  __device__ float operator()(float x, float, float) const {
+    return static_cast<float>(1.0 / (1.0 + static_cast<double>(expf(-x))));
+  }
+};
+struct ReluOp { __device__ float operator()(float x, float, float) const { return x > 0.f ? x : 0.f; } };  // basic.cpp:430
+struct TanhOp { __device__ float operator()(float x, float, float) const { return tanhf(x); } };
+// backward functors take (dy, y, x)
+struct SigmoidBackOp {
+  __device__ float operator()(float dy, float y, float) const {
+    return __fmul_rn(__fmul_rn(dy, y), __fsub_rn(1.0f, y));
+  }
+};
+struct ReluBackOp { __device__ float operator()(float dy, float x, float) const { return x > 0.f ? dy : 0.f; } };
+struct TanhBackOp {
+  __device__ float operator()(float dy, float y, float) const {
+    return __fmul_rn(dy, __fsub_rn(1.0f, __fmul_rn(y, y)));
+  }
+};
+
+// ---- fill -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) fill_kernel(float* __restrict__ dst, size_t n, float v) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // dst is 4-byte aligned at least; peel to a 16-byte boundary, then 128-bit stores
+  size_t head = ((16 - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) / 4;
+  if (head > n) head = n;
+  if (tid < head) dst[tid] = v;
+  float4* d4 = reinterpret_cast<float4*>(dst + head);
+  size_t n4 = (n - head) / 4;
+  float4 vv = make_float4(v, v, v, v);
+  for (size_t i = tid; i < n4; i += stride) d4[i] = vv;
+  size_t done = head + n4 * 4;
+  if (tid < n - done) dst[done + tid] = v;
+}
+
+// ---- Philox4x32-10 (same stream layout as oracle/mnv_oracle.c:orc_philox4x32) -------------------
+__device__ __forceinline__ uint4 philox4x32(uint32_t seed, uint64_t block, uint32_t stream_id) {
+  uint32_t c0 = static_cast<uint32_t>(block), c1 = static_cast<uint32_t>(block >> 32), c2 = stream_id, c3 = 0u;
+  uint32_t k0 = seed, k1 = 0x0B200B20u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ void store4_guarded(float* dst, size_t blk, size_t n, const float v[4]) {
+  size_t i = blk * 4;
+  if (i + 4 <= n && (reinterpret_cast<uintptr_t>(dst + i) & 15u) == 0) {
+    *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    for (int j = 0; j < 4 && i + j < n; ++j) dst[i + j] = v[j];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) bernoulli_kernel(float* __restrict__ dst, size_t n, uint32_t seed, float p) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t nblk = (n + 3) / 4;
+  for (size_t blk = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; blk < nblk; blk += stride) {
+    uint4 r = philox4x32(seed, blk, 1u);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = __fmul_rn(static_cast<float>(w[j] >> 8), 1.0f / 16777216.0f);
+      v[j] = u < p ? 1.0f : 0.0f;
+    }
+    store4_guarded(dst, blk, n, v);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) randn_kernel(float* __restrict__ dst, size_t n, uint32_t seed, float mean, float sd) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t nblk = (n + 3) / 4;
+  for (size_t blk = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; blk < nblk; blk += stride) {
+    uint4 r = philox4x32(seed, blk, 2u);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float v[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float u1 = __fmul_rn(static_cast<float>((w[2 * h] >> 8) + 1u), 1.0f / 16777216.0f);
+      float u2 = __fmul_rn(static_cast<float>(w[2 * h + 1] >> 8), 1.0f / 16777216.0f);
+      float rad = sqrtf(__fmul_rn(-2.0f, logf(u1)));
+      float ang = __fmul_rn(6.283185307179586f, u2);
+      v[2 * h] = __fadd_rn(mean, __fmul_rn(sd, __fmul_rn(rad, cosf(ang))));
+      v[2 * h + 1] = __fadd_rn(mean, __fmul_rn(sd, __fmul_rn(rad, sinf(ang))));
+    }
+    store4_guarded(dst, blk, n, v);
+  }
+}
+
+// ---- fused momentum SGD (in place): 3 reads + 2 writes = 20 B/param ------------------------------
+__global__ void __launch_bounds__(kBlock) sgd_kernel(float* __restrict__ w, float* __restrict__ delta,
+                                                     const float* __restrict__ grad, size_t n, float mom,
+                                                     float lrb, float lrwd, int vec) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto upd = [&](float& wv, float& dv, float g) {
+    float d = __fsub_rn(__fsub_rn(__fmul_rn(mom, dv), __fmul_rn(lrb, g)), __fmul_rn(lrwd, wv));
+    dv = d;
+    wv = __fadd_rn(wv, d);
+  };
+  size_t n4 = vec ? n / 4 : 0;
+  float4* w4 = reinterpret_cast<float4*>(w);
+  float4* d4 = reinterpret_cast<float4*>(delta);
+  const float4* g4 = reinterpret_cast<const float4*>(grad);
+  for (size_t i = tid; i < n4; i += stride) {
+    float4 wv = w4[i], dv = d4[i], gv = __ldg(g4 + i);
+    upd(wv.x, dv.x, gv.x); upd(wv.y, dv.y, gv.y); upd(wv.z, dv.z, gv.z); upd(wv.w, dv.w, gv.w);
+    w4[i] = wv; d4[i] = dv;
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += stride) {
+    float wv = w[i], dv = delta[i];
+    upd(wv, dv, grad[i]);
+    w[i] = wv; delta[i] = dv;
+  }
+}
+
+}  // namespace mnv
+
+using namespace mnv;
+
+extern "C" {
+
+int mnv_add(const float* a, const float* b, float* c, size_t n, mnv_stream_t s) {
+  return launch_ew<2>(a, b, nullptr, c, n, AddOp{}, as_stream(s));
+}
+int mnv_sub(const float* a, const float* b, float* c, size_t n, mnv_stream_t s) {
+  return launch_ew<2>(a, b, nullptr, c, n, SubOp{}, as_stream(s));
+}
+int mnv_dot_mult(const float* a, const float* b, float* c, size_t n, mnv_stream_t s) {
+  return launch_ew<2>(a, b, nullptr, c, n, MulOp{}, as_stream(s));
+}
+int mnv_dot_div(const float* a, const float* b, float* c, size_t n, mnv_stream_t s) {
+  return launch_ew<2>(a, b, nullptr, c, n, DivOp{}, as_stream(s));
+}
+int mnv_const_add(const float* in, float* out, float v, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, ConstAddOp{v}, as_stream(s));
+}
+int mnv_left_const_sub(const float* in, float* out, float v, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, LeftConstSubOp{v}, as_stream(s));
+}
+int mnv_left_const_div(const float* in, float* out, float v, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, LeftConstDivOp{v}, as_stream(s));
+}
+int mnv_scale(const float* in, float* out, size_t n, float v, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, ScaleOp{v}, as_stream(s));
+}
+int mnv_const_div(const float* in, float* out, float v, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, ConstDivOp{v}, as_stream(s));
+}
+int mnv_elewise_exp(const float* in, float* out, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, ExpOp{}, as_stream(s));
+}
+int mnv_elewise_ln(const float* in, float* out, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, LnOp{}, as_stream(s));
+}
+int mnv_elewise_negative(const float* in, float* out, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, NegOp{}, as_stream(s));
+}
+int mnv_copy(const float* src, float* dst, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(src, nullptr, nullptr, dst, n, CopyOp{}, as_stream(s));
+}
+int mnv_reshape(const float* in, float* out, size_t bytes, mnv_stream_t s) {
+  if (bytes % sizeof(float)) return MNV_EINVAL;
+  return launch_ew<1>(in, nullptr, nullptr, out, bytes / sizeof(float), CopyOp{}, as_stream(s));
+}
+
+static inline size_t prod4(int a, int b, int c, int d) {
+  return static_cast<size_t>(a) * b * c * static_cast<size_t>(d);
+}
+#define MNV_DIMS_OK(a, b, c, d) ((a) >= 0 && (b) >= 0 && (c) >= 0 && (d) >= 0)
+
+int mnv_sigmoid_forward(const float* x, float* y, int N, int C, int H, int W, mnv_stream_t s) {
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<1>(x, nullptr, nullptr, y, prod4(N, C, H, W), SigmoidOp{}, as_stream(s));
+}
+int mnv_relu_forward(const float* x, float* y, int N, int C, int H, int W, mnv_stream_t s) {
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<1>(x, nullptr, nullptr, y, prod4(N, C, H, W), ReluOp{}, as_stream(s));
+}
+int mnv_tanh_forward(const float* x, float* y, int N, int C, int H, int W, mnv_stream_t s) {
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<1>(x, nullptr, nullptr, y, prod4(N, C, H, W), TanhOp{}, as_stream(s));
+}
+// Only the operands the formula needs are read (12 B/elem): sigmoid/tanh use (dy, y), relu (dy, x).
+int mnv_sigmoid_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
+                         int W, mnv_stream_t s) {
+  (void)x;
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<2>(dy, y, nullptr, dx, prod4(N, C, H, W), SigmoidBackOp{}, as_stream(s));
+}
+int mnv_relu_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
+                      int W, mnv_stream_t s) {
+  (void)y;
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<2>(dy, x, nullptr, dx, prod4(N, C, H, W), ReluBackOp{}, as_stream(s));
+}
+int mnv_tanh_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
+                      int W, mnv_stream_t s) {
+  (void)x;
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<2>(dy, y, nullptr, dx, prod4(N, C, H, W), TanhBackOp{}, as_stream(s));
+}
+
+int mnv_fill(float* dst, size_t n, float v, mnv_stream_t s) {
+  if (n == 0) return MNV_OK;
+  MNV_CHECK_PTR(dst);
+  fill_kernel<<<stream_grid(n / 4 + 8), kBlock, 0, as_stream(s)>>>(dst, n, v);
+  return finish_launch();
+}
+int mnv_rand_bernoulli(float* dst, size_t n, unsigned int seed, float p, mnv_stream_t s) {
+  if (n == 0) return MNV_OK;
+  MNV_CHECK_PTR(dst);
+  bernoulli_kernel<<<stream_grid((n + 3) / 4), kBlock, 0, as_stream(s)>>>(dst, n, seed, p);
+  return finish_launch();
+}
+int mnv_randn(float* dst, size_t n, unsigned int seed, float mean, float var, mnv_stream_t s) {
+  if (n == 0) return MNV_OK;
+  MNV_CHECK_PTR(dst);
+  randn_kernel<<<stream_grid((n + 3) / 4), kBlock, 0, as_stream(s)>>>(dst, n, seed, mean, var);
+  return finish_launch();
+}
+int mnv_sgd_momentum_update(float* w, float* delta, const float* grad, size_t n, float momentum,
+                            float lr_over_batch, float lr_times_wd, mnv_stream_t s) {
+  if (n == 0) return MNV_OK;
+  if (!w || !delta || !grad) return MNV_EINVAL;
+  int vec = aligned16(w) && aligned16(delta) && aligned16(grad);
+  sgd_kernel<<<stream_grid(n / 4 + 1), kBlock, 0, as_stream(s)>>>(w, delta, grad, n, momentum,
+                                                                    lr_over_batch, lr_times_wd, vec);
+  return finish_launch();
+}
+
+int mnv_abi_version(void) { return 1; }
+const char* mnv_build_info(void) {
+  return "minerva_b200 kernels: sm_100a, nvcc " __VERSION__ ", built " __DATE__;
+}
+size_t mnv_workspace_bytes_hint(void) { return static_cast<size_t>(256) << 20; }
+uint64_t mnv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,721 @@
+// gemm_conv.cu -- a18 MatMult and a14-a16 Convolution forward / backward-data / backward-filter as
+// ONE warp-specialised tcgen05 kernel: TF32 operands, fp32 accumulation in TMEM.
+//
+// Replaces cublasSgemm (L1, minerva/op/impl/cuda/cuda_perform.cu:66-70) and the cuDNN-v2 convolution
+// calls L7-L9 (cuda_perform.cu:227-318: per-call descriptor churn, algorithm search, cudaMalloc /
+// cudaFree of the workspace, a separate bias pass and a stream sync).  Here every op is an
+// enqueue-only launch; bias is fused into the epilogue.
+//
+// Formulation.  Every op is D[M x N] = sum_k A[m,k] * B[n,k] with both operands staged K-major in
+// shared memory (UMMA canonical layout, 128-byte swizzle), D accumulated in TMEM (128 lanes x bn
+// fp32 columns, double buffered) and written back so that the lane (= row m) index runs along the
+// contiguous axis of the output:
+//   MatMult        m = row of C,            n = column of C,  k = inner;   A col-major (m-contig.)
+//   ConvForward    m = (img, oh, ow),       n = co,           k = (ci,r,s) A = im2col gather of x
+//   ConvBackwardData   m = (img, h, w),     n = ci,           k = (co,r,s) A = gather of top_diff
+//   ConvBackwardFilter m = (ci,r,s),        n = co,           k = (img,oh,ow)  A = gather of x
+// (r,s) index the filter as stored; the 180-degree rotation of CUDNN_CONVOLUTION is the
+// identity kh = fh-1-r, kw = fw-1-s applied inside the gathers.
+//
+// NCHW has no TMA-friendly im2col, so operands are gathered by producer warps with coalesced
+// LDG (lanes run along the contiguous axis of the source), rounded to TF32 (cvt.rna), and stored
+// with conflict-free 128-bit STS into the swizzled tile; fence.proxy.async + mbarrier hands the
+// stage to the single MMA-issuing thread.  Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-3  epilogue: tcgen05.ld 32x32b -> +bias -> coalesced STG (lane = row m)
+//   warp  4    TMEM alloc/dealloc; lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 + tcgen05.commit
+//   warp  5    idle (keeps epilogue warps at warp_id % 4 == TMEM lane quadrant)
+//   warps 6-13 producers (256 threads): A tile 128x32, B tile bn x 32 per stage, 4-stage ring
+// Split-K (needs the caller's workspace) keeps all 148 SMs busy when M*N has few tiles (FC layers,
+// backward-filter); partials are folded in split order by a second kernel => deterministic.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string>
+#include "common.cuh"
+
+namespace mnv {
+
+// ------------------------------------------------------------------------------------------------
+// problem description shared by the tcgen05 kernel, the SIMT checker and the split-K reducer
+// ------------------------------------------------------------------------------------------------
+enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD = 3 };
+enum : int { B_KMAJOR = 0, B_DY_WGRAD = 1 };
+
+struct GemmParams {
+  const float* a;
+  const float* b;
+  const float* bias;   // per-n, may be null
+  float* out;
+  float* partial;      // split-K partials [split][n][m], null when splits == 1
+  int M, N, K;
+  int lda;             // A_COLMAJOR leading dimension
+  int ldb, b_vec;      // B_KMAJOR row pitch (floats); 1 if rows are 16B-aligned and K % 4 == 0
+  // convolution geometry (bottom H x W, top Ho x Wo)
+  int Ci, Co, H, W, Ho, Wo, fh, fw, ph, pw, sv, sh;
+  // epilogue addressing: out[(m / P) * img_stride + (m % P) + n * col_stride]
+  int P;
+  long long img_stride, col_stride;
+  // tiling
+  int bn, m_tiles, n_tiles, splits, stages_per_split, k_stages;
+};
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 32;         // floats per stage row = 128 bytes = one swizzle span
+constexpr int BN_MAX = 256;    // UMMA N limit
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 4;       // 16 KB
+constexpr int kBBytes = BN_MAX * BK * 4;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 448;
+constexpr int kProducerWarp0 = 6;
+constexpr int kProducerThreads = 256;
+constexpr int kTmemCols = 512;  // two accumulator buffers of 256 fp32 columns
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Time-bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) asm volatile("trap;");  // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout_type [61,64) with SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;                 // LBO: unused for swizzled K-major
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // SBO
+  d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
+// B=TF32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+// byte offset of 16-byte chunk `kq` of row `r` inside a swizzled tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int kq) { return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(kq ^ (r & 7)) << 4); }
+
+// ------------------------------------------------------------------------------------------------
+// operand element definitions (slow, fully decoded): used by the SIMT checker kernel and as the
+// readable statement of what the fast gathers below compute.
+// ------------------------------------------------------------------------------------------------
+template <int AM>
+__device__ __forceinline__ float a_elem(const GemmParams& p, int m, int k) {
+  if (m >= p.M || k >= p.K) return 0.f;
+  if (AM == A_COLMAJOR) return __ldg(p.a + m + static_cast<size_t>(k) * p.lda);
+  const int ff = p.fh * p.fw;
+  if (AM == A_IM2COL_FWD) {
+    int img = m / p.P, pix = m - img * p.P, oh = pix / p.Wo, ow = pix - oh * p.Wo;
+    int ci = k / ff, rs = k - ci * ff, r = rs / p.fw, s = rs - r * p.fw;
+    int ih = oh * p.sv - p.ph + (p.fh - 1 - r), iw = ow * p.sh - p.pw + (p.fw - 1 - s);
+    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return 0.f;
+    return __ldg(p.a + ((static_cast<size_t>(img) * p.Ci + ci) * p.H + ih) * p.W + iw);
+  }
+  if (AM == A_IM2COL_BWD) {
+    int img = m / p.P, pix = m - img * p.P, h = pix / p.W, w = pix - h * p.W;
+    int co = k / ff, rs = k - co * ff, r = rs / p.fw, s = rs - r * p.fw;
+    int t = h + p.ph - (p.fh - 1 - r), u = w + p.pw - (p.fw - 1 - s);
+    if (t < 0 || u < 0 || t % p.sv || u % p.sh) return 0.f;
+    int i = t / p.sv, j = u / p.sh;
+    if (i >= p.Ho || j >= p.Wo) return 0.f;
+    return __ldg(p.a + ((static_cast<size_t>(img) * p.Co + co) * p.Ho + i) * p.Wo + j);
+  }
+  {  // A_IM2COL_WGRAD: m = (ci,r,s), k = (img,oh,ow)
+    int ci = m / ff, rs = m - ci * ff, r = rs / p.fw, s = rs - r * p.fw;
+    int hw = p.Ho * p.Wo;
+    int img = k / hw, pix = k - img * hw, oh = pix / p.Wo, ow = pix - oh * p.Wo;
+    int ih = oh * p.sv - p.ph + (p.fh - 1 - r), iw = ow * p.sh - p.pw + (p.fw - 1 - s);
+    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return 0.f;
+    return __ldg(p.a + ((static_cast<size_t>(img) * p.Ci + ci) * p.H + ih) * p.W + iw);
+  }
+}
+template <int BMD>
+__device__ __forceinline__ float b_elem(const GemmParams& p, int n, int k) {
+  if (n >= p.N || k >= p.K) return 0.f;
+  if (BMD == B_KMAJOR) return __ldg(p.b + static_cast<size_t>(n) * p.ldb + k);
+  int hw = p.Ho * p.Wo;
+  int img = k / hw, pix = k - img * hw;
+  return __ldg(p.b + (static_cast<size_t>(img) * p.Co + n) * hw + pix);
+}
+__device__ __forceinline__ size_t out_index(const GemmParams& p, int m, int n) {
+  int img = m / p.P, pix = m - img * p.P;
+  return static_cast<size_t>(img) * p.img_stride + pix + static_cast<size_t>(n) * p.col_stride;
+}
+
+// SIMT checker: one thread per output, sequential fp32 k loop.  Debug / cross-check only
+// (mnv_debug_set_option("simt", 1)); never selected by default.
+template <int AM, int BMD>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmParams p) {
+  size_t total = static_cast<size_t>(p.M) * p.N;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int m = static_cast<int>(t % p.M), n = static_cast<int>(t / p.M);
+    float acc = 0.f;
+    for (int k = 0; k < p.K; ++k) acc = fmaf(a_elem<AM>(p, m, k), b_elem<BMD>(p, n, k), acc);
+    p.out[out_index(p, m, n)] = acc + (p.bias ? __ldg(p.bias + n) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast gathers.  A: thread = one tile row, 16 consecutive k per stage (lanes run along m => coalesced
+// for every mode).  B: thread = 16-byte chunk (row, kq); 8 consecutive lanes cover 128 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+struct ARow {           // per-thread, per-tile state of the A gather
+  bool valid;
+  long long base;       // element offset contribution of the row
+  uint32_t mh, mw;      // validity masks over kh / kw (im2col fwd / bwd stride-1)
+  int h0, w0;           // generic: oh*sv-ph (fwd), h+ph (bwd), kh-ph (wgrad)
+};
+
+template <int AM>
+__device__ __forceinline__ ARow a_row_setup(const GemmParams& p, int m) {
+  ARow r;
+  r.valid = m < p.M;
+  r.base = 0; r.mh = r.mw = 0; r.h0 = r.w0 = 0;
+  if (!r.valid) return r;
+  if (AM == A_COLMAJOR) {
+    r.base = m;
+  } else if (AM == A_IM2COL_FWD) {
+    int img = m / p.P, pix = m - img * p.P, oh = pix / p.Wo, ow = pix - oh * p.Wo;
+    r.h0 = oh * p.sv - p.ph; r.w0 = ow * p.sh - p.pw;
+    r.base = static_cast<long long>(img) * p.Ci * p.H * p.W + static_cast<long long>(r.h0) * p.W + r.w0;
+    for (int kh = 0; kh < p.fh; ++kh) if (r.h0 + kh >= 0 && r.h0 + kh < p.H) r.mh |= 1u << kh;
+    for (int kw = 0; kw < p.fw; ++kw) if (r.w0 + kw >= 0 && r.w0 + kw < p.W) r.mw |= 1u << kw;
+  } else if (AM == A_IM2COL_BWD) {
+    int img = m / p.P, pix = m - img * p.P, h = pix / p.W, w = pix - h * p.W;
+    r.h0 = h + p.ph; r.w0 = w + p.pw;
+    r.base = static_cast<long long>(img) * p.Co * p.Ho * p.Wo;
+    for (int kh = 0; kh < p.fh; ++kh) { int t = r.h0 - kh; if (t >= 0 && t % p.sv == 0 && t / p.sv < p.Ho) r.mh |= 1u << kh; }
+    for (int kw = 0; kw < p.fw; ++kw) { int u = r.w0 - kw; if (u >= 0 && u % p.sh == 0 && u / p.sh < p.Wo) r.mw |= 1u << kw; }
+  } else {  // WGRAD: row = (ci, r, s)
+    int ff = p.fh * p.fw;
+    int ci = m / ff, rs = m - ci * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
+    r.h0 = (p.fh - 1 - rr) - p.ph; r.w0 = (p.fw - 1 - ss) - p.pw;
+    r.base = static_cast<long long>(ci) * p.H * p.W + static_cast<long long>(r.h0) * p.W + r.w0;
+  }
+  return r;
+}
+
+// 16 consecutive k starting at k0 for this thread's row
+template <int AM>
+__device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, int k0, float (&v)[16]) {
+  if (AM == A_COLMAJOR) {
+    const float* src = p.a + r.base + static_cast<size_t>(k0) * p.lda;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (r.valid && k0 + j < p.K) ? __ldg(src + static_cast<size_t>(j) * p.lda) : 0.f;
+  } else if (AM == A_IM2COL_FWD || AM == A_IM2COL_BWD) {
+    // k = (c, rr, ss) in filter storage order; kh = fh-1-rr, kw = fw-1-ss
+    const int ff = p.fh * p.fw;
+    int c = k0 / ff, rs = k0 - c * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
+    int kh = p.fh - 1 - rr, kw = p.fw - 1 - ss;
+    if (AM == A_IM2COL_FWD) {
+      const int HW = p.H * p.W;
+      int off = c * HW + kh * p.W + kw;
+      const float* src = p.a + r.base;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
+        v[j] = ok ? __ldg(src + off) : 0.f;
+        --kw; --off;
+        if (kw < 0) { kw = p.fw - 1; off += p.fw - p.W; --kh; if (kh < 0) { kh = p.fh - 1; off += p.fh * p.W + HW; } }
+      }
+    } else {
+      const int HoWo = p.Ho * p.Wo;
+      const float* src = p.a + r.base;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
+        float val = 0.f;
+        if (ok) {
+          int i = (r.h0 - kh) / p.sv, jj = (r.w0 - kw) / p.sh;
+          val = __ldg(src + static_cast<size_t>(c) * HoWo + i * p.Wo + jj);
+        }
+        v[j] = val;
+        --kw;
+        if (kw < 0) { kw = p.fw - 1; --kh; if (kh < 0) { kh = p.fh - 1; ++c; } }
+      }
+    }
+  } else {  // WGRAD: k = (img, oh, ow)
+    const int HoWo = p.Ho * p.Wo;
+    int img = k0 / HoWo, pix = k0 - img * HoWo, oh = pix / p.Wo, ow = pix - oh * p.Wo;
+    int ohs = oh * p.sv, ows = ow * p.sh;
+    long long uoff = static_cast<long long>(img) * p.Ci * p.H * p.W + static_cast<long long>(ohs) * p.W + ows;
+    const float* src = p.a + r.base;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      bool ok = r.valid && (k0 + j < p.K) && static_cast<unsigned>(ohs + r.h0) < static_cast<unsigned>(p.H) &&
+                static_cast<unsigned>(ows + r.w0) < static_cast<unsigned>(p.W);
+      v[j] = ok ? __ldg(src + uoff) : 0.f;
+      ++ow; ows += p.sh; uoff += p.sh;
+      if (ow == p.Wo) {
+        ow = 0; uoff -= static_cast<long long>(p.Wo) * p.sh; ows = 0;
+        ++oh; ohs += p.sv; uoff += static_cast<long long>(p.sv) * p.W;
+        if (oh == p.Ho) { oh = 0; uoff -= static_cast<long long>(p.Ho) * p.sv * p.W; ohs = 0; uoff += static_cast<long long>(p.Ci) * p.H * p.W; }
+      }
+    }
+  }
+}
+
+// one 16-byte chunk: 4 consecutive k starting at k0 of row n
+template <int BMD>
+__device__ __forceinline__ float4 b_gather4(const GemmParams& p, int n, int k0) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n >= p.N || k0 >= p.K) return v;
+  if (BMD == B_KMAJOR) {
+    const float* src = p.b + static_cast<size_t>(n) * p.ldb + k0;
+    if (p.b_vec) return __ldg(reinterpret_cast<const float4*>(src));
+    v.x = __ldg(src);
+    if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+    if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+    if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+    return v;
+  }
+  const int hw = p.Ho * p.Wo;
+  int img = k0 / hw, pix = k0 - img * hw;
+  float* o = &v.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (k0 + e < p.K) o[e] = __ldg(p.b + (static_cast<size_t>(img) * p.Co + n) * hw + pix);
+    if (++pix == hw) { pix = 0; ++img; }
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+struct TileCoord { int mt, nt, split, ks_begin, ks_end; };
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int rest = tile / p.n_tiles;
+  t.mt = rest % p.m_tiles;
+  t.split = rest / p.m_tiles;
+  t.ks_begin = t.split * p.stages_per_split;
+  t.ks_end = min(p.k_stages, t.ks_begin + p.stages_per_split);
+  return t;
+}
+
+template <int AM, int BMD>
+__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: the 128B swizzle pattern is a function of address bits [7,10)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty, then the TMEM base slot
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
+  const uint32_t tfull0 = smem_u32(bars + 2 * kStages), tempty0 = smem_u32(bars + 2 * kStages + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== epilogue =====================
+    int acc_stage = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile);
+      mbar_wait(tfull0 + 8 * acc_stage, acc_phase);
+      tc_fence_after();
+      const int m = t.mt * BM + warp * 32 + lane;
+      const int n0 = t.nt * p.bn;
+      const bool row_ok = m < p.M;
+      float* dst;
+      long long cstride;
+      if (p.splits > 1) {  // partial[split][n][m]
+        dst = p.partial + static_cast<size_t>(t.split) * p.M * p.N + (row_ok ? m : 0);
+        cstride = p.M;
+      } else {
+        dst = p.out + (row_ok ? out_index(p, m, 0) : 0);
+        cstride = p.col_stride;
+      }
+      const bool add_bias = p.bias != nullptr && p.splits == 1;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc_stage * BN_MAX + c0), r);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            int n = n0 + c0 + j;
+            if (n < p.N) {
+              float val = __uint_as_float(r[j]);
+              if (add_bias) val += __ldg(p.bias + n);
+              dst[static_cast<size_t>(n) * cstride] = val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc_stage);
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the pipeline (so every lane reaches the final __syncthreads together);
+    // lane 0 alone issues tcgen05.mma / tcgen05.commit.
+    const uint32_t idesc = make_idesc(p.bn);
+    int stage = 0; uint32_t phase = 0;
+    int acc_stage = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile);
+      mbar_wait(tempty0 + 8 * acc_stage, acc_phase ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc_stage * BN_MAX);
+      for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_base + stage * kStageBytes;
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes inside the swizzle span
+            umma_tf32(tmem_d, make_sw128_desc(a_addr + kk * 32), make_sw128_desc(b_addr + kk * 32), idesc,
+                      (ks > t.ks_begin || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
+          if (ks + 1 == t.ks_end) umma_commit(tfull0 + 8 * acc_stage);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= kProducerWarp0) {
+    // ===================== producers =====================
+    const int pt = threadIdx.x - kProducerWarp0 * 32;   // 0..255
+    const int a_row = pt & 127, a_half = pt >> 7;       // 16 consecutive k: [a_half*16, +16)
+    const int b_kq = pt & 7, b_row0 = pt >> 3;          // rows b_row0 + 32*i
+    const int b_iters = (p.bn + 31) / 32;               // <= 8
+    int stage = 0; uint32_t phase = 0;
+    float va[16];
+    float4 vb[8];
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile);
+      const ARow arow = a_row_setup<AM>(p, t.mt * BM + a_row);
+      const int n_base = t.nt * p.bn;
+      auto load = [&](int ks) {
+        a_gather16<AM>(p, arow, ks * BK + a_half * 16, va);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < b_iters) {
+            int row = b_row0 + 32 * i;
+            vb[i] = row < p.bn ? b_gather4<BMD>(p, n_base + row, ks * BK + b_kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      };
+      load(t.ks_begin);
+      for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        uint8_t* a_tile = smem + stage * kStageBytes;
+        uint8_t* b_tile = a_tile + kABytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 w = make_float4(to_tf32(va[4 * q]), to_tf32(va[4 * q + 1]), to_tf32(va[4 * q + 2]), to_tf32(va[4 * q + 3]));
+          *reinterpret_cast<float4*>(a_tile + sw128_off(a_row, a_half * 4 + q)) = w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < b_iters) {
+            int row = b_row0 + 32 * i;
+            if (row < p.bn) {
+              float4 w = make_float4(to_tf32(vb[i].x), to_tf32(vb[i].y), to_tf32(vb[i].z), to_tf32(vb[i].w));
+              *reinterpret_cast<float4*>(b_tile + sw128_off(row, b_kq)) = w;
+            }
+          }
+        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (ks + 1 < t.ks_end) load(ks + 1);  // next stage's loads fly while the ring drains
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// split-K: out[index(m,n)] = bias[n] + sum_s partial[s][n][m], splits folded in order
+__global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams p) {
+  size_t mn = static_cast<size_t>(p.M) * p.N;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < mn;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int m = static_cast<int>(t % p.M), n = static_cast<int>(t / p.M);
+    float acc = __ldg(p.partial + t);
+    for (int s = 1; s < p.splits; ++s) acc += __ldg(p.partial + static_cast<size_t>(s) * mn + t);
+    if (p.bias) acc += __ldg(p.bias + n);
+    p.out[out_index(p, m, n)] = acc;
+  }
+}
+
+// w[co][ci][r][s] -> wt[ci][co][r][s]: backward-data reads the filter as B[n=ci][k=(co,r,s)]
+__global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci, int ff) {
+  size_t total = static_cast<size_t>(Co) * Ci * ff;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int rs = static_cast<int>(t % ff);
+    size_t rest = t / ff;
+    int co = static_cast<int>(rest % Co), ci = static_cast<int>(rest / Co);
+    wt[t] = __ldg(w + (static_cast<size_t>(co) * Ci + ci) * ff + rs);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
+static std::atomic<int> g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
+
+static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials) {
+  p.m_tiles = (p.M + BM - 1) / BM;
+  int n_tiles = (p.N + BN_MAX - 1) / BN_MAX;
+  int bn = (p.N + n_tiles - 1) / n_tiles;
+  bn = (bn + 15) / 16 * 16;
+  if (bn < 16) bn = 16;
+  p.bn = bn;
+  p.n_tiles = (p.N + bn - 1) / bn;
+  p.k_stages = (p.K + BK - 1) / BK;
+  if (p.k_stages < 1) p.k_stages = 1;
+  long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  int splits = 1;
+  if (tiles * 4 < kNumSMs * 3) {  // fewer than 3/4 of a wave: split K
+    splits = static_cast<int>(kNumSMs / tiles);
+    int max_by_k = p.k_stages / 4;  // at least 4 stages per split
+    if (splits > max_by_k) splits = max_by_k;
+    size_t per_split = static_cast<size_t>(p.M) * p.N * sizeof(float);
+    size_t max_by_ws = per_split ? ws_bytes_for_partials / per_split : 0;
+    if (static_cast<size_t>(splits) > max_by_ws) splits = static_cast<int>(max_by_ws);
+    int clamp = g_opt_max_splits.load();
+    if (clamp > 0 && splits > clamp) splits = clamp;
+    if (splits < 1) splits = 1;
+  }
+  p.stages_per_split = (p.k_stages + splits - 1) / splits;
+  p.splits = (p.k_stages + p.stages_per_split - 1) / p.stages_per_split;  // no empty split
+}
+
+template <int AM, int BMD>
+static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (g_opt_simt.load()) {
+    p.splits = 1; p.partial = nullptr;
+    simt_gemm_kernel<AM, BMD><<<stream_grid(static_cast<size_t>(p.M) * p.N), 256, 0, s>>>(p);
+    return finish_launch();
+  }
+  plan_tiles(p, ws ? ws_bytes : 0);
+  p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
+  // opt in to >48 KB dynamic shared memory once per (device, instantiation)
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+  int grid = static_cast<int>(total < kNumSMs ? total : kNumSMs);
+  umma_gemm_kernel<AM, BMD><<<grid, kThreads, kSmemBytes, s>>>(p);
+  int rc = finish_launch();
+  if (rc || p.splits == 1) return rc;
+  splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
+  return finish_launch();
+}
+
+static void zero_conv(GemmParams& p) {
+  p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
+  p.ph = p.pw = 0; p.sv = p.sh = 1;
+  p.lda = p.ldb = 0; p.b_vec = 0;
+  p.bias = nullptr; p.partial = nullptr;
+}
+
+static int check_conv(int N, int Ci, int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw) {
+  if (N < 0 || Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || ph < 0 || pw < 0 || sv <= 0 || sh <= 0 || fh <= 0 || fw <= 0)
+    return MNV_EINVAL;
+  if (fh > 32 || fw > 32) return MNV_EUNSUPPORTED;  // validity masks are 32-bit
+  if (H + 2 * ph < fh || W + 2 * pw < fw) return MNV_EINVAL;
+  return MNV_OK;
+}
+static bool fits_int(long long v) { return v > 0 && v < 0x7fffffffLL; }
+
+}  // namespace mnv
+
+using namespace mnv;
+
+extern "C" {
+
+// Debug / tuning hook (not part of the reference surface): "simt" -> 1 routes GEMM/conv through the
+// SIMT checker kernel; "max_splits" clamps split-K.  Returns the previous value, or -1 for a bad key.
+__attribute__((visibility("default"))) int mnv_debug_set_option(const char* key, int value) {
+  if (!key) return -1;
+  std::string k(key);
+  if (k == "simt") return g_opt_simt.exchange(value);
+  if (k == "max_splits") return g_opt_max_splits.exchange(value);
+  return -1;
+}
+
+int mnv_matmult(const float* a, const float* b, float* c, int m, int n, int k, void* workspace,
+                size_t workspace_bytes, mnv_stream_t stream) {
+  if (m < 0 || n < 0 || k < 0) return MNV_EINVAL;
+  if (m == 0 || n == 0) return MNV_OK;
+  if (!a || !b || !c) return MNV_EINVAL;
+  if (k == 0) return mnv_fill(c, static_cast<size_t>(m) * n, 0.f, stream);
+  GemmParams p;
+  zero_conv(p);
+  p.a = a; p.b = b; p.out = c;
+  p.M = m; p.N = n; p.K = k;
+  p.lda = m; p.ldb = k;
+  p.b_vec = (k % 4 == 0) && aligned16(b);
+  p.P = m; p.img_stride = 0; p.col_stride = m;
+  return launch_gemm<A_COLMAJOR, B_KMAJOR>(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+int mnv_conv_forward(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
+                     int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                     size_t workspace_bytes, mnv_stream_t stream) {
+  int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
+  if (rc) return rc;
+  if (N == 0) return MNV_OK;
+  if (!bottom || !filter || !bias || !top) return MNV_EINVAL;
+  GemmParams p;
+  zero_conv(p);
+  p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
+  p.Ho = (H + 2 * ph - fh) / sv + 1; p.Wo = (W + 2 * pw - fw) / sh + 1;
+  long long M = static_cast<long long>(N) * p.Ho * p.Wo, K = static_cast<long long>(Ci) * fh * fw;
+  if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Ci * H * W)) return MNV_EUNSUPPORTED;
+  p.a = bottom; p.b = filter; p.bias = bias; p.out = top;
+  p.M = static_cast<int>(M); p.N = Co; p.K = static_cast<int>(K);
+  p.ldb = p.K; p.b_vec = (p.K % 4 == 0) && aligned16(filter);
+  p.P = p.Ho * p.Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
+  return launch_gemm<A_IM2COL_FWD, B_KMAJOR>(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bottom_diff, int N, int Ci, int Co,
+                           int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                           size_t workspace_bytes, mnv_stream_t stream) {
+  int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
+  if (rc) return rc;
+  if (N == 0) return MNV_OK;
+  if (!top_diff || !filter || !bottom_diff) return MNV_EINVAL;
+  // the filter is re-laid out as [ci][(co,r,s)] in the workspace (a few MB at most, once per call)
+  size_t wt_bytes = (static_cast<size_t>(Co) * Ci * fh * fw * sizeof(float) + 255) / 256 * 256;
+  if (!workspace || workspace_bytes < wt_bytes) return MNV_EWORKSPACE;
+  float* wt = static_cast<float*>(workspace);
+  filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(filter, wt, Co, Ci, fh * fw);
+  rc = finish_launch();
+  if (rc) return rc;
+  GemmParams p;
+  zero_conv(p);
+  p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
+  p.Ho = (H + 2 * ph - fh) / sv + 1; p.Wo = (W + 2 * pw - fw) / sh + 1;
+  long long M = static_cast<long long>(N) * H * W, K = static_cast<long long>(Co) * fh * fw;
+  if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Co * p.Ho * p.Wo)) return MNV_EUNSUPPORTED;
+  p.a = top_diff; p.b = wt; p.out = bottom_diff;
+  p.M = static_cast<int>(M); p.N = Ci; p.K = static_cast<int>(K);
+  p.ldb = p.K; p.b_vec = (p.K % 4 == 0);
+  p.P = H * W; p.img_stride = static_cast<long long>(Ci) * p.P; p.col_stride = p.P;
+  return launch_gemm<A_IM2COL_BWD, B_KMAJOR>(p, static_cast<uint8_t*>(workspace) + wt_bytes, workspace_bytes - wt_bytes,
+                                             as_stream(stream));
+}
+
+int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
+                             int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                             size_t workspace_bytes, mnv_stream_t stream) {
+  int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
+  if (rc) return rc;
+  if (!bottom || !top_diff || !filter_diff) return MNV_EINVAL;
+  if (N == 0) return mnv_fill(filter_diff, static_cast<size_t>(Co) * Ci * fh * fw, 0.f, stream);
+  GemmParams p;
+  zero_conv(p);
+  p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
+  p.Ho = (H + 2 * ph - fh) / sv + 1; p.Wo = (W + 2 * pw - fw) / sh + 1;
+  long long M = static_cast<long long>(Ci) * fh * fw, K = static_cast<long long>(N) * p.Ho * p.Wo;
+  if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Ci * H * W)) return MNV_EUNSUPPORTED;
+  p.a = bottom; p.b = top_diff; p.out = filter_diff;
+  p.M = static_cast<int>(M); p.N = Co; p.K = static_cast<int>(K);
+  p.P = p.M; p.img_stride = 0; p.col_stride = p.M;  // filter_diff[co][(ci,r,s)]
+  return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+}  // extern "C"
