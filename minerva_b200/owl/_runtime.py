@@ -1,0 +1,81 @@
+"""Device layer of the owl binding: the role of minerva/device (GpuDevice streams + pooled memory,
+minerva/device/device.cpp:129-222) with one stream and one kernel workspace per device."""
+import torch
+
+from .. import _lib
+
+CPU_DEVICE = -1
+
+
+class _Gpu:
+    def __init__(self, index):
+        self.index = index
+        self.device = torch.device("cuda", index)
+        with torch.cuda.device(index):
+            self.stream = torch.cuda.Stream(device=index)
+            self.workspace = torch.empty(_lib.load().mnv_workspace_bytes_hint(), dtype=torch.uint8, device=self.device)
+        self.stream_ptr = self.stream.cuda_stream
+        self.ws_ptr = self.workspace.data_ptr()
+        self.ws_bytes = self.workspace.numel()
+
+
+_devices = []      # id -> _Gpu or CPU_DEVICE
+_current = None
+_seed = [0x5EED, 0]
+
+
+def has_cuda():
+    return int(torch.cuda.is_available())
+
+
+def get_gpu_device_count():
+    return torch.cuda.device_count()
+
+
+def create_cpu_device():
+    _devices.append(CPU_DEVICE)
+    return len(_devices) - 1
+
+
+def create_gpu_device(which):
+    if not torch.cuda.is_available():
+        raise _lib.MnvError("create_gpu_device(%d): no CUDA device; this build has no CPU path" % which)
+    _lib.load()
+    _devices.append(_Gpu(which))
+    dev_id = len(_devices) - 1
+    if _current is None:
+        set_device(dev_id)
+    return dev_id
+
+
+def set_device(dev):
+    global _current
+    d = _devices[dev]
+    _current = d
+    if d is not CPU_DEVICE:
+        torch.cuda.set_device(d.index)
+        torch.cuda.set_stream(d.stream)
+
+
+def current_device():
+    if _current is None:
+        raise _lib.MnvError("no device: call owl.create_gpu_device() first")
+    if _current is CPU_DEVICE:
+        raise _lib.MnvError("the CPU (basic) device is not provided by this build: the GPU path has no CPU fallback")
+    return _current
+
+
+def wait_for_all():
+    for d in _devices:
+        if d is not CPU_DEVICE:
+            d.stream.synchronize()
+
+
+def set_seed(seed):
+    _seed[0] = int(seed) & 0xFFFFFFFF
+    _seed[1] = 0
+
+
+def next_seed():
+    _seed[1] += 1
+    return (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF

@@ -1,0 +1,53 @@
+"""owl.conv -- convolution, pooling, LRN and softmax wrappers (reference: owl/owl/conv.py:13-182)."""
+from .narray import NArray, ConvInfo, PoolingInfo, pooling_algo, softmax_algo
+
+soft_op = softmax_algo
+pool_op = pooling_algo
+
+
+def softmax(x, op=soft_op.instance):
+    """owl/owl/conv.py:13-33: non-4D inputs are padded to {d0,1,1,N} first."""
+    if len(x.shape) == 4:
+        return NArray.softmax_forward(x, op)
+    ori_shape = list(x.shape)
+    soft_shape = x.shape[0:-1] + [1 for _ in range(4 - len(ori_shape))] + [x.shape[-1]]
+    return NArray.softmax_forward(x.reshape(soft_shape), op).reshape(ori_shape)
+
+
+class Lrner:
+    def __init__(self, local_size, alpha, beta):
+        self.local_size, self.alpha, self.beta = local_size, alpha, beta
+
+    def ff(self, x, scale):
+        return NArray.lrn_forward(x, scale, self.local_size, self.alpha, self.beta)
+
+    def bp(self, bottom_data, top_data, scale, top_diff):
+        return NArray.lrn_backward(bottom_data, top_data, scale, top_diff, self.local_size, self.alpha, self.beta)
+
+
+class Convolver:
+    def __init__(self, pad_h, pad_w, stride_v, stride_h):
+        self.param = ConvInfo(pad_h, pad_w, stride_v, stride_h)
+
+    def ff(self, x, w, b):
+        return NArray.conv_forward(x, w, b, self.param)
+
+    def bp(self, y, x, w):
+        return NArray.conv_backward_data(y, x, w, self.param)
+
+    def weight_grad(self, y, x, w):
+        return NArray.conv_backward_filter(y, x, w, self.param)
+
+    def bias_grad(self, y):
+        return NArray.conv_backward_bias(y)
+
+
+class Pooler:
+    def __init__(self, h, w, stride_v, stride_h, pad_h=0, pad_w=0, op=pool_op.max):
+        self.param = PoolingInfo(op, h, w, stride_v, stride_h, pad_h, pad_w)
+
+    def ff(self, x):
+        return NArray.pooling_forward(x, self.param)
+
+    def bp(self, y, ff_y, ff_x):
+        return NArray.pooling_backward(y, ff_y, ff_x, self.param)

@@ -1,0 +1,490 @@
+"""owl.NArray -- same operators and static methods as the reference binding
+(owl/owl/libowl.pyx:51-444 over minerva/narray/*.cpp); each maps to one C-ABI call."""
+import numpy as np
+import torch
+
+from .. import _lib
+from . import _runtime as _rt
+
+
+def _prod(shape):
+    p = 1
+    for s in shape:
+        p *= int(s)
+    return p
+
+
+class ConvInfo:
+    """minerva/narray/convolution_info.h:5-16"""
+    __slots__ = ("pad_height", "pad_width", "stride_vertical", "stride_horizontal")
+
+    def __init__(self, ph=0, pw=0, sv=1, sh=1):
+        self.pad_height, self.pad_width, self.stride_vertical, self.stride_horizontal = ph, pw, sv, sh
+
+
+class _Algo:
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def is_same(self, rhs):
+        return self.value == rhs.value
+
+    def __repr__(self):
+        return self.name
+
+
+class _Enum:
+    def __init__(self, **kw):
+        self._items = {k: _Algo(k, v) for k, v in kw.items()}
+        self.__dict__.update(self._items)
+
+    def find(self, a):
+        for v in self._items.values():
+            if v.is_same(a):
+                return v
+        raise TypeError("invalid algorithm")
+
+
+pooling_algo = _Enum(max=0, average=1)
+pooling_algo.avg = pooling_algo.average
+softmax_algo = _Enum(instance=0, channel=1)
+activation_algo = _Enum(sigmoid=0, relu=1, tanh=2)
+
+
+class PoolingInfo:
+    """minerva/narray/convolution_info.h:18-46"""
+    __slots__ = ("algorithm", "height", "width", "stride_vertical", "stride_horizontal", "pad_height", "pad_width")
+
+    def __init__(self, algorithm=None, h=0, w=0, sv=1, sh=1, ph=0, pw=0):
+        self.algorithm = algorithm or pooling_algo.max
+        self.height, self.width, self.stride_vertical, self.stride_horizontal = h, w, sv, sh
+        self.pad_height, self.pad_width = ph, pw
+
+
+def _check(cond, msg):
+    if not cond:
+        raise _lib.MnvError(msg)   # the reference CHECK-fails (dmlc::Error)
+
+
+class NArray:
+    __slots__ = ("_t", "_shape", "_dev", "__weakref__")
+
+    def __init__(self, tensor, shape, dev):
+        self._t, self._shape, self._dev = tensor, [int(s) for s in shape], dev
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return list(self._shape)
+
+    @property
+    def size(self):
+        return _prod(self._shape)
+
+    @staticmethod
+    def _new(shape, dev=None):
+        dev = dev or _rt.current_device()
+        return NArray(torch.empty(max(_prod(shape), 0), dtype=torch.float32, device=dev.device), shape, dev)
+
+    def _on(self, dev):
+        """Pull a remote input onto `dev` (the reference's DoCopyRemoteData, device.cpp:75-91,209-212)."""
+        if self._dev is dev:
+            return self._t
+        return self._t.to(dev.device, non_blocking=True)
+
+    @staticmethod
+    def _call(name, dev, *args):
+        rc = getattr(_lib.load(), name)(*args, dev.stream_ptr)
+        if rc:
+            _lib.check(rc, name)
+
+    def wait_for_eval(self):
+        self._dev.stream.synchronize()
+
+    def start_eval(self):
+        pass
+
+    # ---- elementwise arithmetic (narray_elewise.cpp:17-158) ------------------------------------
+    def _arith(self, rhs, fn, norm):
+        dev = _rt.current_device()
+        if self._shape == rhs._shape:
+            out = NArray._new(self._shape, dev)
+            NArray._call(fn, dev, self._on(dev).data_ptr(), rhs._on(dev).data_ptr(), out._t.data_ptr(), self.size)
+            return out
+        # NormArithmetic (narray.cpp:195-214): rhs dims of size 1 are replicated; 2-D, one dim
+        _check(len(self._shape) == len(rhs._shape) == 2, "NormArithmetic: 2-D operands only on the GPU path")
+        rep = [i for i in range(2) if self._shape[i] != rhs._shape[i]]
+        _check(len(rep) == 1 and rhs._shape[rep[0]] == 1, "NormArithmetic cannot replicate a dimension that is not 1")
+        m, n = self._shape
+        out = NArray._new(self._shape, dev)
+        name = "mnv_norm_%s_on_%s" % (norm, "col" if rep[0] == 0 else "row")
+        NArray._call(name, dev, self._on(dev).data_ptr(), rhs._on(dev).data_ptr(), out._t.data_ptr(), m, n)
+        return out
+
+    def _const(self, fn, val):
+        dev = _rt.current_device()
+        out = NArray._new(self._shape, dev)
+        if fn == "mnv_scale":
+            NArray._call(fn, dev, self._on(dev).data_ptr(), out._t.data_ptr(), self.size, float(val))
+        else:
+            NArray._call(fn, dev, self._on(dev).data_ptr(), out._t.data_ptr(), float(val), self.size)
+        return out
+
+    def __add__(self, rhs):
+        return self._arith(rhs, "mnv_add", "add") if isinstance(rhs, NArray) else self._const("mnv_const_add", rhs)
+
+    __radd__ = __add__
+
+    def __sub__(self, rhs):
+        if isinstance(rhs, NArray):
+            return self._arith(rhs, "mnv_sub", "sub")
+        return self._const("mnv_const_add", -float(rhs))       # cuda.cpp:184-186
+
+    def __rsub__(self, lhs):
+        return self._const("mnv_left_const_sub", lhs)
+
+    def __mul__(self, rhs):
+        if isinstance(rhs, NArray):                              # matrix product (narray.cpp:116-123)
+            return NArray.matmult(self, rhs)
+        return self._const("mnv_scale", rhs)
+
+    def __rmul__(self, lhs):
+        return self._const("mnv_scale", lhs)
+
+    def __truediv__(self, rhs):
+        if isinstance(rhs, NArray):
+            return self._arith(rhs, "mnv_dot_div", "div")
+        return self._const("mnv_const_div", rhs)                # IEEE division, not x*(1/v)
+
+    def __rtruediv__(self, lhs):
+        return self._const("mnv_left_const_div", lhs)
+
+    __div__, __rdiv__ = __truediv__, __rtruediv__
+
+    def __neg__(self):
+        return self._unary("mnv_elewise_negative")
+
+    def _unary(self, fn):
+        dev = _rt.current_device()
+        out = NArray._new(self._shape, dev)
+        NArray._call(fn, dev, self._on(dev).data_ptr(), out._t.data_ptr(), self.size)
+        return out
+
+    @staticmethod
+    def mult(lhs, rhs):
+        return lhs._arith(rhs, "mnv_dot_mult", "mult")
+
+    @staticmethod
+    def exp(x):
+        return x._unary("mnv_elewise_exp")
+
+    @staticmethod
+    def ln(x):
+        return x._unary("mnv_elewise_ln")
+
+    # ---- activations (narray_elewise.cpp:51-82; argument order (diff, top, bottom)) --------------
+    def _act(self, fn):
+        dev = _rt.current_device()
+        out = NArray._new(self._shape, dev)
+        NArray._call(fn, dev, self._on(dev).data_ptr(), out._t.data_ptr(), 1, 1, 1, self.size)
+        return out
+
+    @staticmethod
+    def _act_back(fn, diff, top, bottom):
+        _check(diff._shape == top._shape == bottom._shape, "inputs size mismatch")
+        dev = _rt.current_device()
+        out = NArray._new(diff._shape, dev)
+        NArray._call(fn, dev, bottom._on(dev).data_ptr(), top._on(dev).data_ptr(), diff._on(dev).data_ptr(),
+                     out._t.data_ptr(), 1, 1, 1, diff.size)
+        return out
+
+    @staticmethod
+    def sigm(x):
+        return x._act("mnv_sigmoid_forward")
+
+    @staticmethod
+    def relu(x):
+        return x._act("mnv_relu_forward")
+
+    @staticmethod
+    def tanh(x):
+        return x._act("mnv_tanh_forward")
+
+    @staticmethod
+    def sigm_back(diff, top, bottom):
+        return NArray._act_back("mnv_sigmoid_backward", diff, top, bottom)
+
+    @staticmethod
+    def relu_back(diff, top, bottom):
+        return NArray._act_back("mnv_relu_backward", diff, top, bottom)
+
+    @staticmethod
+    def tanh_back(diff, top, bottom):
+        return NArray._act_back("mnv_tanh_backward", diff, top, bottom)
+
+    @staticmethod
+    def activation_forward(src, algo):
+        return src._act("mnv_%s_forward" % algo.name)
+
+    @staticmethod
+    def activation_backward(diff, top, bottom, algo):
+        return NArray._act_back("mnv_%s_backward" % algo.name, diff, top, bottom)
+
+    # ---- matrix ops ---------------------------------------------------------------------------------
+    @staticmethod
+    def matmult(lhs, rhs):
+        _check(len(lhs._shape) == 2 and len(rhs._shape) == 2, "eligible only for 2D")
+        _check(lhs._shape[1] == rhs._shape[0], "size must match")
+        dev = _rt.current_device()
+        m, k, n = lhs._shape[0], lhs._shape[1], rhs._shape[1]
+        out = NArray._new([m, n], dev)
+        NArray._call("mnv_matmult", dev, lhs._on(dev).data_ptr(), rhs._on(dev).data_ptr(), out._t.data_ptr(), m, n, k,
+                     dev.ws_ptr, dev.ws_bytes)
+        return out
+
+    def trans(self):
+        _check(len(self._shape) == 2, "eligible only for 2D")
+        dev = _rt.current_device()
+        m, n = self._shape
+        out = NArray._new([n, m], dev)
+        NArray._call("mnv_transpose", dev, self._on(dev).data_ptr(), out._t.data_ptr(), m, n)
+        return out
+
+    def reshape(self, s):
+        _check(_prod(s) == self.size, "dimension mismatch")
+        dev = _rt.current_device()
+        out = NArray._new(s, dev)                                # the reference's Reshape is a full copy (cuda.cpp:312-316)
+        NArray._call("mnv_reshape", dev, self._on(dev).data_ptr(), out._t.data_ptr(), self.size * 4)
+        return out
+
+    def _as_2d(self, dim):
+        """View an N-d reduction over its first or last dim as the 2-D case the kernels support
+        (the reference CUDA path is 2-D only, cuda.cpp:268-270)."""
+        nd = len(self._shape)
+        _check(0 <= dim < nd, "dim out of bound")
+        if nd == 2:
+            return self._shape[0], self._shape[1], dim
+        if dim == 0:
+            return self._shape[0], _prod(self._shape[1:]), 0
+        _check(dim == nd - 1, "reduction over an inner dimension is not supported on the GPU path")
+        return _prod(self._shape[:-1]), self._shape[-1], 1
+
+    def _reduce(self, dim, kind):
+        if not isinstance(dim, int):
+            _check(len(dim) == 1, "currently do reduction on one dimension only")
+            dim = int(list(dim)[0])
+        m, n, d = self._as_2d(dim)
+        dev = _rt.current_device()
+        oshape = list(self._shape)
+        oshape[dim] = 1
+        out = NArray._new(oshape, dev)
+        NArray._call("mnv_%s_on_%s" % (kind, "col" if d == 0 else "row"), dev, self._on(dev).data_ptr(),
+                     out._t.data_ptr(), m, n)
+        return out
+
+    def sum(self, dim):
+        return self._reduce(dim, "reduction_sum")
+
+    def max(self, dim):
+        return self._reduce(dim, "reduction_max")
+
+    def max_index(self, dim):
+        return self._reduce(dim, "max_index")
+
+    def count_zero(self):
+        """Blocking, like the reference (narray_reduction.cpp:64-75)."""
+        self._dev.stream.synchronize()
+        return int((self._t == 0).sum().item())
+
+    # ---- convolution family (narray/convolution.cpp) -----------------------------------------------
+    @staticmethod
+    def conv_forward(src, filt, bias, info):
+        W, H, Ci, N = src._shape
+        fw, fh, Ci2, Co = filt._shape
+        _check(Ci == Ci2, "#input channels mismatch")
+        _check(len(bias._shape) == 1 and bias._shape[0] == Co, "bias size mismatch")
+        Wo = (W + 2 * info.pad_width - fw) // info.stride_horizontal + 1
+        Ho = (H + 2 * info.pad_height - fh) // info.stride_vertical + 1
+        dev = _rt.current_device()
+        out = NArray._new([Wo, Ho, Co, N], dev)
+        NArray._call("mnv_conv_forward", dev, src._on(dev).data_ptr(), filt._on(dev).data_ptr(), bias._on(dev).data_ptr(),
+                     out._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
+                     info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
+        return out
+
+    @staticmethod
+    def conv_backward_data(diff, bottom, filt, info):
+        W, H, Ci, N = bottom._shape                             # output takes the bottom's shape (convolution.cpp:47)
+        fw, fh, _, Co = filt._shape
+        _check(diff._shape[2] == Co, "#output channels mismatch")
+        dev = _rt.current_device()
+        out = NArray._new(bottom._shape, dev)
+        NArray._call("mnv_conv_backward_data", dev, diff._on(dev).data_ptr(), filt._on(dev).data_ptr(), out._t.data_ptr(),
+                     N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal,
+                     fh, fw, dev.ws_ptr, dev.ws_bytes)
+        return out
+
+    @staticmethod
+    def conv_backward_filter(diff, bottom, filt, info):
+        W, H, Ci, N = bottom._shape
+        fw, fh, _, Co = filt._shape
+        _check(diff._shape[3] == N, "#images mismatch")
+        dev = _rt.current_device()
+        out = NArray._new(filt._shape, dev)
+        NArray._call("mnv_conv_backward_filter", dev, bottom._on(dev).data_ptr(), diff._on(dev).data_ptr(),
+                     out._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
+                     info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
+        return out
+
+    @staticmethod
+    def conv_backward_bias(diff):
+        W, H, C, N = diff._shape
+        dev = _rt.current_device()
+        out = NArray._new([C], dev)
+        NArray._call("mnv_conv_backward_bias", dev, diff._on(dev).data_ptr(), out._t.data_ptr(), N, C, H, W,
+                     dev.ws_ptr, dev.ws_bytes)
+        return out
+
+    @staticmethod
+    def softmax_forward(src, algo):
+        W, H, C, N = src._shape
+        dev = _rt.current_device()
+        out = NArray._new(src._shape, dev)
+        NArray._call("mnv_%s_softmax_forward" % algo.name, dev, src._on(dev).data_ptr(), out._t.data_ptr(), N, C, H, W)
+        return out
+
+    @staticmethod
+    def softmax_backward(diff, top, algo):
+        _check(diff._shape == top._shape, "inputs sizes mismatch")
+        W, H, C, N = diff._shape
+        dev = _rt.current_device()
+        out = NArray._new(diff._shape, dev)
+        NArray._call("mnv_%s_softmax_backward" % algo.name, dev, diff._on(dev).data_ptr(), top._on(dev).data_ptr(),
+                     out._t.data_ptr(), N, C, H, W)
+        return out
+
+    @staticmethod
+    def _pool_args(info):
+        return (info.stride_vertical, info.stride_horizontal, info.height, info.width, info.pad_height, info.pad_width)
+
+    @staticmethod
+    def pooling_forward(src, info):
+        W, H, C, N = src._shape
+        lib = _lib.load()
+        Ho = lib.mnv_pooled_size(H, info.pad_height, info.height, info.stride_vertical)
+        Wo = lib.mnv_pooled_size(W, info.pad_width, info.width, info.stride_horizontal)
+        dev = _rt.current_device()
+        out = NArray._new([Wo, Ho, C, N], dev)
+        name = "mnv_%s_pooling_forward" % ("max" if info.algorithm.value == 0 else "average")
+        NArray._call(name, dev, src._on(dev).data_ptr(), out._t.data_ptr(), N, C, H, W, *NArray._pool_args(info))
+        return out
+
+    @staticmethod
+    def pooling_backward(diff, top, bottom, info):
+        _check(diff._shape == top._shape, "inputs sizes mismatch")
+        W, H, C, N = bottom._shape
+        dev = _rt.current_device()
+        out = NArray._new(bottom._shape, dev)
+        name = "mnv_%s_pooling_backward" % ("max" if info.algorithm.value == 0 else "average")
+        NArray._call(name, dev, bottom._on(dev).data_ptr(), top._on(dev).data_ptr(), diff._on(dev).data_ptr(),
+                     out._t.data_ptr(), N, C, H, W, *NArray._pool_args(info))
+        return out
+
+    @staticmethod
+    def lrn_forward(src, scale, local_size, alpha, beta):
+        """`scale` is written in place, as in the reference (cuda.cpp:45-59; owl/net/net.py:496-500)."""
+        W, H, C, N = src._shape
+        dev = _rt.current_device()
+        _check(scale._dev is dev and scale._shape == src._shape, "scale must be a same-shape array on this device")
+        out = NArray._new(src._shape, dev)
+        NArray._call("mnv_lrn_forward", dev, src._on(dev).data_ptr(), scale._t.data_ptr(), out._t.data_ptr(),
+                     int(local_size), float(alpha), float(beta), N, C, W, H)
+        return out
+
+    @staticmethod
+    def lrn_backward(bottom_data, top_data, scale, top_diff, local_size, alpha, beta):
+        W, H, C, N = bottom_data._shape
+        dev = _rt.current_device()
+        out = NArray._new(bottom_data._shape, dev)
+        NArray._call("mnv_lrn_backward", dev, bottom_data._on(dev).data_ptr(), top_data._on(dev).data_ptr(),
+                     scale._on(dev).data_ptr(), top_diff._on(dev).data_ptr(), out._t.data_ptr(), int(local_size),
+                     float(alpha), float(beta), N, C, W, H)
+        return out
+
+    # ---- constructors / host transfer ---------------------------------------------------------------
+    @staticmethod
+    def _filled(shape, val):
+        dev = _rt.current_device()
+        out = NArray._new(shape, dev)
+        NArray._call("mnv_fill", dev, out._t.data_ptr(), out.size, float(val))
+        return out
+
+    @staticmethod
+    def zeros(s):
+        return NArray._filled(s, 0.0)
+
+    @staticmethod
+    def ones(s):
+        return NArray._filled(s, 1.0)
+
+    @staticmethod
+    def randn(s, mean, var):
+        dev = _rt.current_device()
+        out = NArray._new(s, dev)
+        NArray._call("mnv_randn", dev, out._t.data_ptr(), out.size, _rt.next_seed(), float(mean), float(var))
+        return out
+
+    @staticmethod
+    def randb(s, p):
+        dev = _rt.current_device()
+        out = NArray._new(s, dev)
+        NArray._call("mnv_rand_bernoulli", dev, out._t.data_ptr(), out.size, _rt.next_seed(), float(p))
+        return out
+
+    @staticmethod
+    def concat(arrays, dim):
+        _check(len(arrays) > 1, "Concat more than one narray")
+        nd = len(arrays[0]._shape)
+        _check(nd - dim <= 2, "Currently only support concat on the last two dims!")   # cuda.cpp:83
+        dev = _rt.current_device()
+        oshape = list(arrays[0]._shape)
+        oshape[dim] = sum(a._shape[dim] for a in arrays)
+        out = NArray._new(oshape, dev)
+        inner_unit = _prod(oshape[:dim])
+        outer = _prod(oshape[dim + 1:])
+        dst_stride = inner_unit * oshape[dim]
+        off = 0
+        for a in arrays:
+            inner = inner_unit * a._shape[dim]
+            NArray._call("mnv_copy_strided", dev, a._on(dev).data_ptr(), out._t.data_ptr() + 4 * off, inner, outer,
+                         inner, dst_stride)
+            off += inner
+        return out
+
+    @staticmethod
+    def slice(src, slice_dim, st_off, slice_count):
+        nd = len(src._shape)
+        _check(nd - slice_dim <= 2, "Currently only support slice on the last two dims!")
+        dev = _rt.current_device()
+        oshape = list(src._shape)
+        oshape[slice_dim] = slice_count
+        out = NArray._new(oshape, dev)
+        inner_unit = _prod(oshape[:slice_dim])
+        outer = _prod(oshape[slice_dim + 1:])
+        NArray._call("mnv_copy_strided", dev, src._on(dev).data_ptr() + 4 * inner_unit * st_off, out._t.data_ptr(),
+                     inner_unit * slice_count, outer, inner_unit * src._shape[slice_dim], inner_unit * slice_count)
+        return out
+
+    @staticmethod
+    def from_numpy(n):
+        dev = _rt.current_device()
+        host = torch.from_numpy(np.ascontiguousarray(n, dtype=np.float32).reshape(-1))
+        t = torch.empty(host.numel(), dtype=torch.float32, device=dev.device)
+        t.copy_(host, non_blocking=True)
+        return NArray(t, list(reversed(n.shape)), dev)
+
+    def to_numpy(self):
+        """Blocking device->host read (NArray::Get, narray.cpp:221-224), shape reversed."""
+        self._dev.stream.synchronize()
+        torch.cuda.current_stream(self._dev.device).synchronize()
+        return self._t.cpu().numpy().reshape(tuple(reversed(self._shape)))
