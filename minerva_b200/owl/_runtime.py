@@ -22,6 +22,29 @@ class _Gpu:
 _devices = []      # id -> _Gpu or CPU_DEVICE
 _current = None
 _seed = [0x5EED, 0]
+profiler = None    # set to an object with begin(name, args, dev) / end(token, dev) to time every C-ABI call
+
+
+class EventProfiler:
+    """Per-op-name device time table from CUDA events on the launching stream -- what the reference's
+    ExecutionProfiler (minerva/profiler/execution_profiler.cpp:17-53) kept with wall clocks."""
+
+    def __init__(self):
+        self.records = []   # (name, args, start_event, end_event)
+
+    def begin(self, name, args, dev):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(dev.stream)
+        return (name, args, e0)
+
+    def end(self, tok, dev):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(dev.stream)
+        self.records.append(tok + (e1,))
+
+    def table(self):
+        """-> list of (name, args, milliseconds); call after the streams are synchronised."""
+        return [(n, a, e0.elapsed_time(e1)) for (n, a, e0, e1) in self.records]
 
 
 def has_cuda():

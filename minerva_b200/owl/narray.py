@@ -94,12 +94,30 @@ class NArray:
 
     @staticmethod
     def _call(name, dev, *args):
+        prof = _rt.profiler
+        if prof is not None:          # per-op device timing (the reference's ExecutionProfiler role)
+            tok = prof.begin(name, args, dev)
         rc = getattr(_lib.load(), name)(*args, dev.stream_ptr)
         if rc:
             _lib.check(rc, name)
+        if prof is not None:
+            prof.end(tok, dev)
 
     def wait_for_eval(self):
         self._dev.stream.synchronize()
+
+    def as_torch(self):
+        """The underlying flat device buffer (for torch.distributed collectives)."""
+        return self._t
+
+    @staticmethod
+    def sgd_update(w, delta, grad, momentum, lr_over_batch, lr_times_wd):
+        """the reference's momentum-SGD chain (owl/net/net.py:252-256, ten ops
+        and 60 B/param per tensor) as one in-place kernel (20 B/param)."""
+        dev = _rt.current_device()
+        _check(w._dev is dev and delta._dev is dev, "sgd_update is in place: w and delta must live on this device")
+        NArray._call("mnv_sgd_momentum_update", dev, w._t.data_ptr(), delta._t.data_ptr(), grad._on(dev).data_ptr(),
+                     w.size, float(momentum), float(lr_over_batch), float(lr_times_wd))
 
     def start_eval(self):
         pass

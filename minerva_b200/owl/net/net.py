@@ -1,0 +1,352 @@
+"""Compute units and the Net DAG (reference: owl/owl/net/net.py:24-1139)."""
+import numpy as np
+
+
+def _default_backend():
+    import minerva_b200.owl as owl
+    import minerva_b200.owl.conv as co
+    import minerva_b200.owl.elewise as ele
+
+    class _B:
+        pass
+    b = _B()
+    b.owl, b.co, b.ele = owl, co, ele
+    return b
+
+
+class ComputeUnit(object):
+    """net.py:24-80: named bottoms/tops, forward(from_btm, to_top, phase), backward(from_top, to_btm, phase)."""
+
+    def __init__(self, name, btm_names, top_names):
+        self.name, self.btm_names, self.top_names = name, list(btm_names), list(top_names)
+        self.out = None
+        self.B = None
+
+    def forward(self, from_btm, to_top, phase):
+        pass
+
+    def backward(self, from_top, to_btm, phase):
+        pass
+
+    def weight_update(self, base_lr, base_weight_decay, momentum, batch_size):
+        pass
+
+
+class ComputeUnitSimple(ComputeUnit):
+    """net.py:82-110: one bottom, one top, ff/bp."""
+
+    def forward(self, from_btm, to_top, phase):
+        to_top[self.top_names[0]] = self.ff(from_btm[self.btm_names[0]], phase)
+        self.out = to_top[self.top_names[0]]
+
+    def backward(self, from_top, to_btm, phase):
+        to_btm[self.btm_names[0]] = self.bp(from_top[self.top_names[0]], phase)
+
+
+class WeightedComputeUnit(ComputeUnitSimple):
+    """net.py:112-266: weight/bias, their grads and momentum buffers, fillers, SGD update."""
+
+    def __init__(self, name, btm, top, lr_mult=(1.0, 2.0), decay_mult=(1.0, 0.0), weight_std=0.01, bias_value=0.0,
+                 weight_filler="gaussian"):
+        super().__init__(name, [btm], [top])
+        self.lr_mult_w, self.lr_mult_b = lr_mult
+        self.decay_mult_w, self.decay_mult_b = decay_mult
+        self.weight_std, self.bias_value, self.weight_filler = weight_std, bias_value, weight_filler
+        self.weight = self.bias = None
+        self.weightdelta = self.biasdelta = None
+        self.weightgrad = self.biasgrad = None
+        self.wshape = self.bshape = None
+        self.fan_in = self.fan_out = 1
+        self.need_bp = True     # first layer: the data gradient is not needed (owl.net computes it anyway)
+
+    def init_weights_with_filler(self):
+        """net.py:196-238.  Gaussian fillers are drawn on the device; xavier (uniform) on the host with
+        numpy, as the reference does, then uploaded."""
+        owl = self.B.owl
+        if self.weight_filler == "xavier":       # net.py:222-224
+            scale = float(np.sqrt(3.0 / self.fan_in))
+            rs = np.random.RandomState(1234 + len(self.name))
+            self.weight = owl.from_numpy(rs.uniform(-scale, scale, list(reversed(self.wshape))).astype(np.float32))
+        else:
+            self.weight = owl.randn(self.wshape, 0.0, self.weight_std)
+        self.bias = owl.zeros(self.bshape)
+        if self.bias_value:
+            self.bias = self.bias + self.bias_value
+        self.weightdelta = owl.zeros(self.wshape)
+        self.biasdelta = owl.zeros(self.bshape)
+
+    def weight_update(self, base_lr, base_weight_decay, momentum, batch_size):
+        """net.py:240-266, the reference's ten-op chain per tensor."""
+        self.weightdelta = momentum * self.weightdelta \
+            - (base_lr * self.lr_mult_w / batch_size) * self.weightgrad \
+            - (base_lr * self.lr_mult_w * base_weight_decay * self.decay_mult_w) * self.weight
+        self.weight = self.weight + self.weightdelta
+        self.weightgrad = None
+        self.biasdelta = momentum * self.biasdelta \
+            - (base_lr * self.lr_mult_b / batch_size) * self.biasgrad \
+            - (base_lr * self.lr_mult_b * base_weight_decay * self.decay_mult_b) * self.bias
+        self.bias = self.bias + self.biasdelta
+        self.biasgrad = None
+
+
+class ReluUnit(ComputeUnitSimple):
+    def __init__(self, name, btm, top):
+        super().__init__(name, [btm], [top])
+
+    def ff(self, x, phase):
+        self.ff_y = self.B.ele.relu(x)
+        return self.ff_y
+
+    def bp(self, y, phase):
+        return self.B.ele.relu_back(y, self.ff_y)
+
+
+class SigmoidUnit(ComputeUnitSimple):
+    def __init__(self, name, btm, top):
+        super().__init__(name, [btm], [top])
+
+    def ff(self, x, phase):
+        self.ff_y = self.B.ele.sigm(x)
+        return self.ff_y
+
+    def bp(self, y, phase):
+        return self.B.owl.NArray.sigm_back(y, self.ff_y, self.ff_y)
+
+
+class TanhUnit(ComputeUnitSimple):
+    def __init__(self, name, btm, top):
+        super().__init__(name, [btm], [top])
+
+    def ff(self, x, phase):
+        self.ff_y = self.B.ele.tanh(x)
+        return self.ff_y
+
+    def bp(self, y, phase):
+        return self.B.owl.NArray.tanh_back(y, self.ff_y, self.ff_y)
+
+
+class PoolingUnit(ComputeUnitSimple):
+    def __init__(self, name, btm, top, kernel, stride, pad=0, pool="max"):
+        super().__init__(name, [btm], [top])
+        self.geom = (kernel, kernel, stride, stride, pad, pad)
+        self.pool = pool
+
+    def ff(self, x, phase):
+        if not hasattr(self, "pooler"):
+            co = self.B.co
+            self.pooler = co.Pooler(*self.geom, op=co.pool_op.max if self.pool == "max" else co.pool_op.avg)
+        self.ff_x = x
+        self.ff_y = self.pooler.ff(x)
+        return self.ff_y
+
+    def bp(self, y, phase):
+        return self.pooler.bp(y, self.ff_y, self.ff_x)
+
+
+class DropoutUnit(ComputeUnitSimple):
+    """net.py:355-383: mask = randb(shape, keep); y = x o mask * 1/(1-ratio)."""
+
+    def __init__(self, name, btm, top, dropout_ratio):
+        super().__init__(name, [btm], [top])
+        self.scale = 1.0 / (1.0 - dropout_ratio)
+        self.keep_ratio = 1 - dropout_ratio
+
+    def ff(self, x, phase):
+        if phase == "TRAIN":
+            self.dropmask = self.B.owl.randb(x.shape, self.keep_ratio)
+            return self.B.ele.mult(x, self.dropmask) * self.scale
+        return x
+
+    def bp(self, y, phase):
+        if phase == "TRAIN":
+            return self.B.ele.mult(y, self.dropmask) * self.scale
+        return y
+
+
+class LRNUnit(ComputeUnitSimple):
+    """net.py:486-502"""
+
+    def __init__(self, name, btm, top, local_size=5, alpha=1e-4, beta=0.75):
+        super().__init__(name, [btm], [top])
+        self.args = (local_size, alpha, beta)
+
+    def ff(self, x, phase):
+        if not hasattr(self, "lrner"):
+            self.lrner = self.B.co.Lrner(*self.args)
+        self.ff_x = x
+        self.scale = self.B.owl.zeros(x.shape)
+        self.ff_y = self.lrner.ff(x, self.scale)
+        return self.ff_y
+
+    def bp(self, y, phase):
+        return self.lrner.bp(self.ff_x, self.ff_y, self.scale, y)
+
+
+class ConcatUnit(ComputeUnit):
+    """net.py:504-560: concat on the channel dim (Caffe concat_dim 1 == owl dim 2), slice on the way back."""
+
+    def __init__(self, name, btms, top, concat_dim_caffe=1):
+        super().__init__(name, btms, [top])
+        self.concat_dim_caffe = concat_dim_caffe
+
+    def forward(self, from_btm, to_top, phase):
+        narrays = [from_btm[b] for b in self.btm_names]
+        self.dim = len(narrays[0].shape) - 1 - self.concat_dim_caffe
+        self.slice_count = [a.shape[self.dim] for a in narrays]
+        to_top[self.top_names[0]] = self.B.owl.concat(narrays, self.dim)
+        self.out = to_top[self.top_names[0]]
+
+    def backward(self, from_top, to_btm, phase):
+        st = 0
+        for b, cnt in zip(self.btm_names, self.slice_count):
+            to_btm[b] = self.B.owl.slice(from_top[self.top_names[0]], self.dim, st, cnt)
+            st += cnt
+
+
+class FullyConnection(WeightedComputeUnit):
+    """net.py:563-619: y = W * x + b with x reshaped to {features, N}."""
+
+    def __init__(self, name, btm, top, num_output, **kw):
+        super().__init__(name, btm, top, **kw)
+        self.num_output = num_output
+
+    def ff(self, act, phase):
+        shp = act.shape
+        a = act.reshape([int(np.prod(shp[0:-1])), shp[-1]]) if len(shp) > 2 else act
+        self.ff_act, self.ff_a2d = act, a
+        if self.weight is None:
+            self.fan_in, self.fan_out = a.shape[0], self.num_output
+            self.wshape, self.bshape = [self.num_output, a.shape[0]], [self.num_output, 1]
+            self.init_weights_with_filler()
+        return self.weight * a + self.bias
+
+    def bp(self, sen, phase):
+        shp = self.ff_act.shape
+        self.weightgrad = sen * self.ff_a2d.trans()
+        self.biasgrad = sen.sum(1)
+        if not self.need_bp:
+            return None
+        s = self.weight.trans() * sen
+        return s.reshape(shp) if len(shp) > 2 else s
+
+
+class ConvConnection(WeightedComputeUnit):
+    """net.py:621-716 (group == 1 only, as the reference asserts at :690-697)."""
+
+    def __init__(self, name, btm, top, num_output, kernel_size, stride=1, pad=0, **kw):
+        super().__init__(name, btm, top, **kw)
+        self.num_output, self.kernel_size, self.stride, self.pad = num_output, kernel_size, stride, pad
+
+    def ff(self, act, phase):
+        if not hasattr(self, "convolver"):
+            self.convolver = self.B.co.Convolver(self.pad, self.pad, self.stride, self.stride)
+        self.ff_act = act
+        if self.weight is None:
+            ci = act.shape[2]
+            self.fan_in = self.kernel_size * self.kernel_size * ci
+            self.wshape, self.bshape = [self.kernel_size, self.kernel_size, ci, self.num_output], [self.num_output]
+            self.init_weights_with_filler()
+        return self.convolver.ff(act, self.weight, self.bias)
+
+    def bp(self, sen, phase):
+        self.weightgrad = self.convolver.weight_grad(sen, self.ff_act, self.weight)
+        self.biasgrad = self.convolver.bias_grad(sen)
+        if not self.need_bp:
+            return None
+        return self.convolver.bp(sen, self.ff_act, self.weight)
+
+
+class SoftmaxUnit(ComputeUnit):
+    """net.py:385-440: softmax + cross-entropy; backward is (y - label) * loss_weight."""
+
+    def __init__(self, name, btm, label, top, loss_weight=1.0):
+        super().__init__(name, [btm, label], [top])
+        self.loss_weight = loss_weight
+
+    def forward(self, from_btm, to_top, phase):
+        co = self.B.co
+        self.ff_y = co.softmax(from_btm[self.btm_names[0]], co.soft_op.instance)
+        self.y = from_btm[self.btm_names[1]]      # one-hot {classes, N}
+        to_top[self.top_names[0]] = self.ff_y
+        self.out = self.ff_y
+
+    def backward(self, from_top, to_btm, phase):
+        d = self.ff_y - self.y
+        to_btm[self.btm_names[0]] = d * self.loss_weight if self.loss_weight != 1.0 else d
+
+    def getloss(self):
+        lossmat = self.B.ele.mult(self.B.ele.ln(self.ff_y), self.y)
+        res = lossmat.sum(0).sum(1).to_numpy()
+        return -float(res.reshape(-1)[0]) / lossmat.shape[1]
+
+
+class DataUnit(ComputeUnit):
+    """Synthetic data layer: the caller sets `.data` / `.label` (owl NArrays) before forward."""
+
+    def __init__(self, name, tops):
+        super().__init__(name, [], tops)
+        self.data = self.label = None
+
+    def forward(self, from_btm, to_top, phase):
+        to_top[self.top_names[0]] = self.data
+        if len(self.top_names) > 1:
+            to_top[self.top_names[1]] = self.label
+
+
+class Net(object):
+    """The unit DAG (net.py:880-1139): topological forward, reverse backward with multi-consumer
+    sensitivities summed by `+` (net.py:1102-1114), per-unit update."""
+
+    def __init__(self, backend=None):
+        self.B = backend or _default_backend()
+        self.units = []
+        self.name_to_uid = {}
+        self.base_lr = self.current_lr = 0.01
+        self.momentum = 0.9
+        self.base_weight_decay = 5e-4
+        self.batch_size = 0          # GLOBAL batch: the update divisor (net.py:252-254,1121-1124)
+        self.on_weight_grad = None   # hook(unit) fired as soon as a unit's gradients exist
+
+    def add_unit(self, unit):
+        unit.B = self.B
+        self.name_to_uid[unit.name] = len(self.units)
+        self.units.append(unit)
+        return unit
+
+    def get_weighted_unit_ids(self):
+        return [i for i, u in enumerate(self.units) if isinstance(u, WeightedComputeUnit)]
+
+    def get_loss_units(self):
+        return [u for u in self.units if isinstance(u, SoftmaxUnit)]
+
+    def get_data_unit(self):
+        return [u for u in self.units if isinstance(u, DataUnit)][0]
+
+    def forward(self, phase="TRAIN"):
+        blobs = {}
+        for u in self.units:      # builders append units in topological order
+            u.forward(blobs, blobs, phase)
+        self._blobs = blobs
+
+    def backward(self, phase="TRAIN"):
+        sens = {}
+        for u in reversed(self.units):
+            if isinstance(u, DataUnit):
+                continue
+            if not isinstance(u, SoftmaxUnit) and any(sens.get(t) is None for t in u.top_names):
+                continue
+            out = {}
+            u.backward(sens, out, phase)
+            for k, v in out.items():
+                if v is None:
+                    continue
+                sens[k] = sens[k] + v if sens.get(k) is not None else v
+            if self.on_weight_grad is not None and isinstance(u, WeightedComputeUnit):
+                self.on_weight_grad(u)
+
+    def update(self, uid):
+        self.units[uid].weight_update(self.current_lr, self.base_weight_decay, self.momentum, self.batch_size)
+
+    def weight_update(self):
+        for uid in self.get_weighted_unit_ids():
+            self.update(uid)

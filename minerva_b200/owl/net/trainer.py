@@ -1,0 +1,69 @@
+"""Data-parallel training loop (reference: owl/owl/net/trainer.py:101-148).
+
+The reference runs every replica from one Python thread (`for gpuid: owl.set_device(...)`) and
+merges gradients by copying them to a per-layer "update GPU" and adding (trainer.py:126-138); the
+updated weight is then re-read by the other GPUs on their next use.  Here there is one process per
+GPU (torchrun); the merge is an NCCL all-reduce over NVLink/NVSwitch issued per weighted unit the
+moment its dW/db exist -- i.e. in reverse layer order, overlapping the rest of backward -- and
+every rank applies the identical update to its own replica, so no weight broadcast is needed.
+The update divisor stays the GLOBAL batch (net.py:252-254).
+"""
+import time
+
+
+class NetTrainer(object):
+    def __init__(self, net, dist=None, fused_update=True):
+        """dist: an initialised torch.distributed module (or None for 1 GPU).
+        fused_update: one mnv_sgd_momentum_update per tensor instead of the reference's op chain."""
+        self.net = net
+        self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.fused_update = fused_update
+        self._pending = []
+        net.on_weight_grad = self._on_weight_grad if self.dist else None
+
+    # -- gradient merge -------------------------------------------------------------------------
+    def _on_weight_grad(self, unit):
+        d = self.dist
+        for g in (unit.weightgrad, unit.biasgrad):
+            self._pending.append(d.all_reduce(g.as_torch(), op=d.ReduceOp.SUM, async_op=True))
+
+    def _wait_merge(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
+    # -- one iteration ------------------------------------------------------------------------------
+    def step(self):
+        net = self.net
+        net.forward("TRAIN")
+        net.backward("TRAIN")
+        self._wait_merge()
+        if not self.fused_update:
+            net.weight_update()
+            return
+        NArray = net.B.owl.NArray
+        lr, wd, mom, bs = net.current_lr, net.base_weight_decay, net.momentum, net.batch_size
+        for uid in net.get_weighted_unit_ids():
+            u = net.units[uid]
+            NArray.sgd_update(u.weight, u.weightdelta, u.weightgrad, mom, lr * u.lr_mult_w / bs,
+                              lr * u.lr_mult_w * wd * u.decay_mult_w)
+            NArray.sgd_update(u.bias, u.biasdelta, u.biasgrad, mom, lr * u.lr_mult_b / bs,
+                              lr * u.lr_mult_b * wd * u.decay_mult_b)
+            u.weightgrad = u.biasgrad = None
+
+    def run(self, iters, sync_freq=1, log=None):
+        """trainer.py:101-148: img/s = batch_size * sync_freq / wall time between wait_for_all() calls."""
+        owl = self.net.B.owl
+        last = time.time()
+        speeds = []
+        for it in range(iters):
+            self.step()
+            if (it + 1) % sync_freq == 0:
+                owl.wait_for_all()
+                now = time.time()
+                speeds.append(self.net.batch_size * sync_freq / (now - last))
+                if log:
+                    log("Finished training %d minibatch (speed: %.1f img/s)" % (it + 1, speeds[-1]))
+                last = time.time()
+        return speeds

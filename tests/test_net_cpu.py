@@ -1,0 +1,137 @@
+"""Host-logic tests that need no GPU: the owl.net graph on the CPU oracle backend -- gradient check of
+the layer graph, fused-vs-chained update, and the N>1 data-parallel path on gloo (world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tiny_net(backend):
+    """AlexNet's layer types at toy size: conv-relu-lrn-pool-conv-relu-pool-fc-relu-dropout-fc-softmax."""
+    from minerva_b200.owl.net.net import (Net, DataUnit, ConvConnection, ReluUnit, LRNUnit, PoolingUnit, FullyConnection,
+                                          DropoutUnit, SoftmaxUnit)
+    net = Net(backend)
+    net.add_unit(DataUnit("data", ["data", "label"]))
+    net.add_unit(ConvConnection("conv1", "data", "conv1", 6, 3, 2, 0, weight_std=0.3))
+    net.add_unit(ReluUnit("relu1", "conv1", "c1r"))
+    net.add_unit(LRNUnit("norm1", "c1r", "norm1", 5, 1e-2, 0.75))
+    net.add_unit(PoolingUnit("pool1", "norm1", "pool1", 3, 2))
+    net.add_unit(ConvConnection("conv2", "pool1", "conv2", 8, 3, 1, 1, weight_std=0.3, bias_value=0.1))
+    net.add_unit(ReluUnit("relu2", "conv2", "c2r"))
+    net.add_unit(PoolingUnit("pool2", "c2r", "pool2", 2, 2))
+    net.add_unit(FullyConnection("fc6", "pool2", "fc6", 16, weight_std=0.2, bias_value=0.1))
+    net.add_unit(ReluUnit("relu6", "fc6", "fc6r"))
+    net.add_unit(DropoutUnit("drop6", "fc6r", "fc6d", 0.5))
+    net.add_unit(FullyConnection("fc8", "fc6d", "fc8", 5, weight_std=0.2))
+    net.add_unit(SoftmaxUnit("loss", "fc8", "label", "prob"))
+    net.base_lr = net.current_lr = 0.05
+    return net
+
+
+def _batch(backend, n, seed=0, lo=0):
+    rs = np.random.RandomState(seed)
+    x = rs.normal(0, 1, (64, 3, 17, 17)).astype(np.float32)[lo:lo + n]
+    lab = rs.randint(0, 5, 64)[lo:lo + n]
+    onehot = np.zeros((n, 5), np.float32)
+    onehot[np.arange(n), lab] = 1
+    return backend.owl.from_numpy(x), backend.owl.from_numpy(onehot)
+
+
+def test_numeric_gradient_of_the_graph():
+    """The reference ships this as a tool (owl/net/gradient_checker.py); here it is a test."""
+    from oracle import owl_cpu
+    B = owl_cpu.Backend()
+    owl_cpu.set_seed(3)
+    net = _tiny_net(B)
+    du = net.get_data_unit()
+    du.data, du.label = _batch(B, 4)
+    net.batch_size = 4
+    net.forward("TEST")          # TEST: no dropout, deterministic
+    net.backward("TEST")
+    loss_unit = net.get_loss_units()[0]
+    for uname, idxs in (("fc8", [0, 7, 33]), ("conv2", [1, 50, 200]), ("conv1", [0, 11, 100])):
+        u = net.units[net.name_to_uid[uname]]
+        g = u.weightgrad.a.copy()
+        for i in idxs:
+            h = 1e-2
+            old = u.weight.a[i]
+            u.weight.a[i] = old + h
+            net.forward("TEST"); lp = loss_unit.getloss()
+            u.weight.a[i] = old - h
+            net.forward("TEST"); lm = loss_unit.getloss()
+            u.weight.a[i] = old
+            num = (lp - lm) / (2 * h) * 4    # getloss averages over the batch; grads are sums
+            assert abs(num - g[i]) <= 2e-2 * max(1.0, abs(g[i])), (uname, i, num, g[i])
+
+
+def test_fused_update_equals_reference_chain():
+    from oracle import owl_cpu
+    from minerva_b200.owl.net.trainer import NetTrainer
+    B = owl_cpu.Backend()
+    res = []
+    for fused in (False, True):
+        owl_cpu.set_seed(5)
+        net = _tiny_net(B)
+        du = net.get_data_unit()
+        du.data, du.label = _batch(B, 8)
+        net.batch_size = 8
+        tr = NetTrainer(net, None, fused_update=fused)
+        tr.step(); tr.step()
+        res.append(np.concatenate([net.units[i].weight.a for i in net.get_weighted_unit_ids()]))
+    np.testing.assert_allclose(res[0], res[1], rtol=1e-6, atol=1e-7)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import owl_cpu
+    from minerva_b200.owl.net.trainer import NetTrainer
+    B = owl_cpu.Backend()
+    owl_cpu.set_seed(11)                       # identical initial weights on every rank
+    net = _tiny_net(B)
+    per = 8 // world
+    du = net.get_data_unit()
+    du.data, du.label = _batch(B, per, lo=rank * per)
+    net.batch_size = 8                         # GLOBAL batch is the update divisor
+    tr = NetTrainer(net, dist if world > 1 else None)
+    assert tr.world == world
+    net.forward("TEST"); net.backward("TEST"); tr._wait_merge()
+    grads = np.concatenate([net.units[i].weightgrad.a for i in net.get_weighted_unit_ids()])
+    net.forward("TEST"); net.backward("TEST"); tr._wait_merge()
+    tr.fused_update = True
+    # finish the iteration by hand (phase TEST keeps dropout out of the comparison)
+    for uid in net.get_weighted_unit_ids():
+        net.update(uid)
+    w = np.concatenate([net.units[i].weight.a for i in net.get_weighted_unit_ids()])
+    if rank == 0:
+        np.save(out, np.stack([grads, w]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_data_parallel_matches_single_process(tmp_path):
+    """2 ranks x 4 samples must give the merged gradient and the updated weights of 1 rank x 8 samples
+    (the reference's claim, owl/owl/net/README.md:104), to 1e-5 relative (summation order differs)."""
+    f1, f2 = str(tmp_path / "w1.npy"), str(tmp_path / "w2.npy")
+    mp.spawn(_dp_worker, args=(1, _free_port(), f1), nprocs=1, join=True)
+    mp.spawn(_dp_worker, args=(2, _free_port(), f2), nprocs=2, join=True)
+    a, b = np.load(f1), np.load(f2)
+    assert np.abs(a[0] - b[0]).max() <= 1e-5 * np.abs(a[0]).max()
+    assert np.abs(a[1] - b[1]).max() <= 1e-5 * np.abs(a[1]).max()
