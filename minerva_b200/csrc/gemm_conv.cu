@@ -57,6 +57,7 @@ struct GemmParams {
   long long img_stride, col_stride;
   // tiling
   int bn, m_tiles, n_tiles, splits, stages_per_split, k_stages;
+  int use_ktab;         // A_IM2COL_FWD: k -> (offset, kh, kw) table in shared memory
 };
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -66,7 +67,8 @@ constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 4;       // 16 KB
 constexpr int kBBytes = BN_MAX * BK * 4;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kKtabMax = 6144;            // entries of the im2col k-decomposition table (24 KB)
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kKtabMax * 4;
 constexpr int kThreads = 448;
 constexpr int kProducerWarp0 = 6;
 constexpr int kProducerThreads = 256;
@@ -227,14 +229,23 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast gathers.  A: thread = one tile row, 16 consecutive k per stage (lanes run along m => coalesced
-// for every mode).  B: thread = 16-byte chunk (row, kq); 8 consecutive lanes cover 128 contiguous bytes.
+// fast gathers.  Every producer thread stages 16 floats of A per k-stage (4 chunks of 16 bytes):
+//   MC mapping (A_COLMAJOR, A_IM2COL_FWD, A_IM2COL_BWD): thread = one tile row, 16 consecutive k;
+//      lanes run along m, which is the contiguous axis of the source => coalesced LDG.
+//   KC mapping (A_IM2COL_WGRAD): thread = chunk column kq of 4 rows; 8 consecutive lanes cover 32
+//      consecutive pixels (k), the contiguous axis of x for this mode.
+// B (when it is not fetched by TMA): thread = 16-byte chunk (row, kq), rows b_row0 + 32*i.
 // ------------------------------------------------------------------------------------------------
 struct ARow {           // per-thread, per-tile state of the A gather
   bool valid;
   long long base;       // element offset contribution of the row
-  uint32_t mh, mw;      // validity masks over kh / kw (im2col fwd / bwd stride-1)
-  int h0, w0;           // generic: oh*sv-ph (fwd), h+ph (bwd), kh-ph (wgrad)
+  uint32_t mh, mw;      // validity masks over kh / kw (im2col fwd / bwd)
+  int h0, w0;           // oh*sv-ph (fwd), h+ph (bwd)
+};
+struct AWgrad {         // KC mapping: 4 rows (taps) per thread
+  int toff[4];          // ci*H*W + (kh-ph)*W + (kw-pw)
+  int dh[4], dw[4];     // kh-ph, kw-pw
+  bool valid[4];
 };
 
 template <int AM>
@@ -257,23 +268,34 @@ __device__ __forceinline__ ARow a_row_setup(const GemmParams& p, int m) {
     r.base = static_cast<long long>(img) * p.Co * p.Ho * p.Wo;
     for (int kh = 0; kh < p.fh; ++kh) { int t = r.h0 - kh; if (t >= 0 && t % p.sv == 0 && t / p.sv < p.Ho) r.mh |= 1u << kh; }
     for (int kw = 0; kw < p.fw; ++kw) { int u = r.w0 - kw; if (u >= 0 && u % p.sh == 0 && u / p.sh < p.Wo) r.mw |= 1u << kw; }
-  } else {  // WGRAD: row = (ci, r, s)
-    int ff = p.fh * p.fw;
-    int ci = m / ff, rs = m - ci * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
-    r.h0 = (p.fh - 1 - rr) - p.ph; r.w0 = (p.fw - 1 - ss) - p.pw;
-    r.base = static_cast<long long>(ci) * p.H * p.W + static_cast<long long>(r.h0) * p.W + r.w0;
   }
   return r;
 }
 
-// 16 consecutive k starting at k0 for this thread's row
+__device__ __forceinline__ AWgrad a_wgrad_setup(const GemmParams& p, int m_base, int row0) {
+  AWgrad w;
+  const int ff = p.fh * p.fw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m_base + row0 + 32 * i;
+    w.valid[i] = m < p.M;
+    int mm = w.valid[i] ? m : 0;
+    int ci = mm / ff, rs = mm - ci * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
+    w.dh[i] = (p.fh - 1 - rr) - p.ph;
+    w.dw[i] = (p.fw - 1 - ss) - p.pw;
+    w.toff[i] = ci * p.H * p.W + w.dh[i] * p.W + w.dw[i];
+  }
+  return w;
+}
+
+// MC mapping: 16 consecutive k starting at k0 for this thread's row
 template <int AM>
 __device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, int k0, float (&v)[16]) {
   if (AM == A_COLMAJOR) {
     const float* src = p.a + r.base + static_cast<size_t>(k0) * p.lda;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = (r.valid && k0 + j < p.K) ? __ldg(src + static_cast<size_t>(j) * p.lda) : 0.f;
-  } else if (AM == A_IM2COL_FWD || AM == A_IM2COL_BWD) {
+  } else {
     // k = (c, rr, ss) in filter storage order; kh = fh-1-rr, kw = fw-1-ss
     const int ff = p.fh * p.fw;
     int c = k0 / ff, rs = k0 - c * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
@@ -283,13 +305,13 @@ __device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, i
       int off = c * HW + kh * p.W + kw;
       const float* src = p.a + r.base;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 16; ++j) {  // table-free fallback (K or C*H*W too large for the smem table)
         bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
         v[j] = ok ? __ldg(src + off) : 0.f;
         --kw; --off;
         if (kw < 0) { kw = p.fw - 1; off += p.fw - p.W; --kh; if (kh < 0) { kh = p.fh - 1; off += p.fh * p.W + HW; } }
       }
-    } else {
+    } else {  // strided backward-data: divisions per element, first-layer shapes only
       const int HoWo = p.Ho * p.Wo;
       const float* src = p.a + r.base;
 #pragma unroll
@@ -305,50 +327,115 @@ __device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, i
         if (kw < 0) { kw = p.fw - 1; --kh; if (kh < 0) { kh = p.fh - 1; ++c; } }
       }
     }
-  } else {  // WGRAD: k = (img, oh, ow)
-    const int HoWo = p.Ho * p.Wo;
-    int img = k0 / HoWo, pix = k0 - img * HoWo, oh = pix / p.Wo, ow = pix - oh * p.Wo;
-    int ohs = oh * p.sv, ows = ow * p.sh;
-    long long uoff = static_cast<long long>(img) * p.Ci * p.H * p.W + static_cast<long long>(ohs) * p.W + ows;
-    const float* src = p.a + r.base;
+  }
+}
+
+// Forward im2col with the k-decomposition table: entry = offset | kh << 22 | kw << 27 where
+// offset = c*H*W + kh*W + kw; entries past K carry kh = 31, a bit no row mask ever has (fh <= 31).
+// Row validity is folded into the masks (mh = 0 for rows past M), so one element costs
+// LDS(broadcast) + 3 shifts + LOP3 + address add + predicated LDG, with no branches.
+__device__ __forceinline__ void a_gather16_ktab(const GemmParams& p, const ARow& r, const uint32_t* __restrict__ ktab, int k0,
+                                                float (&v)[16]) {
+  const float* src = p.a + r.base;
+  const uint4* t4 = reinterpret_cast<const uint4*>(ktab + k0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      bool ok = r.valid && (k0 + j < p.K) && static_cast<unsigned>(ohs + r.h0) < static_cast<unsigned>(p.H) &&
-                static_cast<unsigned>(ows + r.w0) < static_cast<unsigned>(p.W);
-      v[j] = ok ? __ldg(src + uoff) : 0.f;
-      ++ow; ows += p.sh; uoff += p.sh;
-      if (ow == p.Wo) {
-        ow = 0; uoff -= static_cast<long long>(p.Wo) * p.sh; ows = 0;
-        ++oh; ohs += p.sv; uoff += static_cast<long long>(p.sv) * p.W;
-        if (oh == p.Ho) { oh = 0; uoff -= static_cast<long long>(p.Ho) * p.sv * p.W; ohs = 0; uoff += static_cast<long long>(p.Ci) * p.H * p.W; }
-      }
+  for (int q = 0; q < 4; ++q) {
+    uint4 e4 = t4[q];
+    const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool ok = (__funnelshift_r(r.mh, 0u, e[j] >> 22) & (r.mw >> (e[j] >> 27))) & 1u;
+      v[4 * q + j] = ok ? __ldg(src + (e[j] & 0x3FFFFFu)) : 0.f;
     }
   }
 }
 
-// one 16-byte chunk: 4 consecutive k starting at k0 of row n
-template <int BMD>
-__device__ __forceinline__ float4 b_gather4(const GemmParams& p, int n, int k0) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (n >= p.N || k0 >= p.K) return v;
-  if (BMD == B_KMAJOR) {
-    const float* src = p.b + static_cast<size_t>(n) * p.ldb + k0;
-    if (p.b_vec) return __ldg(reinterpret_cast<const float4*>(src));
-    v.x = __ldg(src);
-    if (k0 + 1 < p.K) v.y = __ldg(src + 1);
-    if (k0 + 2 < p.K) v.z = __ldg(src + 2);
-    if (k0 + 3 < p.K) v.w = __ldg(src + 3);
-    return v;
-  }
-  const int hw = p.Ho * p.Wo;
-  int img = k0 / hw, pix = k0 - img * hw;
-  float* o = &v.x;
+// KC mapping (backward-filter): this thread's 4 pixels k0..k0+3 for its 4 tap rows; v[4*i + e]
+__device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad& w, int k0, float (&v)[16]) {
+  const int HoWo = p.Ho * p.Wo;
+  int img = k0 / HoWo, pix = k0 - img * HoWo, oh = pix / p.Wo, ow = pix - oh * p.Wo;
+  long long uoff[4];
+  int ohs[4], ows[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    if (k0 + e < p.K) o[e] = __ldg(p.b + (static_cast<size_t>(img) * p.Co + n) * hw + pix);
-    if (++pix == hw) { pix = 0; ++img; }
+    ohs[e] = (k0 + e < p.K) ? oh * p.sv : -(1 << 28);   // out-of-range k fails the bounds test below
+    ows[e] = ow * p.sh;
+    uoff[e] = static_cast<long long>(img) * p.Ci * p.H * p.W + static_cast<long long>(oh * p.sv) * p.W + ow * p.sh;
+    if (++ow == p.Wo) { ow = 0; if (++oh == p.Ho) { oh = 0; ++img; } }
   }
-  return v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* src = p.a + w.toff[i];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      bool ok = w.valid[i] && static_cast<unsigned>(ohs[e] + w.dh[i]) < static_cast<unsigned>(p.H) &&
+                static_cast<unsigned>(ows[e] + w.dw[i]) < static_cast<unsigned>(p.W);
+      v[4 * i + e] = ok ? __ldg(src + uoff[e]) : 0.f;
+    }
+  }
+}
+
+// B gathered by threads: `iters` chunks (rows b_row0 + 32*i, column chunk kq) of 4 consecutive k
+template <int BMD>
+__device__ __forceinline__ void b_gather(const GemmParams& p, int n_base, int b_row0, int iters, int k0, float4 (&vb)[8]) {
+  if (BMD == B_KMAJOR) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= iters) break;
+      int row = b_row0 + 32 * i, n = n_base + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.bn && n < p.N && k0 < p.K) {
+        const float* src = p.b + static_cast<size_t>(n) * p.ldb + k0;
+        if (p.b_vec) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          v.x = __ldg(src);
+          if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+          if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+          if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+        }
+      }
+      vb[i] = v;
+    }
+  } else {  // B_DY_WGRAD: k = (img, pix): top_diff[(img*Co + n)*hw + pix]; same k for all of this thread's rows
+    const int hw = p.Ho * p.Wo;
+    int img = k0 / hw, pix = k0 - img * hw;
+    long long off[4];
+    bool okk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      okk[e] = k0 + e < p.K;
+      off[e] = static_cast<long long>(img) * p.Co * hw + pix;
+      if (++pix == hw) { pix = 0; ++img; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= iters) break;
+      int row = b_row0 + 32 * i, n = n_base + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.bn && n < p.N) {
+        const float* src = p.b + static_cast<size_t>(n) * hw;
+        if (okk[0]) v.x = __ldg(src + off[0]);
+        if (okk[1]) v.y = __ldg(src + off[1]);
+        if (okk[2]) v.z = __ldg(src + off[2]);
+        if (okk[3]) v.w = __ldg(src + off[3]);
+      }
+      vb[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA (B operand when it is a plain K-major matrix with 16-byte-aligned rows)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,8 +453,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-template <int AM, int BMD>
-__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+template <int AM, int BMD, bool BTMA>
+__global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p,
+                                                                const __grid_constant__ CUtensorMap tmap_b) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of address bits [7,10)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -376,17 +464,31 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
   const uint32_t tfull0 = smem_u32(bars + 2 * kStages), tempty0 = smem_u32(bars + 2 * kStages + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 256);
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }
+    // full: one arrive per producer warp (+ the TMA thread's arrive.expect_tx)
+    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, kProducerThreads / 32 + (BTMA ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (AM == A_IM2COL_FWD && p.use_ktab) {
+    const int ff = p.fh * p.fw, HW = p.H * p.W;
+    for (int k = threadIdx.x; k < p.k_stages * BK; k += blockDim.x) {
+      uint32_t e = 31u << 22;
+      if (k < p.K) {
+        int c = k / ff, rs = k - c * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
+        int kh = p.fh - 1 - rr, kw = p.fw - 1 - ss;
+        e = static_cast<uint32_t>(c * HW + kh * p.W + kw) | (static_cast<uint32_t>(kh) << 22) | (static_cast<uint32_t>(kw) << 27);
+      }
+      ktab[k] = e;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -463,52 +565,82 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       }
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= kProducerWarp0) {
-    // ===================== producers =====================
+  } else if (warp == 5) {
+    // ===================== TMA producer for B =====================
+    if (BTMA && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4;   // the whole box, OOB rows/cols arrive as zeros
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord t = decode_tile(p, tile);
+        for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
+          tma_load_2d(smem_base + stage * kStageBytes + kABytes, &tmap_b, full0 + 8 * stage, ks * BK, t.nt * p.bn);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== gather producers =====================
+    constexpr int LOOK = BTMA ? 2 : 1;                   // register look-ahead in k-stages
     const int pt = threadIdx.x - kProducerWarp0 * 32;   // 0..255
-    const int a_row = pt & 127, a_half = pt >> 7;       // 16 consecutive k: [a_half*16, +16)
-    const int b_kq = pt & 7, b_row0 = pt >> 3;          // rows b_row0 + 32*i
+    const int a_row = pt & 127, a_half = pt >> 7;       // MC mapping: 16 consecutive k: [a_half*16, +16)
+    const int b_kq = pt & 7, b_row0 = pt >> 3;          // KC mapping: rows b_row0 + 32*i, chunk column b_kq
     const int b_iters = (p.bn + 31) / 32;               // <= 8
     int stage = 0; uint32_t phase = 0;
-    float va[16];
-    float4 vb[8];
+    float va[LOOK][16];
+    float4 vb[BTMA ? 1 : LOOK][8];
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
-      const ARow arow = a_row_setup<AM>(p, t.mt * BM + a_row);
+      ARow arow;
+      AWgrad awg;
+      if (AM == A_IM2COL_WGRAD) awg = a_wgrad_setup(p, t.mt * BM, b_row0);
+      else arow = a_row_setup<AM>(p, t.mt * BM + a_row);
       const int n_base = t.nt * p.bn;
-      auto load = [&](int ks) {
-        a_gather16<AM>(p, arow, ks * BK + a_half * 16, va);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < b_iters) {
-            int row = b_row0 + 32 * i;
-            vb[i] = row < p.bn ? b_gather4<BMD>(p, n_base + row, ks * BK + b_kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      auto load = [&](int l, int ks) {
+        if (AM == A_IM2COL_WGRAD) a_gather_wgrad(p, awg, ks * BK + b_kq * 4, va[l]);
+        else if (AM == A_IM2COL_FWD && p.use_ktab) a_gather16_ktab(p, arow, ktab, ks * BK + a_half * 16, va[l]);
+        else a_gather16<AM>(p, arow, ks * BK + a_half * 16, va[l]);
+        if (!BTMA) b_gather<BMD>(p, n_base, b_row0, b_iters, ks * BK + b_kq * 4, vb[BTMA ? 0 : l]);
       };
-      load(t.ks_begin);
-      for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+      auto store = [&](int l) {
         uint8_t* a_tile = smem + stage * kStageBytes;
         uint8_t* b_tile = a_tile + kABytes;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 w = make_float4(to_tf32(va[4 * q]), to_tf32(va[4 * q + 1]), to_tf32(va[4 * q + 2]), to_tf32(va[4 * q + 3]));
-          *reinterpret_cast<float4*>(a_tile + sw128_off(a_row, a_half * 4 + q)) = w;
+          float4 w = make_float4(to_tf32(va[l][4 * q]), to_tf32(va[l][4 * q + 1]), to_tf32(va[l][4 * q + 2]), to_tf32(va[l][4 * q + 3]));
+          uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(b_row0 + 32 * q, b_kq) : sw128_off(a_row, a_half * 4 + q);
+          *reinterpret_cast<float4*>(a_tile + off) = w;
         }
+        if (!BTMA) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < b_iters) {
+          for (int i = 0; i < 8; ++i) {
+            if (i >= b_iters) break;
             int row = b_row0 + 32 * i;
             if (row < p.bn) {
-              float4 w = make_float4(to_tf32(vb[i].x), to_tf32(vb[i].y), to_tf32(vb[i].z), to_tf32(vb[i].w));
-              *reinterpret_cast<float4*>(b_tile + sw128_off(row, b_kq)) = w;
+              const float4& s4 = vb[BTMA ? 0 : l][i];
+              *reinterpret_cast<float4*>(b_tile + sw128_off(row, b_kq)) = make_float4(to_tf32(s4.x), to_tf32(s4.y), to_tf32(s4.z), to_tf32(s4.w));
             }
           }
-        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * stage);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-        if (ks + 1 < t.ks_end) load(ks + 1);  // next stage's loads fly while the ring drains
+        }
+      };
+#pragma unroll
+      for (int l = 0; l < LOOK; ++l)
+        if (t.ks_begin + l < t.ks_end) load(l, t.ks_begin + l);
+      for (int ks = t.ks_begin; ks < t.ks_end; ks += LOOK) {
+#pragma unroll
+        for (int l = 0; l < LOOK; ++l) {
+          if (ks + l < t.ks_end) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            store(l);
+            fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * stage);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (ks + l + LOOK < t.ks_end) load(l, ks + l + LOOK);  // flies while the ring drains
+          }
+        }
       }
     }
   }
@@ -531,15 +663,17 @@ __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams 
   }
 }
 
-// w[co][ci][r][s] -> wt[ci][co][r][s]: backward-data reads the filter as B[n=ci][k=(co,r,s)]
-__global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci, int ff) {
+// w[co][ci][r][s] -> wt[ci][co][r'][s']: backward-data reads the filter as B[n=ci][k=(co,r,s)].
+// flip = 1 additionally rotates the taps by 180 degrees (r' = fh-1-r, s' = fw-1-s), which turns a
+// stride-1 backward-data into a forward convolution of top_diff with pad' = f-1-pad.
+__global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci, int ff, int flip) {
   size_t total = static_cast<size_t>(Co) * Ci * ff;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
     int rs = static_cast<int>(t % ff);
     size_t rest = t / ff;
     int co = static_cast<int>(rest % Co), ci = static_cast<int>(rest / Co);
-    wt[t] = __ldg(w + (static_cast<size_t>(co) * Ci + ci) * ff + rs);
+    wt[t] = __ldg(w + (static_cast<size_t>(co) * Ci + ci) * ff + (flip ? ff - 1 - rs : rs));
   }
 }
 
@@ -548,6 +682,37 @@ __global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
 static std::atomic<int> g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
+static std::atomic<int> g_opt_no_tma{0};     // 1: gather B with threads even where TMA applies (debug)
+static std::atomic<int> g_opt_no_fwd_bwd{0};
+static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug) // 1: use the generic backward-data gather for stride 1 too (debug)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static std::atomic<EncodeTiledFn> cached{nullptr};
+  EncodeTiledFn fn = cached.load(std::memory_order_acquire);
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  cached.store(fn, std::memory_order_release);
+  return fn;
+}
+// K-major fp32 matrix [rows][ld] seen as a 2-D tensor (k fastest); box = 32 k x bn rows, 128B swizzle.
+static bool make_b_tmap(CUtensorMap* tm, const float* b, int rows, int K, int ld, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(b), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials) {
   p.m_tiles = (p.M + BM - 1) / BM;
@@ -576,6 +741,23 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials) {
   p.splits = (p.k_stages + p.stages_per_split - 1) / p.stages_per_split;  // no empty split
 }
 
+template <int AM, int BMD, bool BTMA>
+static int launch_umma(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s) {
+  // opt in to >48 KB dynamic shared memory once per (device, instantiation)
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD, BTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+  int grid = static_cast<int>(total < kNumSMs ? total : kNumSMs);
+  umma_gemm_kernel<AM, BMD, BTMA><<<grid, kThreads, kSmemBytes, s>>>(p, tm);
+  return finish_launch();
+}
+
 template <int AM, int BMD>
 static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (g_opt_simt.load()) {
@@ -585,19 +767,15 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   }
   plan_tiles(p, ws ? ws_bytes : 0);
   p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
-  // opt in to >48 KB dynamic shared memory once per (device, instantiation)
-  static std::atomic<uint64_t> attr_done{0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
-  }
-  long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
-  int grid = static_cast<int>(total < kNumSMs ? total : kNumSMs);
-  umma_gemm_kernel<AM, BMD><<<grid, kThreads, kSmemBytes, s>>>(p);
-  int rc = finish_launch();
+  p.use_ktab = (AM == A_IM2COL_FWD) && p.k_stages * BK <= kKtabMax &&
+               static_cast<long long>(p.Ci) * p.H * p.W < (1ll << 22) && !g_opt_no_ktab.load();
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  bool tma = false;
+  if (BMD == B_KMAJOR && p.b_vec && !g_opt_no_tma.load()) tma = make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.bn);
+  int rc;
+  if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
+  else rc = launch_umma<AM, BMD, false>(p, tm, s);
   if (rc || p.splits == 1) return rc;
   splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
   return finish_launch();
@@ -606,14 +784,14 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0;
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0;
   p.bias = nullptr; p.partial = nullptr;
 }
 
 static int check_conv(int N, int Ci, int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw) {
   if (N < 0 || Ci <= 0 || Co <= 0 || H <= 0 || W <= 0 || ph < 0 || pw < 0 || sv <= 0 || sh <= 0 || fh <= 0 || fw <= 0)
     return MNV_EINVAL;
-  if (fh > 32 || fw > 32) return MNV_EUNSUPPORTED;  // validity masks are 32-bit
+  if (fh > 31 || fw > 31) return MNV_EUNSUPPORTED;  // validity masks are 32-bit, bit 31 is the k-table sentinel
   if (H + 2 * ph < fh || W + 2 * pw < fw) return MNV_EINVAL;
   return MNV_OK;
 }
@@ -625,13 +803,17 @@ using namespace mnv;
 
 extern "C" {
 
-// Debug / tuning hook (not part of the reference surface): "simt" -> 1 routes GEMM/conv through the
-// SIMT checker kernel; "max_splits" clamps split-K.  Returns the previous value, or -1 for a bad key.
+// Debug / tuning hook (not part of the reference surface).  Keys: "simt" (1 routes GEMM/conv through
+// the SIMT checker kernel), "max_splits" (clamp split-K), "no_tma" (gather B with threads),
+// "no_fwd_bwd" (generic backward-data gather for stride 1).  Returns the previous value, -1 for a bad key.
 __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key, int value) {
   if (!key) return -1;
   std::string k(key);
   if (k == "simt") return g_opt_simt.exchange(value);
   if (k == "max_splits") return g_opt_max_splits.exchange(value);
+  if (k == "no_tma") return g_opt_no_tma.exchange(value);
+  if (k == "no_fwd_bwd") return g_opt_no_fwd_bwd.exchange(value);
+  if (k == "no_ktab") return g_opt_no_ktab.exchange(value);
   return -1;
 }
 
@@ -682,21 +864,33 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
   size_t wt_bytes = (static_cast<size_t>(Co) * Ci * fh * fw * sizeof(float) + 255) / 256 * 256;
   if (!workspace || workspace_bytes < wt_bytes) return MNV_EWORKSPACE;
   float* wt = static_cast<float*>(workspace);
-  filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(filter, wt, Co, Ci, fh * fw);
+  const int Ho = (H + 2 * ph - fh) / sv + 1, Wo = (W + 2 * pw - fw) / sh + 1;
+  // stride 1: backward-data == forward convolution of top_diff with the swapped, 180-degree-rotated
+  // filter and pad' = f-1-pad, so it runs on the (fast) forward gather.
+  const bool as_forward = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && !g_opt_no_fwd_bwd.load();
+  filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(
+      filter, wt, Co, Ci, fh * fw, as_forward ? 1 : 0);
   rc = finish_launch();
   if (rc) return rc;
   GemmParams p;
   zero_conv(p);
-  p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
-  p.Ho = (H + 2 * ph - fh) / sv + 1; p.Wo = (W + 2 * pw - fw) / sh + 1;
   long long M = static_cast<long long>(N) * H * W, K = static_cast<long long>(Co) * fh * fw;
-  if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Co * p.Ho * p.Wo)) return MNV_EUNSUPPORTED;
+  if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Co * Ho * Wo)) return MNV_EUNSUPPORTED;
   p.a = top_diff; p.b = wt; p.out = bottom_diff;
   p.M = static_cast<int>(M); p.N = Ci; p.K = static_cast<int>(K);
   p.ldb = p.K; p.b_vec = (p.K % 4 == 0);
   p.P = H * W; p.img_stride = static_cast<long long>(Ci) * p.P; p.col_stride = p.P;
-  return launch_gemm<A_IM2COL_BWD, B_KMAJOR>(p, static_cast<uint8_t*>(workspace) + wt_bytes, workspace_bytes - wt_bytes,
-                                             as_stream(stream));
+  p.fh = fh; p.fw = fw;
+  void* ws2 = static_cast<uint8_t*>(workspace) + wt_bytes;
+  size_t ws2_bytes = workspace_bytes - wt_bytes;
+  if (as_forward) {
+    // forward-gather view: source = top_diff (Co channels, Ho x Wo), output pixels = bottom (H x W)
+    p.Ci = Co; p.Co = Ci; p.H = Ho; p.W = Wo; p.Ho = H; p.Wo = W;
+    p.ph = fh - 1 - ph; p.pw = fw - 1 - pw; p.sv = 1; p.sh = 1;
+    return launch_gemm<A_IM2COL_FWD, B_KMAJOR>(p, ws2, ws2_bytes, as_stream(stream));
+  }
+  p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
+  return launch_gemm<A_IM2COL_BWD, B_KMAJOR>(p, ws2, ws2_bytes, as_stream(stream));
 }
 
 int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
