@@ -346,7 +346,7 @@ int mnv_abi_version(void) { return 1; }
 const char* mnv_build_info(void) {
   return "minerva_b200 kernels: sm_100a, nvcc " __VERSION__ ", built " __DATE__;
 }
-size_t mnv_workspace_bytes_hint(void) { return static_cast<size_t>(256) << 20; }
+size_t mnv_workspace_bytes_hint(void) { return static_cast<size_t>(768) << 20; }
 uint64_t mnv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

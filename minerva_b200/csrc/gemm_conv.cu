@@ -20,11 +20,13 @@
 // NCHW has no TMA-friendly im2col, so operands are gathered by producer warps with coalesced
 // LDG (lanes run along the contiguous axis of the source), rounded to TF32 (cvt.rna), and stored
 // with conflict-free 128-bit STS into the swizzled tile; fence.proxy.async + mbarrier hands the
-// stage to the single MMA-issuing thread.  Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
+// stage to the single MMA-issuing thread.  Warp roles (704 threads, 1 CTA/SM, persistent over tiles):
 //   warps 0-3  epilogue: tcgen05.ld 32x32b -> +bias -> coalesced STG (lane = row m)
 //   warp  4    TMEM alloc/dealloc; lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 + tcgen05.commit
-//   warp  5    idle (keeps epilogue warps at warp_id % 4 == TMEM lane quadrant)
-//   warps 6-13 producers (256 threads): A tile 128x32, B tile bn x 32 per stage, 4-stage ring
+//   warp  5    TMA producer for B when B is a plain K-major matrix (cp.async.bulk.tensor, 128B swizzle)
+//   warps 6-21 gather producers (512 threads = 4 warps per SM sub-partition: the gathers are
+//              issue-bound, so thread-level parallelism matters): A tile 128x32 (+ B when it is not
+//              TMA-able) per stage, 4-stage ring, 2-stage register look-ahead
 // Split-K (needs the caller's workspace) keeps all 148 SMs busy when M*N has few tiles (FC layers,
 // backward-filter); partials are folded in split order by a second kernel => deterministic.
 #include <cuda.h>
@@ -58,6 +60,7 @@ struct GemmParams {
   // tiling
   int bn, m_tiles, n_tiles, splits, stages_per_split, k_stages;
   int use_ktab;         // A_IM2COL_FWD: k -> (offset, kh, kw) table in shared memory
+  int spi;              // backward-filter with TMA-fed top_diff: k-stages per image (K padded per image), else 0
 };
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -67,11 +70,11 @@ constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 4;       // 16 KB
 constexpr int kBBytes = BN_MAX * BK * 4;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kKtabMax = 6144;            // entries of the im2col k-decomposition table (24 KB)
+constexpr int kKtabMax = 8192;            // entries of the im2col k-decomposition table (32 KB)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kKtabMax * 4;
-constexpr int kThreads = 448;
+constexpr int kThreads = 704;
 constexpr int kProducerWarp0 = 6;
-constexpr int kProducerThreads = 256;
+constexpr int kProducerThreads = 512;
 constexpr int kTmemCols = 512;  // two accumulator buffers of 256 fp32 columns
 
 // ------------------------------------------------------------------------------------------------
@@ -242,10 +245,11 @@ struct ARow {           // per-thread, per-tile state of the A gather
   uint32_t mh, mw;      // validity masks over kh / kw (im2col fwd / bwd)
   int h0, w0;           // oh*sv-ph (fwd), h+ph (bwd)
 };
-struct AWgrad {         // KC mapping: 4 rows (taps) per thread
-  int toff[4];          // ci*H*W + (kh-ph)*W + (kw-pw)
-  int dh[4], dw[4];     // kh-ph, kw-pw
-  bool valid[4];
+constexpr int kARows = 2;   // KC mapping: tile rows per thread (128 rows x 8 chunks / 512 threads)
+struct AWgrad {         // KC mapping: kARows rows (taps) per thread
+  int toff[kARows];     // ci*H*W + (kh-ph)*W + (kw-pw)
+  int dh[kARows], dw[kARows];     // kh-ph, kw-pw
+  bool valid[kARows];
 };
 
 template <int AM>
@@ -276,8 +280,8 @@ __device__ __forceinline__ AWgrad a_wgrad_setup(const GemmParams& p, int m_base,
   AWgrad w;
   const int ff = p.fh * p.fw;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int m = m_base + row0 + 32 * i;
+  for (int i = 0; i < kARows; ++i) {
+    int m = m_base + row0 + 64 * i;
     w.valid[i] = m < p.M;
     int mm = w.valid[i] ? m : 0;
     int ci = mm / ff, rs = mm - ci * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
@@ -288,13 +292,13 @@ __device__ __forceinline__ AWgrad a_wgrad_setup(const GemmParams& p, int m_base,
   return w;
 }
 
-// MC mapping: 16 consecutive k starting at k0 for this thread's row
+// MC mapping: 8 consecutive k starting at k0 for this thread's row
 template <int AM>
-__device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, int k0, float (&v)[16]) {
+__device__ __forceinline__ void a_gather8(const GemmParams& p, const ARow& r, int k0, float (&v)[8]) {
   if (AM == A_COLMAJOR) {
     const float* src = p.a + r.base + static_cast<size_t>(k0) * p.lda;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (r.valid && k0 + j < p.K) ? __ldg(src + static_cast<size_t>(j) * p.lda) : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = (r.valid && k0 + j < p.K) ? __ldg(src + static_cast<size_t>(j) * p.lda) : 0.f;
   } else {
     // k = (c, rr, ss) in filter storage order; kh = fh-1-rr, kw = fw-1-ss
     const int ff = p.fh * p.fw;
@@ -305,7 +309,7 @@ __device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, i
       int off = c * HW + kh * p.W + kw;
       const float* src = p.a + r.base;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {  // table-free fallback (K or C*H*W too large for the smem table)
+      for (int j = 0; j < 8; ++j) {  // table-free fallback (K or C*H*W too large for the smem table)
         bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
         v[j] = ok ? __ldg(src + off) : 0.f;
         --kw; --off;
@@ -315,7 +319,7 @@ __device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, i
       const int HoWo = p.Ho * p.Wo;
       const float* src = p.a + r.base;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
         float val = 0.f;
         if (ok) {
@@ -334,12 +338,12 @@ __device__ __forceinline__ void a_gather16(const GemmParams& p, const ARow& r, i
 // offset = c*H*W + kh*W + kw; entries past K carry kh = 31, a bit no row mask ever has (fh <= 31).
 // Row validity is folded into the masks (mh = 0 for rows past M), so one element costs
 // LDS(broadcast) + 3 shifts + LOP3 + address add + predicated LDG, with no branches.
-__device__ __forceinline__ void a_gather16_ktab(const GemmParams& p, const ARow& r, const uint32_t* __restrict__ ktab, int k0,
-                                                float (&v)[16]) {
+__device__ __forceinline__ void a_gather8_ktab(const GemmParams& p, const ARow& r, const uint32_t* __restrict__ ktab, int k0,
+                                               float (&v)[8]) {
   const float* src = p.a + r.base;
   const uint4* t4 = reinterpret_cast<const uint4*>(ktab + k0);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
     uint4 e4 = t4[q];
     const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
@@ -350,21 +354,36 @@ __device__ __forceinline__ void a_gather16_ktab(const GemmParams& p, const ARow&
   }
 }
 
-// KC mapping (backward-filter): this thread's 4 pixels k0..k0+3 for its 4 tap rows; v[4*i + e]
-__device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad& w, int k0, float (&v)[16]) {
+// KC mapping (backward-filter): this thread's 4 pixels for its kARows tap rows; v[4*i + e].
+// spi == 0: k = (img, oh, ow) flat, k0 = ks*32 + kq*4.  spi > 0 (top_diff comes by TMA): every image's
+// pixels are padded to spi*32, so a k-stage never straddles two images.
+__device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad& w, int ks, int kq, float (&v)[8]) {
   const int HoWo = p.Ho * p.Wo;
-  int img = k0 / HoWo, pix = k0 - img * HoWo, oh = pix / p.Wo, ow = pix - oh * p.Wo;
+  int img, pix;
+  bool in_k;
+  if (p.spi > 0) {
+    img = ks / p.spi;
+    pix = (ks - img * p.spi) * BK + kq * 4;
+    in_k = true;
+  } else {
+    int k0 = ks * BK + kq * 4;
+    img = k0 / HoWo;
+    pix = k0 - img * HoWo;
+    in_k = false;
+  }
+  int oh = pix / p.Wo, ow = pix - oh * p.Wo;
   long long uoff[4];
   int ohs[4], ows[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    ohs[e] = (k0 + e < p.K) ? oh * p.sv : -(1 << 28);   // out-of-range k fails the bounds test below
+    bool ok = in_k ? (pix + e < HoWo) : (ks * BK + kq * 4 + e < p.K);
+    ohs[e] = ok ? oh * p.sv : -(1 << 28);   // out-of-range k fails the bounds test below
     ows[e] = ow * p.sh;
     uoff[e] = static_cast<long long>(img) * p.Ci * p.H * p.W + static_cast<long long>(oh * p.sv) * p.W + ow * p.sh;
     if (++ow == p.Wo) { ow = 0; if (++oh == p.Ho) { oh = 0; ++img; } }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kARows; ++i) {
     const float* src = p.a + w.toff[i];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -377,12 +396,12 @@ __device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad
 
 // B gathered by threads: `iters` chunks (rows b_row0 + 32*i, column chunk kq) of 4 consecutive k
 template <int BMD>
-__device__ __forceinline__ void b_gather(const GemmParams& p, int n_base, int b_row0, int iters, int k0, float4 (&vb)[8]) {
+__device__ __forceinline__ void b_gather(const GemmParams& p, int n_base, int b_row0, int iters, int k0, float4 (&vb)[4]) {
   if (BMD == B_KMAJOR) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       if (i >= iters) break;
-      int row = b_row0 + 32 * i, n = n_base + row;
+      int row = b_row0 + 64 * i, n = n_base + row;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < p.bn && n < p.N && k0 < p.K) {
         const float* src = p.b + static_cast<size_t>(n) * p.ldb + k0;
@@ -409,9 +428,9 @@ __device__ __forceinline__ void b_gather(const GemmParams& p, int n_base, int b_
       if (++pix == hw) { pix = 0; ++img; }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       if (i >= iters) break;
-      int row = b_row0 + 32 * i, n = n_base + row;
+      int row = b_row0 + 64 * i, n = n_base + row;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < p.bn && n < p.N) {
         const float* src = p.b + static_cast<size_t>(n) * hw;
@@ -435,6 +454,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 
@@ -575,7 +601,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
         for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
-          tma_load_2d(smem_base + stage * kStageBytes + kABytes, &tmap_b, full0 + 8 * stage, ks * BK, t.nt * p.bn);
+          const uint32_t dst = smem_base + stage * kStageBytes + kABytes;
+          if (p.spi > 0) {   // top_diff as (pixel, channel, image): one image's 32-pixel slab per stage
+            int img = ks / p.spi;
+            tma_load_3d(dst, &tmap_b, full0 + 8 * stage, (ks - img * p.spi) * BK, t.nt * p.bn, img);
+          } else {
+            tma_load_2d(dst, &tmap_b, full0 + 8 * stage, ks * BK, t.nt * p.bn);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -583,41 +615,42 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     __syncwarp();
   } else {
     // ===================== gather producers =====================
-    constexpr int LOOK = BTMA ? 2 : 1;                   // register look-ahead in k-stages
-    const int pt = threadIdx.x - kProducerWarp0 * 32;   // 0..255
-    const int a_row = pt & 127, a_half = pt >> 7;       // MC mapping: 16 consecutive k: [a_half*16, +16)
-    const int b_kq = pt & 7, b_row0 = pt >> 3;          // KC mapping: rows b_row0 + 32*i, chunk column b_kq
-    const int b_iters = (p.bn + 31) / 32;               // <= 8
+    constexpr int LOOK = (AM == A_IM2COL_WGRAD && !BTMA) ? 1 : 2;   // register look-ahead in k-stages (gathered wgrad stages A and B: 1 to stay spill-free)
+    const int pt = threadIdx.x - kProducerWarp0 * 32;   // 0..511
+    const int a_row = pt & 127, a_q = pt >> 7;          // MC mapping: 8 consecutive k: [a_q*8, +8)
+    const int b_kq = pt & 7, b_row0 = pt >> 3;          // KC mapping: rows b_row0 + 64*i, chunk column b_kq
+    const int b_iters = (p.bn + 63) / 64;               // <= 4
     int stage = 0; uint32_t phase = 0;
-    float va[LOOK][16];
-    float4 vb[BTMA ? 1 : LOOK][8];
+    float va[LOOK][8];
+    float4 vb[BTMA ? 1 : LOOK][4];
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
       ARow arow;
       AWgrad awg;
       if (AM == A_IM2COL_WGRAD) awg = a_wgrad_setup(p, t.mt * BM, b_row0);
       else arow = a_row_setup<AM>(p, t.mt * BM + a_row);
+      if (AM == A_IM2COL_FWD && !arow.valid) arow.mh = 0;   // rows past M: every tap masked
       const int n_base = t.nt * p.bn;
       auto load = [&](int l, int ks) {
-        if (AM == A_IM2COL_WGRAD) a_gather_wgrad(p, awg, ks * BK + b_kq * 4, va[l]);
-        else if (AM == A_IM2COL_FWD && p.use_ktab) a_gather16_ktab(p, arow, ktab, ks * BK + a_half * 16, va[l]);
-        else a_gather16<AM>(p, arow, ks * BK + a_half * 16, va[l]);
+        if (AM == A_IM2COL_WGRAD) a_gather_wgrad(p, awg, ks, b_kq, va[l]);
+        else if (AM == A_IM2COL_FWD && p.use_ktab) a_gather8_ktab(p, arow, ktab, ks * BK + a_q * 8, va[l]);
+        else a_gather8<AM>(p, arow, ks * BK + a_q * 8, va[l]);
         if (!BTMA) b_gather<BMD>(p, n_base, b_row0, b_iters, ks * BK + b_kq * 4, vb[BTMA ? 0 : l]);
       };
       auto store = [&](int l) {
         uint8_t* a_tile = smem + stage * kStageBytes;
         uint8_t* b_tile = a_tile + kABytes;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           float4 w = make_float4(to_tf32(va[l][4 * q]), to_tf32(va[l][4 * q + 1]), to_tf32(va[l][4 * q + 2]), to_tf32(va[l][4 * q + 3]));
-          uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(b_row0 + 32 * q, b_kq) : sw128_off(a_row, a_half * 4 + q);
+          uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(b_row0 + 64 * q, b_kq) : sw128_off(a_row, a_q * 2 + q);
           *reinterpret_cast<float4*>(a_tile + off) = w;
         }
         if (!BTMA) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             if (i >= b_iters) break;
-            int row = b_row0 + 32 * i;
+            int row = b_row0 + 64 * i;
             if (row < p.bn) {
               const float4& s4 = vb[BTMA ? 0 : l][i];
               *reinterpret_cast<float4*>(b_tile + sw128_off(row, b_kq)) = make_float4(to_tf32(s4.x), to_tf32(s4.y), to_tf32(s4.z), to_tf32(s4.w));
@@ -714,6 +747,34 @@ static bool make_b_tmap(CUtensorMap* tm, const float* b, int rows, int K, int ld
   return r == CUDA_SUCCESS;
 }
 
+// top_diff[img][co][pitch] (pitch % 4 == 0, only the first P pixels of a row are real) as a 3-D tensor;
+// box = 32 pixels x bn channels x 1 image.  Pixels past P are out of bounds => zero-filled.
+static bool make_dy_tmap(CUtensorMap* tm, const float* dy, int P, int pitch, int Co, int N, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(P), static_cast<cuuint64_t>(Co), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * sizeof(float), static_cast<cuuint64_t>(pitch) * Co * sizeof(float)};
+  cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(bn), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dy), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// row-pitch repack for TMA: dst[r][0..inner) = src[r][0..inner), dst rows `pitch` floats apart
+__global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int inner, int pitch, size_t rows) {
+  // one warp per row keeps both sides coalesced without integer division
+  size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+  int lane = threadIdx.x & 31;
+  for (size_t r = warp; r < rows; r += nwarps) {
+    const float* s = src + r * inner;
+    float* d = dst + r * pitch;
+    for (int i = lane; i < inner; i += 32) d[i] = __ldg(s + i);
+  }
+}
+
 static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials) {
   p.m_tiles = (p.M + BM - 1) / BM;
   int n_tiles = (p.N + BN_MAX - 1) / BN_MAX;
@@ -784,7 +845,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0;
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0;
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -904,12 +965,50 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
   zero_conv(p);
   p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
   p.Ho = (H + 2 * ph - fh) / sv + 1; p.Wo = (W + 2 * pw - fw) / sh + 1;
-  long long M = static_cast<long long>(Ci) * fh * fw, K = static_cast<long long>(N) * p.Ho * p.Wo;
+  const int P = p.Ho * p.Wo;
+  long long M = static_cast<long long>(Ci) * fh * fw, K = static_cast<long long>(N) * P;
   if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Ci * H * W)) return MNV_EUNSUPPORTED;
   p.a = bottom; p.b = top_diff; p.out = filter_diff;
   p.M = static_cast<int>(M); p.N = Co; p.K = static_cast<int>(K);
   p.P = p.M; p.img_stride = 0; p.col_stride = p.M;  // filter_diff[co][(ci,r,s)]
-  return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, as_stream(stream));
+  cudaStream_t s = as_stream(stream);
+  if (g_opt_simt.load() || g_opt_no_tma.load())
+    return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, s);
+
+  // TMA-fed top_diff: rows must be 16-byte pitched.  When Ho*Wo % 4 != 0 the tensor is re-pitched
+  // into the workspace first (one streaming pass, << the GEMM).  Each image's pixel range is padded to
+  // a whole number of 32-pixel k-stages so a TMA box never straddles two images.
+  const int pitch = (P + 3) / 4 * 4;
+  const float* dy_tma = top_diff;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  size_t ws_left = workspace ? workspace_bytes : 0;
+  if (pitch != P || !aligned16(top_diff)) {
+    size_t need = (static_cast<size_t>(N) * Co * pitch * sizeof(float) + 255) / 256 * 256;
+    if (ws_left < need) return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, s);
+    float* packed = reinterpret_cast<float*>(ws);
+    size_t rows = static_cast<size_t>(N) * Co;
+    repitch_kernel<<<stream_grid(rows * 32), kBlock, 0, s>>>(top_diff, packed, P, pitch, rows);
+    rc = finish_launch();
+    if (rc) return rc;
+    dy_tma = packed;
+    ws += need; ws_left -= need;
+  }
+  p.spi = (P + BK - 1) / BK;
+  long long kpad = static_cast<long long>(N) * p.spi * BK;
+  if (!fits_int(kpad)) return MNV_EUNSUPPORTED;
+  p.K = static_cast<int>(kpad);          // k-stages = N * spi; validity is per-pixel inside the gathers
+  plan_tiles(p, ws_left);
+  p.partial = p.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (!make_dy_tmap(&tm, dy_tma, P, pitch, Co, N, p.bn)) {
+    p.spi = 0; p.K = static_cast<int>(K);
+    return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, ws, ws_left, s);
+  }
+  rc = launch_umma<A_IM2COL_WGRAD, B_KMAJOR, true>(p, tm, s);
+  if (rc || p.splits == 1) return rc;
+  splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
+  return finish_launch();
 }
 
 }  // extern "C"

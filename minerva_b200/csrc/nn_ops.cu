@@ -192,6 +192,158 @@ __global__ void __launch_bounds__(kBlock) avgpool_bwd_kernel(const float* __rest
   }
 }
 
+// ---- shared-memory staged variants -------------------------------------------------------------
+// A CTA stages G consecutive (n,c) planes (they are contiguous in NCHW) with coalesced loads, works
+// out of shared memory, and writes its outputs coalesced: every HBM byte is touched exactly once
+// (algorithmic traffic), window re-reads hit shared memory.  G is chosen so that small planes
+// (13x13, 6x6) still give the CTA a few thousand elements per pass.  Index decomposition uses
+// multiply-high by a host-computed reciprocal instead of integer division.
+struct FastDiv {
+  uint32_t d, magic;   // q = umulhi(n, magic) is exact for n*d < 2^32
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = static_cast<uint32_t>(d);
+  f.magic = d == 1 ? 0u : static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(d)) + 1u;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return f.d == 1 ? n : __umulhi(n, f.magic); }
+
+__device__ __forceinline__ void stage_in(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(kBlock) pool_fwd_smem_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, PoolGeom g,
+                                                                int G, FastDiv d_howo, FastDiv d_wo) {
+  extern __shared__ float sm[];
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  const float div = static_cast<float>(g.wh * g.ww);
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    stage_in(sm, x + static_cast<size_t>(p0) * HW, cnt * HW);
+    __syncthreads();
+    float* yp = y + static_cast<size_t>(p0) * HoWo;
+    for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {
+      int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * g.Wo;
+      const float* xp = sm + gq * HW;
+      int h0 = i * g.sv - g.ph, w0 = j * g.sh - g.pw;
+      int hs = max(h0, 0), he = min(h0 + g.wh, g.H), ws = max(w0, 0), we = min(w0 + g.ww, g.W);
+      float acc = IS_MAX ? -CUDART_INF_F : 0.f;
+      for (int h = hs; h < he; ++h)
+        for (int w = ws; w < we; ++w) {
+          float v = xp[h * g.W + w];
+          if (IS_MAX) { if (v > acc) acc = v; } else { acc = __fadd_rn(acc, v); }
+        }
+      yp[o] = IS_MAX ? acc : __fdiv_rn(acc, div);
+    }
+    __syncthreads();
+  }
+}
+
+// same rule as maxpool_bwd_kernel, operands in shared memory
+__global__ void __launch_bounds__(kBlock) maxpool_bwd_smem_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                  const float* __restrict__ dy, float* __restrict__ dx, int planes,
+                                                                  PoolGeom g, int G, FastDiv d_hw, FastDiv d_w, FastDiv d_sv, FastDiv d_sh) {
+  extern __shared__ float sm[];
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  float* sx = sm;
+  float* sy = sm + G * HW;
+  float* sdy = sy + G * HoWo;
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    stage_in(sx, x + static_cast<size_t>(p0) * HW, cnt * HW);
+    stage_in(sy, y + static_cast<size_t>(p0) * HoWo, cnt * HoWo);
+    stage_in(sdy, dy + static_cast<size_t>(p0) * HoWo, cnt * HoWo);
+    __syncthreads();
+    float* dxp = dx + static_cast<size_t>(p0) * HW;
+    for (int e = threadIdx.x; e < cnt * HW; e += blockDim.x) {
+      int gq = fdiv(e, d_hw), r = e - gq * HW, h = fdiv(r, d_w), w = r - h * g.W;
+      const float* xp = sx + gq * HW;
+      const float* yp = sy + gq * HoWo;
+      const float* dyp = sdy + gq * HoWo;
+      float xv = xp[r];
+      int i_lo = fdiv(h + g.ph - g.wh + g.sv, d_sv);
+      if (h + g.ph - g.wh + 1 <= 0) i_lo = 0;
+      int i_hi = min(static_cast<int>(fdiv(h + g.ph, d_sv)), g.Ho - 1);
+      int j_lo = fdiv(w + g.pw - g.ww + g.sh, d_sh);
+      if (w + g.pw - g.ww + 1 <= 0) j_lo = 0;
+      int j_hi = min(static_cast<int>(fdiv(w + g.pw, d_sh)), g.Wo - 1);
+      float acc = 0.f;
+      for (int i = i_lo; i <= i_hi; ++i)
+        for (int j = j_lo; j <= j_hi; ++j) {
+          float top = yp[i * g.Wo + j];
+          if (xv != top) continue;
+          int h0 = i * g.sv - g.ph, w0 = j * g.sh - g.pw;
+          int hs = max(h0, 0), ws = max(w0, 0), we = min(w0 + g.ww, g.W);
+          bool first = true;
+          for (int hh = hs; hh <= h && first; ++hh) {
+            int wend = hh == h ? w : we;
+            for (int wc = ws; wc < wend; ++wc)
+              if (xp[hh * g.W + wc] == top) { first = false; break; }
+          }
+          if (first) acc = __fadd_rn(acc, dyp[i * g.Wo + j]);
+        }
+      dxp[e] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) avgpool_bwd_smem_kernel(const float* __restrict__ dy, float* __restrict__ dx, int planes, PoolGeom g,
+                                                                  int G, FastDiv d_hw, FastDiv d_w, FastDiv d_sv, FastDiv d_sh) {
+  extern __shared__ float sm[];
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  const float div = static_cast<float>(g.wh * g.ww);
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    stage_in(sm, dy + static_cast<size_t>(p0) * HoWo, cnt * HoWo);
+    __syncthreads();
+    float* dxp = dx + static_cast<size_t>(p0) * HW;
+    for (int e = threadIdx.x; e < cnt * HW; e += blockDim.x) {
+      int gq = fdiv(e, d_hw), r = e - gq * HW, h = fdiv(r, d_w), w = r - h * g.W;
+      const float* dyp = sm + gq * HoWo;
+      int i_lo = fdiv(h + g.ph - g.wh + g.sv, d_sv);
+      if (h + g.ph - g.wh + 1 <= 0) i_lo = 0;
+      int i_hi = min(static_cast<int>(fdiv(h + g.ph, d_sv)), g.Ho - 1);
+      int j_lo = fdiv(w + g.pw - g.ww + g.sh, d_sh);
+      if (w + g.pw - g.ww + 1 <= 0) j_lo = 0;
+      int j_hi = min(static_cast<int>(fdiv(w + g.pw, d_sh)), g.Wo - 1);
+      float acc = 0.f;
+      for (int i = i_lo; i <= i_hi; ++i)
+        for (int j = j_lo; j <= j_hi; ++j) acc = __fadd_rn(acc, __fdiv_rn(dyp[i * g.Wo + j], div));
+      dxp[e] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int kPoolSmemMax = 96 * 1024;      // opt-in dynamic shared memory ceiling for the staged kernels
+constexpr int kPoolSmemTarget = 24 * 1024;   // aim: ~6K floats per CTA pass, several CTAs per SM
+
+// planes per CTA pass for `per_plane` floats of staging; 0 => does not fit, use the global-memory kernel
+static int pool_group(size_t per_plane_floats, size_t planes, size_t max_index) {
+  size_t bytes = per_plane_floats * sizeof(float);
+  if (bytes > static_cast<size_t>(kPoolSmemMax)) return 0;
+  size_t G = kPoolSmemTarget / bytes;
+  if (G < 1) G = 1;
+  // keep >= ~4 CTAs per SM busy and the fast-division precondition n*d < 2^32
+  while (G > 1 && (planes / G < static_cast<size_t>(kNumSMs) * 4 || G * max_index * max_index >= (1ull << 32))) --G;
+  if (max_index * max_index * G >= (1ull << 32)) return 0;
+  return static_cast<int>(G);
+}
+template <class K>
+static int pool_smem_attr(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return MNV_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemMax);
+  return e == cudaSuccess ? MNV_OK : static_cast<int>(e);
+}
+static int pool_grid(size_t planes, int G) {
+  size_t groups = (planes + G - 1) / G;
+  size_t cap = static_cast<size_t>(kNumSMs) * kBlocksPerSM;
+  return static_cast<int>(groups < cap ? groups : cap);
+}
+
 static int make_geom(PoolGeom* g, int N, int C, int H, int W, int sv, int sh, int wh, int ww, int ph, int pw) {
   if (N < 0 || C < 0 || H <= 0 || W <= 0 || sv <= 0 || sh <= 0 || wh <= 0 || ww <= 0 || ph < 0 || pw < 0)
     return MNV_EINVAL;
@@ -235,9 +387,24 @@ __global__ void bias_grad_final_kernel(const float* __restrict__ partial, float*
 // the restated oracle; scale and output are produced in one pass (the reference used two kernels
 // and re-read bottom and scale from HBM).
 // ------------------------------------------------------------------------------------------------
+// scale^(-beta): beta = 0.75 (AlexNet, GoogLeNet) is rsqrt(s) * sqrt(rsqrt(s)), three SFU ops instead of
+// a ~40-instruction powf; any other beta takes powf.  Both are within a few ulp of the oracle's powf.
+template <bool BETA075>
+__device__ __forceinline__ float pow_neg_beta(float s, float neg_beta) {
+  if (BETA075) {
+    float r = rsqrtf(s);
+    return __fmul_rn(r, sqrtf(r));
+  }
+  return powf(s, neg_beta);
+}
+
+// SIZE > 0: compile-time window with the squares kept in a register ring (no re-load of the element
+// leaving the window); SIZE == 0: generic window, re-loads from L1/L2.
+template <int SIZE, bool BETA075>
 __global__ void __launch_bounds__(kBlock) lrn_fwd_kernel(const float* __restrict__ in, float* __restrict__ scale, float* __restrict__ out,
-                                                         int num, int C, size_t step, int size, float alpha_over_size, float neg_beta) {
+                                                         int num, int C, size_t step, int size_rt, float alpha_over_size, float neg_beta) {
   size_t total = static_cast<size_t>(num) * step;
+  const int size = SIZE > 0 ? SIZE : size_rt;
   const int pre_pad = (size - 1) / 2, post_pad = size - pre_pad - 1;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -246,25 +413,58 @@ __global__ void __launch_bounds__(kBlock) lrn_fwd_kernel(const float* __restrict
     float* ssc = scale + off;
     float* sout = out + off;
     float acc = 0.f;
+    float sq[SIZE > 0 ? SIZE : 1];   // squares of the last SIZE inputs
+    float xv[SIZE > 0 ? SIZE : 1];   // and the inputs themselves (the output channel trails the head by post_pad)
     // head runs ahead of the output channel o = head - post_pad
-    for (int head = 0; head < C + post_pad; ++head) {
-      if (head < C) { float v = __ldg(sin + head * step); acc = __fadd_rn(acc, __fmul_rn(v, v)); }
-      if (head >= size) { float v = __ldg(sin + (head - size) * step); acc = __fsub_rn(acc, __fmul_rn(v, v)); }
-      int o = head - post_pad;
-      if (o >= 0) {
-        float sc = static_cast<float>(1.0 + static_cast<double>(__fmul_rn(acc, alpha_over_size)));
-        ssc[o * step] = sc;
-        sout[o * step] = __fmul_rn(__ldg(sin + o * step), powf(sc, neg_beta));
+    for (int head0 = 0; head0 < C + post_pad; head0 += (SIZE > 0 ? SIZE : 1)) {
+#pragma unroll
+      for (int u = 0; u < (SIZE > 0 ? SIZE : 1); ++u) {
+        int head = head0 + u;
+        if (head >= C + post_pad) break;
+        if (head >= size) {
+          float old = SIZE > 0 ? sq[u] : 0.f;
+          if (SIZE == 0) { float v = __ldg(sin + (head - size) * step); old = __fmul_rn(v, v); }
+          // subtraction happens AFTER this step's addition in the reference; keep that order below
+          float add = 0.f, xin = 0.f;
+          if (head < C) { xin = __ldg(sin + head * step); add = __fmul_rn(xin, xin); acc = __fadd_rn(acc, add); }
+          acc = __fsub_rn(acc, old);
+          if (SIZE > 0) { sq[u] = add; xv[u] = xin; }
+        } else if (head < C) {
+          float xin = __ldg(sin + head * step);
+          float add = __fmul_rn(xin, xin);
+          acc = __fadd_rn(acc, add);
+          if (SIZE > 0) { sq[u] = add; xv[u] = xin; }
+        }
+        int o = head - post_pad;
+        if (o >= 0) {
+          // (float)(1. + (double)t) == fadd_rn(1.0f, t): the double sum of two floats is exact, so both round once
+          float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
+          float xo;
+          if (SIZE > 0) {
+            // element o sits post_pad slots behind the head in the ring
+            int slot = u - post_pad;
+            if (slot < 0) slot += SIZE;
+            xo = xv[0];
+#pragma unroll
+            for (int q = 1; q < SIZE; ++q) if (slot == q) xo = xv[q];
+          } else {
+            xo = __ldg(sin + o * step);
+          }
+          ssc[o * step] = sc;
+          sout[o * step] = __fmul_rn(xo, pow_neg_beta<BETA075>(sc, neg_beta));
+        }
       }
     }
   }
 }
 
+template <int SIZE, bool BETA075>
 __global__ void __launch_bounds__(kBlock) lrn_bwd_kernel(const float* __restrict__ bottom, const float* __restrict__ top,
                                                          const float* __restrict__ scale, const float* __restrict__ top_diff,
-                                                         float* __restrict__ bottom_diff, int num, int C, size_t step, int size,
+                                                         float* __restrict__ bottom_diff, int num, int C, size_t step, int size_rt,
                                                          float neg_beta, float cache_ratio) {
   size_t total = static_cast<size_t>(num) * step;
+  const int size = SIZE > 0 ? SIZE : size_rt;
   const int pre_pad = size - (size + 1) / 2, post_pad = size - pre_pad - 1;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -275,24 +475,62 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd_kernel(const float* __restrict
     const float* td = top_diff + off;
     float* bd = bottom_diff + off;
     float acc = 0.f;
-    for (int head = 0; head < C + post_pad; ++head) {
-      if (head < C) {
-        size_t o = head * step;
-        acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(__ldg(td + o), __ldg(tp + o)), __ldg(s + o)));
-      }
-      if (head >= size) {
-        size_t o = (head - size) * step;
-        acc = __fsub_rn(acc, __fdiv_rn(__fmul_rn(__ldg(td + o), __ldg(tp + o)), __ldg(s + o)));
-      }
-      int oc = head - post_pad;
-      if (oc >= 0) {
-        size_t o = oc * step;
-        float lhs = __fmul_rn(__ldg(td + o), powf(__ldg(s + o), neg_beta));
-        float rhs = __fmul_rn(__fmul_rn(cache_ratio, __ldg(b + o)), acc);
-        bd[o] = __fsub_rn(lhs, rhs);
+    float ratio[SIZE > 0 ? SIZE : 1];   // td*top/scale of the last SIZE channels
+    float tdv[SIZE > 0 ? SIZE : 1], scv[SIZE > 0 ? SIZE : 1];
+    for (int head0 = 0; head0 < C + post_pad; head0 += (SIZE > 0 ? SIZE : 1)) {
+#pragma unroll
+      for (int u = 0; u < (SIZE > 0 ? SIZE : 1); ++u) {
+        int head = head0 + u;
+        if (head >= C + post_pad) break;
+        float old = 0.f;
+        if (head >= size) {
+          if (SIZE > 0) old = ratio[u];
+          else { size_t o = (head - size) * step; old = __fdiv_rn(__fmul_rn(__ldg(td + o), __ldg(tp + o)), __ldg(s + o)); }
+        }
+        if (head < C) {
+          size_t o = head * step;
+          float tdh = __ldg(td + o), sch = __ldg(s + o);
+          float r = __fdiv_rn(__fmul_rn(tdh, __ldg(tp + o)), sch);
+          acc = __fadd_rn(acc, r);
+          if (SIZE > 0) { ratio[u] = r; tdv[u] = tdh; scv[u] = sch; }
+        }
+        if (head >= size) acc = __fsub_rn(acc, old);
+        int oc = head - post_pad;
+        if (oc >= 0) {
+          size_t o = oc * step;
+          float tdo, sco;
+          if (SIZE > 0) {
+            int slot = u - post_pad;
+            if (slot < 0) slot += SIZE;
+            tdo = tdv[0]; sco = scv[0];
+#pragma unroll
+            for (int q = 1; q < SIZE; ++q) if (slot == q) { tdo = tdv[q]; sco = scv[q]; }
+          } else {
+            tdo = __ldg(td + o); sco = __ldg(s + o);
+          }
+          float lhs = __fmul_rn(tdo, pow_neg_beta<BETA075>(sco, neg_beta));
+          float rhs = __fmul_rn(__fmul_rn(cache_ratio, __ldg(b + o)), acc);
+          bd[o] = __fsub_rn(lhs, rhs);
+        }
       }
     }
   }
+}
+
+template <bool IS_MAX>
+static int launch_pool_fwd(const float* x, float* y, size_t planes, const PoolGeom& g, cudaStream_t s) {
+  size_t per = static_cast<size_t>(g.H) * g.W;
+  int G = planes < 0x7fffffff ? pool_group(per, planes, per) : 0;
+  if (G > 0) {
+    size_t bytes = per * G * sizeof(float);
+    int rc = pool_smem_attr(pool_fwd_smem_kernel<IS_MAX>, bytes);
+    if (rc) return rc;
+    pool_fwd_smem_kernel<IS_MAX><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
+                                                                            make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
+    return finish_launch();
+  }
+  pool_fwd_kernel<IS_MAX><<<stream_grid(planes * g.Ho * g.Wo), kBlock, 0, s>>>(x, y, planes, g);
+  return finish_launch();
 }
 
 }  // namespace mnv
@@ -344,8 +582,7 @@ int mnv_max_pooling_forward(const float* x, float* y, int N, int C, int H, int W
   size_t planes = static_cast<size_t>(N) * C;
   if (planes == 0) return MNV_OK;
   if (!x || !y) return MNV_EINVAL;
-  pool_fwd_kernel<true><<<stream_grid(planes * g.Ho * g.Wo), kBlock, 0, as_stream(s)>>>(x, y, planes, g);
-  return finish_launch();
+  return launch_pool_fwd<true>(x, y, planes, g, as_stream(s));
 }
 int mnv_average_pooling_forward(const float* x, float* y, int N, int C, int H, int W, int sv, int sh, int wh,
                                 int ww, int ph, int pw, mnv_stream_t s) {
@@ -355,8 +592,7 @@ int mnv_average_pooling_forward(const float* x, float* y, int N, int C, int H, i
   size_t planes = static_cast<size_t>(N) * C;
   if (planes == 0) return MNV_OK;
   if (!x || !y) return MNV_EINVAL;
-  pool_fwd_kernel<false><<<stream_grid(planes * g.Ho * g.Wo), kBlock, 0, as_stream(s)>>>(x, y, planes, g);
-  return finish_launch();
+  return launch_pool_fwd<false>(x, y, planes, g, as_stream(s));
 }
 int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
                              int W, int sv, int sh, int wh, int ww, int ph, int pw, mnv_stream_t s) {
@@ -366,6 +602,18 @@ int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, fl
   size_t planes = static_cast<size_t>(N) * C;
   if (planes == 0) return MNV_OK;
   if (!x || !y || !dy || !dx) return MNV_EINVAL;
+  {
+    size_t per = static_cast<size_t>(H) * W + 2 * static_cast<size_t>(g.Ho) * g.Wo;
+    int G = planes < 0x7fffffff ? pool_group(per, planes, static_cast<size_t>(H) * W) : 0;
+    if (G > 0) {
+      size_t bytes = per * G * sizeof(float);
+      rc = pool_smem_attr(maxpool_bwd_smem_kernel, bytes);
+      if (rc) return rc;
+      maxpool_bwd_smem_kernel<<<pool_grid(planes, G), kBlock, bytes, as_stream(s)>>>(x, y, dy, dx, static_cast<int>(planes), g, G,
+                                                                                  make_fastdiv(H * W), make_fastdiv(W), make_fastdiv(sv), make_fastdiv(sh));
+      return finish_launch();
+    }
+  }
   maxpool_bwd_kernel<<<stream_grid(planes * H * W), kBlock, 0, as_stream(s)>>>(x, y, dy, dx, planes, g);
   return finish_launch();
 }
@@ -378,6 +626,18 @@ int mnv_average_pooling_backward(const float* x, const float* y, const float* dy
   size_t planes = static_cast<size_t>(N) * C;
   if (planes == 0) return MNV_OK;
   if (!dy || !dx) return MNV_EINVAL;
+  {
+    size_t per = static_cast<size_t>(g.Ho) * g.Wo;
+    int G = planes < 0x7fffffff ? pool_group(per, planes, static_cast<size_t>(H) * W) : 0;
+    if (G > 0) {
+      size_t bytes = per * G * sizeof(float);
+      rc = pool_smem_attr(avgpool_bwd_smem_kernel, bytes);
+      if (rc) return rc;
+      avgpool_bwd_smem_kernel<<<pool_grid(planes, G), kBlock, bytes, as_stream(s)>>>(dy, dx, static_cast<int>(planes), g, G,
+                                                                                  make_fastdiv(H * W), make_fastdiv(W), make_fastdiv(sv), make_fastdiv(sh));
+      return finish_launch();
+    }
+  }
   avgpool_bwd_kernel<<<stream_grid(planes * H * W), kBlock, 0, as_stream(s)>>>(dy, dx, planes, g);
   return finish_launch();
 }
@@ -411,8 +671,16 @@ int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_siz
   size_t step = static_cast<size_t>(width) * height, work = step * num_img;
   if (work == 0 || channel == 0) return MNV_OK;
   if (!bottom || !scale || !res) return MNV_EINVAL;
-  lrn_fwd_kernel<<<stream_grid(work), kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size,
-                                                               alpha / local_size, -beta);
+  const float aos = alpha / local_size;
+  const bool b075 = beta == 0.75f;
+  const int grid = stream_grid(work);
+  if (local_size == 5 && channel >= 5) {
+    if (b075) lrn_fwd_kernel<5, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, 5, aos, -beta);
+    else lrn_fwd_kernel<5, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, 5, aos, -beta);
+  } else {
+    if (b075) lrn_fwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
+    else lrn_fwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
+  }
   return finish_launch();
 }
 int mnv_lrn_backward(const float* bottom_data, const float* top_data, const float* scale, const float* top_diff,
@@ -423,8 +691,15 @@ int mnv_lrn_backward(const float* bottom_data, const float* top_data, const floa
   if (work == 0 || channel == 0) return MNV_OK;
   if (!bottom_data || !top_data || !scale || !top_diff || !bottom_diff) return MNV_EINVAL;
   float cache_ratio = static_cast<float>(2. * alpha * beta / local_size);  // cuda_perform.cu:665
-  lrn_bwd_kernel<<<stream_grid(work), kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img,
-                                                               channel, step, local_size, -beta, cache_ratio);
+  const bool b075 = beta == 0.75f;
+  const int grid = stream_grid(work);
+  if (local_size == 5 && channel >= 5) {
+    if (b075) lrn_bwd_kernel<5, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, 5, -beta, cache_ratio);
+    else lrn_bwd_kernel<5, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, 5, -beta, cache_ratio);
+  } else {
+    if (b075) lrn_bwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
+    else lrn_bwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
+  }
   return finish_launch();
 }
 

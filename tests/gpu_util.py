@@ -31,7 +31,7 @@ def run(name, *args):
 _ws = None
 
 
-def workspace(nbytes=256 << 20):
+def workspace(nbytes=768 << 20):
     global _ws
     if _ws is None or _ws.numel() < nbytes:
         _ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")

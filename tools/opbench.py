@@ -33,7 +33,7 @@ TF32 = peaks["bf16_tflops"] / 2.0   # dense TF32 tensor peak = half the (measure
 
 st = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-ws = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+ws = torch.empty(lib.mnv_workspace_bytes_hint(), dtype=torch.uint8, device="cuda")
 B = args.batch
 
 
