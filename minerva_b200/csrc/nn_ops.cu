@@ -209,8 +209,20 @@ static inline FastDiv make_fastdiv(int d) {
 }
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return f.d == 1 ? n : __umulhi(n, f.magic); }
 
+// Copy n floats global -> shared.  `dst` must satisfy (dst index) == (src index) mod 4 in units of
+// floats relative to 16-byte boundaries (callers offset the smem base by the source misalignment), so
+// the body moves 128-bit vectors on both sides; at most 3 scalars at either end.
+__device__ __forceinline__ int misalign4(const float* p) { return static_cast<int>((reinterpret_cast<uintptr_t>(p) >> 2) & 3u); }
 __device__ __forceinline__ void stage_in(float* __restrict__ dst, const float* __restrict__ src, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+  int head = (4 - misalign4(src)) & 3;
+  if (head > n) head = n;
+  if (static_cast<int>(threadIdx.x) < head) dst[threadIdx.x] = __ldg(src + threadIdx.x);
+  int n4 = (n - head) >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src + head);
+  float4* d4 = reinterpret_cast<float4*>(dst + head);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  int done = head + (n4 << 2);
+  if (static_cast<int>(threadIdx.x) < n - done) dst[done + threadIdx.x] = __ldg(src + done + threadIdx.x);
 }
 
 template <bool IS_MAX>
@@ -221,12 +233,14 @@ __global__ void __launch_bounds__(kBlock) pool_fwd_smem_kernel(const float* __re
   const float div = static_cast<float>(g.wh * g.ww);
   for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
     const int cnt = min(G, planes - p0);
-    stage_in(sm, x + static_cast<size_t>(p0) * HW, cnt * HW);
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    float* sx = sm + misalign4(xsrc);
+    stage_in(sx, xsrc, cnt * HW);
     __syncthreads();
     float* yp = y + static_cast<size_t>(p0) * HoWo;
     for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {
       int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * g.Wo;
-      const float* xp = sm + gq * HW;
+      const float* xp = sx + gq * HW;
       int h0 = i * g.sv - g.ph, w0 = j * g.sh - g.pw;
       int hs = max(h0, 0), he = min(h0 + g.wh, g.H), ws = max(w0, 0), we = min(w0 + g.ww, g.W);
       float acc = IS_MAX ? -CUDART_INF_F : 0.f;
@@ -241,49 +255,75 @@ __global__ void __launch_bounds__(kBlock) pool_fwd_smem_kernel(const float* __re
   }
 }
 
-// same rule as maxpool_bwd_kernel, operands in shared memory
-__global__ void __launch_bounds__(kBlock) maxpool_bwd_smem_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                                  const float* __restrict__ dy, float* __restrict__ dx, int planes,
-                                                                  PoolGeom g, int G, FastDiv d_hw, FastDiv d_w, FastDiv d_sv, FastDiv d_sh) {
+// Max backward, two phases per staged plane group (same rule as maxpool_bwd_kernel, bit-identical):
+//  A. one thread per window: argmax position (first maximum in h-major, w-minor scan) -> arg[] in smem;
+//  B. one thread per bottom element: sum, in (i-major, j-minor) window order, of dy over the windows whose
+//     argmax is this element.  No float equality tests, `top` is not read (4*E_out bytes less traffic).
+// WH/WW/SV/SH > 0 are compile-time window/stride (3x3/2, 2x2/2, 3x3/3, 3x3/1: divisions become shifts,
+// loops unroll); 0 = run-time geometry.
+template <int WH, int WW, int SV, int SH>
+__global__ void __launch_bounds__(kBlock) maxpool_bwd_smem_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  float* __restrict__ dx, int planes, PoolGeom g, int G,
+                                                                  FastDiv d_hw, FastDiv d_w, FastDiv d_howo, FastDiv d_wo,
+                                                                  FastDiv d_sv, FastDiv d_sh) {
   extern __shared__ float sm[];
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
-  float* sx = sm;
-  float* sy = sm + G * HW;
-  float* sdy = sy + G * HoWo;
+  const int wh = WH ? WH : g.wh, ww = WW ? WW : g.ww, sv = SV ? SV : g.sv, sh = SH ? SH : g.sh;
+  float* sx_base = sm;                                               // G*HW + 4, rounded to 16 bytes
+  float* sdy_base = sm + ((G * HW + 4 + 3) & ~3);                    // G*HoWo + 4, rounded to 16 bytes
+  int* sarg = reinterpret_cast<int*>(sdy_base + ((G * HoWo + 4 + 3) & ~3));   // G*HoWo
   for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
     const int cnt = min(G, planes - p0);
-    stage_in(sx, x + static_cast<size_t>(p0) * HW, cnt * HW);
-    stage_in(sy, y + static_cast<size_t>(p0) * HoWo, cnt * HoWo);
-    stage_in(sdy, dy + static_cast<size_t>(p0) * HoWo, cnt * HoWo);
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    const float* dysrc = dy + static_cast<size_t>(p0) * HoWo;
+    float* sx = sx_base + misalign4(xsrc);
+    float* sdy = sdy_base + misalign4(dysrc);
+    stage_in(sx, xsrc, cnt * HW);
+    stage_in(sdy, dysrc, cnt * HoWo);
+    __syncthreads();
+    for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {       // phase A
+      int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * g.Wo;
+      const float* xp = sx + gq * HW;
+      int h0 = i * sv - g.ph, w0 = j * sh - g.pw;
+      float best = -CUDART_INF_F;
+      int arg = -1;
+#pragma unroll
+      for (int kh = 0; kh < (WH ? WH : 1); ++kh)
+#pragma unroll
+        for (int kw = 0; kw < (WW ? WW : 1); ++kw) {
+          if (WH) {
+            int h = h0 + kh, w = w0 + kw;
+            if (static_cast<unsigned>(h) < static_cast<unsigned>(g.H) && static_cast<unsigned>(w) < static_cast<unsigned>(g.W)) {
+              float v = xp[h * g.W + w];
+              if (v > best) { best = v; arg = h * g.W + w; }
+            }
+          }
+        }
+      if (!WH) {
+        int hs = max(h0, 0), he = min(h0 + wh, g.H), ws = max(w0, 0), we = min(w0 + ww, g.W);
+        for (int h = hs; h < he; ++h)
+          for (int w = ws; w < we; ++w) {
+            float v = xp[h * g.W + w];
+            if (v > best) { best = v; arg = h * g.W + w; }
+          }
+      }
+      sarg[o] = arg;
+    }
     __syncthreads();
     float* dxp = dx + static_cast<size_t>(p0) * HW;
-    for (int e = threadIdx.x; e < cnt * HW; e += blockDim.x) {
+    for (int e = threadIdx.x; e < cnt * HW; e += blockDim.x) {         // phase B
       int gq = fdiv(e, d_hw), r = e - gq * HW, h = fdiv(r, d_w), w = r - h * g.W;
-      const float* xp = sx + gq * HW;
-      const float* yp = sy + gq * HoWo;
       const float* dyp = sdy + gq * HoWo;
-      float xv = xp[r];
-      int i_lo = fdiv(h + g.ph - g.wh + g.sv, d_sv);
-      if (h + g.ph - g.wh + 1 <= 0) i_lo = 0;
-      int i_hi = min(static_cast<int>(fdiv(h + g.ph, d_sv)), g.Ho - 1);
-      int j_lo = fdiv(w + g.pw - g.ww + g.sh, d_sh);
-      if (w + g.pw - g.ww + 1 <= 0) j_lo = 0;
-      int j_hi = min(static_cast<int>(fdiv(w + g.pw, d_sh)), g.Wo - 1);
+      const int* ap = sarg + gq * HoWo;
+      int hn = h + g.ph, wn = w + g.pw;
+      int i_lo = hn - wh + 1 <= 0 ? 0 : (SV ? (hn - wh + sv) / SV : static_cast<int>(fdiv(hn - wh + sv, d_sv)));
+      int i_hi = min(SV ? hn / SV : static_cast<int>(fdiv(hn, d_sv)), g.Ho - 1);
+      int j_lo = wn - ww + 1 <= 0 ? 0 : (SH ? (wn - ww + sh) / SH : static_cast<int>(fdiv(wn - ww + sh, d_sh)));
+      int j_hi = min(SH ? wn / SH : static_cast<int>(fdiv(wn, d_sh)), g.Wo - 1);
       float acc = 0.f;
       for (int i = i_lo; i <= i_hi; ++i)
-        for (int j = j_lo; j <= j_hi; ++j) {
-          float top = yp[i * g.Wo + j];
-          if (xv != top) continue;
-          int h0 = i * g.sv - g.ph, w0 = j * g.sh - g.pw;
-          int hs = max(h0, 0), ws = max(w0, 0), we = min(w0 + g.ww, g.W);
-          bool first = true;
-          for (int hh = hs; hh <= h && first; ++hh) {
-            int wend = hh == h ? w : we;
-            for (int wc = ws; wc < wend; ++wc)
-              if (xp[hh * g.W + wc] == top) { first = false; break; }
-          }
-          if (first) acc = __fadd_rn(acc, dyp[i * g.Wo + j]);
-        }
+        for (int j = j_lo; j <= j_hi; ++j)
+          if (ap[i * g.Wo + j] == r) acc = __fadd_rn(acc, dyp[i * g.Wo + j]);
       dxp[e] = acc;
     }
     __syncthreads();
@@ -297,12 +337,14 @@ __global__ void __launch_bounds__(kBlock) avgpool_bwd_smem_kernel(const float* _
   const float div = static_cast<float>(g.wh * g.ww);
   for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
     const int cnt = min(G, planes - p0);
-    stage_in(sm, dy + static_cast<size_t>(p0) * HoWo, cnt * HoWo);
+    const float* dysrc = dy + static_cast<size_t>(p0) * HoWo;
+    float* sdy = sm + misalign4(dysrc);
+    stage_in(sdy, dysrc, cnt * HoWo);
     __syncthreads();
     float* dxp = dx + static_cast<size_t>(p0) * HW;
     for (int e = threadIdx.x; e < cnt * HW; e += blockDim.x) {
       int gq = fdiv(e, d_hw), r = e - gq * HW, h = fdiv(r, d_w), w = r - h * g.W;
-      const float* dyp = sm + gq * HoWo;
+      const float* dyp = sm + misalign4(dysrc) + gq * HoWo;
       int i_lo = fdiv(h + g.ph - g.wh + g.sv, d_sv);
       if (h + g.ph - g.wh + 1 <= 0) i_lo = 0;
       int i_hi = min(static_cast<int>(fdiv(h + g.ph, d_sv)), g.Ho - 1);
@@ -365,12 +407,24 @@ __global__ void __launch_bounds__(kBlock) bias_grad_partial_kernel(const float* 
   int c = blockIdx.x, sp = blockIdx.y;
   int n_per = (N + splits - 1) / splits;
   int n0 = sp * n_per, n1 = min(N, n0 + n_per);
-  float acc = 0.f;
-  for (int n = n0; n < n1; ++n) {
-    const float* p = dy + (static_cast<size_t>(n) * C + c) * hw;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) acc += __ldg(p + i);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // independent chains: 4 loads in flight per thread
+  // 4 images at a time (one accumulator each), threads striding the plane: small planes (13x13) still
+  // keep 4 independent loads in flight per thread
+  const size_t img_stride = static_cast<size_t>(C) * hw;
+  const float* base = dy + static_cast<size_t>(c) * hw;
+  int n = n0;
+  for (; n + 3 < n1; n += 4) {
+    const float* p0 = base + n * img_stride;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+      float v0 = __ldg(p0 + i), v1 = __ldg(p0 + img_stride + i), v2 = __ldg(p0 + 2 * img_stride + i), v3 = __ldg(p0 + 3 * img_stride + i);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
   }
-  acc = block_reduce(acc, false, red);
+  for (; n < n1; ++n) {
+    const float* p0 = base + n * img_stride;
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) a0 += __ldg(p0 + i);
+  }
+  float acc = block_reduce((a0 + a1) + (a2 + a3), false, red);
   if (threadIdx.x == 0) partial[static_cast<size_t>(sp) * C + c] = acc;
 }
 __global__ void bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int C, int splits) {
@@ -517,12 +571,122 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd_kernel(const float* __restrict
   }
 }
 
+// ---- local_size == 5 fast path: 8-channel register prefetch ----------------------------------------
+// The channel walk is a serial recurrence per pixel, so the only memory-level parallelism is what a
+// thread keeps in flight itself: the next 8 channels are loaded while the current 8 are consumed.
+// The window lives in shifted registers; adding/subtracting an exact +0.0f outside the valid range keeps
+// the reference's add-then-subtract rounding sequence bit for bit.
+constexpr int kLrnChunk = 8;
+
+template <bool BETA075>
+__global__ void __launch_bounds__(kBlock) lrn_fwd5_kernel(const float* __restrict__ in, float* __restrict__ scale, float* __restrict__ out,
+                                                          int num, int C, size_t step, float alpha_over_size, float neg_beta) {
+  size_t total = static_cast<size_t>(num) * step;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t n = t / step, p = t - n * step, off = n * C * step + p;
+    const float* sin = in + off;
+    float* ssc = scale + off;
+    float* sout = out + off;
+    float cur[kLrnChunk], nxt[kLrnChunk];
+#pragma unroll
+    for (int u = 0; u < kLrnChunk; ++u) cur[u] = u < C ? __ldg(sin + u * step) : 0.f;
+    float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sq4 = 0.f;   // squares of x[head-1..head-5]
+    float x1 = 0.f, x2 = 0.f;                                        // x[head-1], x[head-2]
+    float acc = 0.f;
+    for (int c0 = 0; c0 < C + 2; c0 += kLrnChunk) {
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) {
+        int hn = c0 + kLrnChunk + u;
+        nxt[u] = hn < C ? __ldg(sin + hn * step) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) {
+        int head = c0 + u;
+        float xin = cur[u];                      // 0 past C
+        float add = __fmul_rn(xin, xin);
+        acc = __fadd_rn(acc, add);
+        acc = __fsub_rn(acc, sq4);               // x[head-5]^2, +0 while the window is filling
+        sq4 = sq3; sq3 = sq2; sq2 = sq1; sq1 = sq0; sq0 = add;
+        int o = head - 2;
+        if (o >= 0 && o < C) {
+          float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
+          ssc[o * step] = sc;
+          sout[o * step] = __fmul_rn(x2, pow_neg_beta<BETA075>(sc, neg_beta));
+        }
+        x2 = x1; x1 = xin;
+      }
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) cur[u] = nxt[u];
+    }
+  }
+}
+
+template <bool BETA075>
+__global__ void __launch_bounds__(kBlock) lrn_bwd5_kernel(const float* __restrict__ bottom, const float* __restrict__ top,
+                                                          const float* __restrict__ scale, const float* __restrict__ top_diff,
+                                                          float* __restrict__ bottom_diff, int num, int C, size_t step,
+                                                          float neg_beta, float cache_ratio) {
+  size_t total = static_cast<size_t>(num) * step;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t n = t / step, p = t - n * step, off = n * C * step + p;
+    const float* b = bottom + off;
+    const float* tp = top + off;
+    const float* s = scale + off;
+    const float* td = top_diff + off;
+    float* bd = bottom_diff + off;
+    float ctd[kLrnChunk], ctp[kLrnChunk], csc[kLrnChunk], cb[kLrnChunk];
+    float ntd[kLrnChunk], ntp[kLrnChunk], nsc[kLrnChunk], nb[kLrnChunk];
+#pragma unroll
+    for (int u = 0; u < kLrnChunk; ++u) {
+      bool ok = u < C;
+      ctd[u] = ok ? __ldg(td + u * step) : 0.f;
+      ctp[u] = ok ? __ldg(tp + u * step) : 0.f;
+      csc[u] = ok ? __ldg(s + u * step) : 1.f;
+      cb[u] = (u >= 2 && u - 2 < C) ? __ldg(b + (u - 2) * step) : 0.f;   // bottom of the output channel head-2
+    }
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;   // td*top/scale of head-1..head-5
+    float td1 = 0.f, td2 = 0.f, sc1 = 1.f, sc2 = 1.f;
+    float acc = 0.f;
+    for (int c0 = 0; c0 < C + 2; c0 += kLrnChunk) {
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) {
+        int hn = c0 + kLrnChunk + u;
+        bool ok = hn < C;
+        ntd[u] = ok ? __ldg(td + hn * step) : 0.f;
+        ntp[u] = ok ? __ldg(tp + hn * step) : 0.f;
+        nsc[u] = ok ? __ldg(s + hn * step) : 1.f;
+        nb[u] = (hn - 2 < C) ? __ldg(b + (hn - 2) * step) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) {
+        int head = c0 + u;
+        float tdh = ctd[u], sch = csc[u];
+        float r = __fdiv_rn(__fmul_rn(tdh, ctp[u]), sch);      // +0 past C (0*0/1)
+        acc = __fadd_rn(acc, r);
+        acc = __fsub_rn(acc, r4);
+        r4 = r3; r3 = r2; r2 = r1; r1 = r0; r0 = r;
+        int o = head - 2;
+        if (o >= 0 && o < C) {
+          float lhs = __fmul_rn(td2, pow_neg_beta<BETA075>(sc2, neg_beta));
+          float rhs = __fmul_rn(__fmul_rn(cache_ratio, cb[u]), acc);
+          bd[o * step] = __fsub_rn(lhs, rhs);
+        }
+        td2 = td1; td1 = tdh; sc2 = sc1; sc1 = sch;
+      }
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) { ctd[u] = ntd[u]; ctp[u] = ntp[u]; csc[u] = nsc[u]; cb[u] = nb[u]; }
+    }
+  }
+}
+
 template <bool IS_MAX>
 static int launch_pool_fwd(const float* x, float* y, size_t planes, const PoolGeom& g, cudaStream_t s) {
   size_t per = static_cast<size_t>(g.H) * g.W;
   int G = planes < 0x7fffffff ? pool_group(per, planes, per) : 0;
   if (G > 0) {
-    size_t bytes = per * G * sizeof(float);
+    size_t bytes = (per * G + 4) * sizeof(float);
     int rc = pool_smem_attr(pool_fwd_smem_kernel<IS_MAX>, bytes);
     if (rc) return rc;
     pool_fwd_smem_kernel<IS_MAX><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
@@ -603,14 +767,27 @@ int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, fl
   if (planes == 0) return MNV_OK;
   if (!x || !y || !dy || !dx) return MNV_EINVAL;
   {
-    size_t per = static_cast<size_t>(H) * W + 2 * static_cast<size_t>(g.Ho) * g.Wo;
+    size_t per = static_cast<size_t>(H) * W + 2 * static_cast<size_t>(g.Ho) * g.Wo;   // x, dy, argmax
     int G = planes < 0x7fffffff ? pool_group(per, planes, static_cast<size_t>(H) * W) : 0;
     if (G > 0) {
-      size_t bytes = per * G * sizeof(float);
-      rc = pool_smem_attr(maxpool_bwd_smem_kernel, bytes);
-      if (rc) return rc;
-      maxpool_bwd_smem_kernel<<<pool_grid(planes, G), kBlock, bytes, as_stream(s)>>>(x, y, dy, dx, static_cast<int>(planes), g, G,
-                                                                                  make_fastdiv(H * W), make_fastdiv(W), make_fastdiv(sv), make_fastdiv(sh));
+      size_t bytes = (per * G + 16) * sizeof(float);
+      const int P = static_cast<int>(planes);
+      const FastDiv f1 = make_fastdiv(H * W), f2 = make_fastdiv(W), f3 = make_fastdiv(g.Ho * g.Wo), f4 = make_fastdiv(g.Wo),
+                    f5 = make_fastdiv(sv), f6 = make_fastdiv(sh);
+      const int grid = pool_grid(planes, G);
+      cudaStream_t st = as_stream(s);
+#define MNV_POOL_BWD(WH_, WW_, SV_, SH_)                                                                         \
+  do {                                                                                                            \
+    rc = pool_smem_attr(maxpool_bwd_smem_kernel<WH_, WW_, SV_, SH_>, bytes);                                      \
+    if (rc) return rc;                                                                                            \
+    maxpool_bwd_smem_kernel<WH_, WW_, SV_, SH_><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f1, f2, f3, f4, f5, f6); \
+  } while (0)
+      if (wh == 3 && ww == 3 && sv == 2 && sh == 2) MNV_POOL_BWD(3, 3, 2, 2);
+      else if (wh == 2 && ww == 2 && sv == 2 && sh == 2) MNV_POOL_BWD(2, 2, 2, 2);
+      else if (wh == 3 && ww == 3 && sv == 3 && sh == 3) MNV_POOL_BWD(3, 3, 3, 3);
+      else if (wh == 3 && ww == 3 && sv == 1 && sh == 1) MNV_POOL_BWD(3, 3, 1, 1);
+      else MNV_POOL_BWD(0, 0, 0, 0);
+#undef MNV_POOL_BWD
       return finish_launch();
     }
   }
@@ -630,7 +807,7 @@ int mnv_average_pooling_backward(const float* x, const float* y, const float* dy
     size_t per = static_cast<size_t>(g.Ho) * g.Wo;
     int G = planes < 0x7fffffff ? pool_group(per, planes, static_cast<size_t>(H) * W) : 0;
     if (G > 0) {
-      size_t bytes = per * G * sizeof(float);
+      size_t bytes = (per * G + 4) * sizeof(float);
       rc = pool_smem_attr(avgpool_bwd_smem_kernel, bytes);
       if (rc) return rc;
       avgpool_bwd_smem_kernel<<<pool_grid(planes, G), kBlock, bytes, as_stream(s)>>>(dy, dx, static_cast<int>(planes), g, G,
@@ -649,7 +826,7 @@ int mnv_conv_backward_bias(const float* dy, float* db, int N, int C, int H, int 
   if (!dy || !db) return MNV_EINVAL;
   int hw = H * W;
   // enough CTAs for ~4 per SM, bounded by the images available and the workspace
-  int splits = (kNumSMs * 4 + C - 1) / C;
+  int splits = (kNumSMs * 8 + C - 1) / C;
   if (splits > N) splits = N > 0 ? N : 1;
   size_t max_splits = workspace ? workspace_bytes / (sizeof(float) * C) : 0;
   if (static_cast<size_t>(splits) > max_splits) splits = static_cast<int>(max_splits);
@@ -675,8 +852,8 @@ int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_siz
   const bool b075 = beta == 0.75f;
   const int grid = stream_grid(work);
   if (local_size == 5 && channel >= 5) {
-    if (b075) lrn_fwd_kernel<5, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, 5, aos, -beta);
-    else lrn_fwd_kernel<5, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, 5, aos, -beta);
+    if (b075) lrn_fwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, aos, -beta);
+    else lrn_fwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, aos, -beta);
   } else {
     if (b075) lrn_fwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
     else lrn_fwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
@@ -694,8 +871,8 @@ int mnv_lrn_backward(const float* bottom_data, const float* top_data, const floa
   const bool b075 = beta == 0.75f;
   const int grid = stream_grid(work);
   if (local_size == 5 && channel >= 5) {
-    if (b075) lrn_bwd_kernel<5, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, 5, -beta, cache_ratio);
-    else lrn_bwd_kernel<5, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, 5, -beta, cache_ratio);
+    if (b075) lrn_bwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, -beta, cache_ratio);
+    else lrn_bwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, -beta, cache_ratio);
   } else {
     if (b075) lrn_bwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
     else lrn_bwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
