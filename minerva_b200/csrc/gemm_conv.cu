@@ -95,22 +95,22 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires, so a
+  // long hint keeps the poll loop out of the issue slots the gather warps need.
   uint32_t done = 0;
   uint64_t t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) return;
-    if ((spin & 1023u) == 1023u) {
-      uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) asm volatile("trap;");  // 4 s
-    }
+    uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) asm volatile("trap;");  // 4 s: a protocol bug traps instead of hanging
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -144,10 +144,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// fp32 -> tf32 round-to-nearest (ties away from zero, == cvt.rna.tf32.f32) as ONE integer add of half a
+// tf32 ulp: kind::tf32 reads only the top 19 bits of each operand word, so the low 13 bits need not be
+// cleared.  inf stays inf (0x7f800000 + 0x1000 still has the inf pattern in its top 19 bits).
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
@@ -334,22 +344,32 @@ __device__ __forceinline__ void a_gather8(const GemmParams& p, const ARow& r, in
   }
 }
 
-// Forward im2col with the k-decomposition table: entry = offset | kh << 22 | kw << 27 where
-// offset = c*H*W + kh*W + kw; entries past K carry kh = 31, a bit no row mask ever has (fh <= 31).
-// Row validity is folded into the masks (mh = 0 for rows past M), so one element costs
-// LDS(broadcast) + 3 shifts + LOP3 + address add + predicated LDG, with no branches.
-__device__ __forceinline__ void a_gather8_ktab(const GemmParams& p, const ARow& r, const uint32_t* __restrict__ ktab, int k0,
+// Forward im2col with the k-decomposition table in shared memory (built once per CTA), one word per k:
+//   KT == 1 (fh*fw <= 31): (c*H*W + kh*W + kw) << 5 | (kh*fw + kw); the tap index is tested against ONE
+//            combined per-row mask (bit kh*fw+kw = tap in bounds);
+//   KT == 2: (c*H*W + kh*W + kw) | kh << 22 | kw << 27, tested against the row's kh and kw masks.
+//   Entries past K select bit 31, which no mask has.
+// Row validity is folded into the masks (zero for rows past M), so one element costs two shifts, a
+// predicate, a 64-bit shift-add and a predicated LDG; the table words are one LDS.128 per four elements.
+template <int KT>
+__device__ __forceinline__ void a_gather8_ktab(const float* __restrict__ src, uint32_t m0, uint32_t m1, uint32_t ktab_addr,
                                                float (&v)[8]) {
-  const float* src = p.a + r.base;
-  const uint4* t4 = reinterpret_cast<const uint4*>(ktab + k0);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    uint4 e4 = t4[q];
+    uint4 e4 = ld_shared_v4(ktab_addr + 16 * q);
     const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      bool ok = (__funnelshift_r(r.mh, 0u, e[j] >> 22) & (r.mw >> (e[j] >> 27))) & 1u;
-      v[4 * q + j] = ok ? __ldg(src + (e[j] & 0x3FFFFFu)) : 0.f;
+      bool ok;
+      uint32_t off;
+      if (KT == 1) {
+        ok = __funnelshift_r(m0, 0u, e[j]) & 1u;     // shift amount = low 5 bits = tap index
+        off = e[j] >> 5;
+      } else {
+        ok = (__funnelshift_r(m0, 0u, e[j] >> 22) & (m1 >> (e[j] >> 27))) & 1u;
+        off = e[j] & 0x3FFFFFu;
+      }
+      v[4 * q + j] = ok ? __ldg(src + off) : 0.f;
     }
   }
 }
@@ -490,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
   const uint32_t tfull0 = smem_u32(bars + 2 * kStages), tempty0 = smem_u32(bars + 2 * kStages + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 256);
+  const uint32_t ktab0 = smem_u32(smem + kStages * kStageBytes + 256);   // uint32 ktab[kKtabMax]
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -506,13 +526,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   if (AM == A_IM2COL_FWD && p.use_ktab) {
     const int ff = p.fh * p.fw, HW = p.H * p.W;
     for (int k = threadIdx.x; k < p.k_stages * BK; k += blockDim.x) {
-      uint32_t e = 31u << 22;
+      uint32_t e = p.use_ktab == 1 ? 31u : (31u << 22);
       if (k < p.K) {
         int c = k / ff, rs = k - c * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
         int kh = p.fh - 1 - rr, kw = p.fw - 1 - ss;
-        e = static_cast<uint32_t>(c * HW + kh * p.W + kw) | (static_cast<uint32_t>(kh) << 22) | (static_cast<uint32_t>(kw) << 27);
+        uint32_t off = static_cast<uint32_t>(c * HW + kh * p.W + kw);
+        e = p.use_ktab == 1 ? (off << 5 | static_cast<uint32_t>(kh * p.fw + kw))
+                            : (off | static_cast<uint32_t>(kh) << 22 | static_cast<uint32_t>(kw) << 27);
       }
-      ktab[k] = e;
+      st_shared_u32(ktab0 + 4 * k, e);
     }
   }
   tc_fence_before();
@@ -625,26 +647,36 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     float4 vb[BTMA ? 1 : LOOK][4];
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
-      ARow arow;
+      ARow arow = {};
       AWgrad awg;
       if (AM == A_IM2COL_WGRAD) awg = a_wgrad_setup(p, t.mt * BM, b_row0);
       else arow = a_row_setup<AM>(p, t.mt * BM + a_row);
-      if (AM == A_IM2COL_FWD && !arow.valid) arow.mh = 0;   // rows past M: every tap masked
+      // k-table path: byte pointer of the row's window origin + validity mask(s)
+      const float* srcr = p.a + arow.base;
+      uint32_t m0 = 0, m1 = 0;
+      if (AM == A_IM2COL_FWD && p.use_ktab && arow.valid) {
+        if (p.use_ktab == 1) {   // combined mask: bit kh*fw + kw
+          for (int kh = 0; kh < p.fh; ++kh)
+            if ((arow.mh >> kh) & 1u) m0 |= (arow.mw & ((1u << p.fw) - 1u)) << (kh * p.fw);
+        } else {
+          m0 = arow.mh; m1 = arow.mw;
+        }
+      }
       const int n_base = t.nt * p.bn;
       auto load = [&](int l, int ks) {
         if (AM == A_IM2COL_WGRAD) a_gather_wgrad(p, awg, ks, b_kq, va[l]);
-        else if (AM == A_IM2COL_FWD && p.use_ktab) a_gather8_ktab(p, arow, ktab, ks * BK + a_q * 8, va[l]);
+        else if (AM == A_IM2COL_FWD && p.use_ktab == 1) a_gather8_ktab<1>(srcr, m0, m1, ktab0 + 4 * (ks * BK + a_q * 8), va[l]);
+        else if (AM == A_IM2COL_FWD && p.use_ktab == 2) a_gather8_ktab<2>(srcr, m0, m1, ktab0 + 4 * (ks * BK + a_q * 8), va[l]);
         else a_gather8<AM>(p, arow, ks * BK + a_q * 8, va[l]);
         if (!BTMA) b_gather<BMD>(p, n_base, b_row0, b_iters, ks * BK + b_kq * 4, vb[BTMA ? 0 : l]);
       };
       auto store = [&](int l) {
-        uint8_t* a_tile = smem + stage * kStageBytes;
-        uint8_t* b_tile = a_tile + kABytes;
+        const uint32_t a_tile = smem_base + stage * kStageBytes;
+        const uint32_t b_tile = a_tile + kABytes;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          float4 w = make_float4(to_tf32(va[l][4 * q]), to_tf32(va[l][4 * q + 1]), to_tf32(va[l][4 * q + 2]), to_tf32(va[l][4 * q + 3]));
           uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(b_row0 + 64 * q, b_kq) : sw128_off(a_row, a_q * 2 + q);
-          *reinterpret_cast<float4*>(a_tile + off) = w;
+          st_shared_v4(a_tile + off, to_tf32(va[l][4 * q]), to_tf32(va[l][4 * q + 1]), to_tf32(va[l][4 * q + 2]), to_tf32(va[l][4 * q + 3]));
         }
         if (!BTMA) {
 #pragma unroll
@@ -653,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             int row = b_row0 + 64 * i;
             if (row < p.bn) {
               const float4& s4 = vb[BTMA ? 0 : l][i];
-              *reinterpret_cast<float4*>(b_tile + sw128_off(row, b_kq)) = make_float4(to_tf32(s4.x), to_tf32(s4.y), to_tf32(s4.z), to_tf32(s4.w));
+              st_shared_v4(b_tile + sw128_off(row, b_kq), to_tf32(s4.x), to_tf32(s4.y), to_tf32(s4.z), to_tf32(s4.w));
             }
           }
         }
@@ -828,8 +860,12 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   }
   plan_tiles(p, ws ? ws_bytes : 0);
   p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
-  p.use_ktab = (AM == A_IM2COL_FWD) && p.k_stages * BK <= kKtabMax &&
-               static_cast<long long>(p.Ci) * p.H * p.W < (1ll << 22) && !g_opt_no_ktab.load();
+  p.use_ktab = 0;
+  if (AM == A_IM2COL_FWD && p.k_stages * BK <= kKtabMax && !g_opt_no_ktab.load()) {
+    long long img = static_cast<long long>(p.Ci) * p.H * p.W;
+    if (p.fh * p.fw <= 31 && img < (1ll << 27)) p.use_ktab = 1;
+    else if (img < (1ll << 22)) p.use_ktab = 2;
+  }
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   bool tma = false;
