@@ -88,6 +88,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Producer-side arrive.  The default .release.cta form compiles to MEMBAR.ALL.CTA, which also waits for
+// the look-ahead LDGs of later stages still in flight and serialises the gather pipeline.  What the
+// consumer needs is only (1) this warp's st.shared performed before the arrive -- same thread, same
+// shared-memory pipe, program order -- and (2) generic->async proxy visibility, given by
+// fence.proxy.async.shared::cta right before.  Hence .relaxed.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // Time-bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
@@ -255,11 +263,10 @@ struct ARow {           // per-thread, per-tile state of the A gather
   uint32_t mh, mw;      // validity masks over kh / kw (im2col fwd / bwd)
   int h0, w0;           // oh*sv-ph (fwd), h+ph (bwd)
 };
-constexpr int kARows = 2;   // KC mapping: tile rows per thread (128 rows x 8 chunks / 512 threads)
-struct AWgrad {         // KC mapping: kARows rows (taps) per thread
-  int toff[kARows];     // ci*H*W + (kh-ph)*W + (kw-pw)
-  int dh[kARows], dw[kARows];     // kh-ph, kw-pw
-  bool valid[kARows];
+template <int NR>
+struct AWgrad {         // KC mapping: NR rows (taps) per thread
+  int toff[NR];         // ci*H*W + (kh-ph)*W + (kw-pw); row past M: a bound-failing dh instead of a flag
+  int dhw[NR];          // (kh-ph) << 16 | ((kw-pw) & 0xffff)
 };
 
 template <int AM>
@@ -286,29 +293,31 @@ __device__ __forceinline__ ARow a_row_setup(const GemmParams& p, int m) {
   return r;
 }
 
-__device__ __forceinline__ AWgrad a_wgrad_setup(const GemmParams& p, int m_base, int row0) {
-  AWgrad w;
+template <int NR>
+__device__ __forceinline__ AWgrad<NR> a_wgrad_setup(const GemmParams& p, int m_base, int row0, int row_step) {
+  AWgrad<NR> w;
   const int ff = p.fh * p.fw;
 #pragma unroll
-  for (int i = 0; i < kARows; ++i) {
-    int m = m_base + row0 + 64 * i;
-    w.valid[i] = m < p.M;
-    int mm = w.valid[i] ? m : 0;
+  for (int i = 0; i < NR; ++i) {
+    int m = m_base + row0 + row_step * i;
+    bool valid = m < p.M;
+    int mm = valid ? m : 0;
     int ci = mm / ff, rs = mm - ci * ff, rr = rs / p.fw, ss = rs - rr * p.fw;
-    w.dh[i] = (p.fh - 1 - rr) - p.ph;
-    w.dw[i] = (p.fw - 1 - ss) - p.pw;
-    w.toff[i] = ci * p.H * p.W + w.dh[i] * p.W + w.dw[i];
+    int dh = valid ? (p.fh - 1 - rr) - p.ph : -20000;   // invalid row: every bounds test fails
+    int dw = (p.fw - 1 - ss) - p.pw;
+    w.dhw[i] = (dh << 16) | (dw & 0xffff);
+    w.toff[i] = valid ? ci * p.H * p.W + dh * p.W + dw : 0;
   }
   return w;
 }
 
-// MC mapping: 8 consecutive k starting at k0 for this thread's row
-template <int AM>
-__device__ __forceinline__ void a_gather8(const GemmParams& p, const ARow& r, int k0, float (&v)[8]) {
+// MC mapping: NE consecutive k starting at k0 for this thread's row
+template <int AM, int NE>
+__device__ __forceinline__ void a_gatherN(const GemmParams& p, const ARow& r, int k0, float (&v)[NE]) {
   if (AM == A_COLMAJOR) {
     const float* src = p.a + r.base + static_cast<size_t>(k0) * p.lda;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (r.valid && k0 + j < p.K) ? __ldg(src + static_cast<size_t>(j) * p.lda) : 0.f;
+    for (int j = 0; j < NE; ++j) v[j] = (r.valid && k0 + j < p.K) ? __ldg(src + static_cast<size_t>(j) * p.lda) : 0.f;
   } else {
     // k = (c, rr, ss) in filter storage order; kh = fh-1-rr, kw = fw-1-ss
     const int ff = p.fh * p.fw;
@@ -319,7 +328,7 @@ __device__ __forceinline__ void a_gather8(const GemmParams& p, const ARow& r, in
       int off = c * HW + kh * p.W + kw;
       const float* src = p.a + r.base;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {  // table-free fallback (K or C*H*W too large for the smem table)
+      for (int j = 0; j < NE; ++j) {  // table-free fallback (K or C*H*W too large for the smem table)
         bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
         v[j] = ok ? __ldg(src + off) : 0.f;
         --kw; --off;
@@ -329,7 +338,7 @@ __device__ __forceinline__ void a_gather8(const GemmParams& p, const ARow& r, in
       const int HoWo = p.Ho * p.Wo;
       const float* src = p.a + r.base;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NE; ++j) {
         bool ok = r.valid && (k0 + j < p.K) && (((r.mh >> kh) & (r.mw >> kw)) & 1u);
         float val = 0.f;
         if (ok) {
@@ -351,11 +360,11 @@ __device__ __forceinline__ void a_gather8(const GemmParams& p, const ARow& r, in
 //   Entries past K select bit 31, which no mask has.
 // Row validity is folded into the masks (zero for rows past M), so one element costs two shifts, a
 // predicate, a 64-bit shift-add and a predicated LDG; the table words are one LDS.128 per four elements.
-template <int KT>
-__device__ __forceinline__ void a_gather8_ktab(const float* __restrict__ src, uint32_t m0, uint32_t m1, uint32_t ktab_addr,
-                                               float (&v)[8]) {
+template <int KT, int NE>
+__device__ __forceinline__ void a_gatherN_ktab(const float* __restrict__ src, uint32_t m0, uint32_t m1, uint32_t ktab_addr,
+                                               float (&v)[NE]) {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < NE / 4; ++q) {
     uint4 e4 = ld_shared_v4(ktab_addr + 16 * q);
     const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
@@ -377,7 +386,8 @@ __device__ __forceinline__ void a_gather8_ktab(const float* __restrict__ src, ui
 // KC mapping (backward-filter): this thread's 4 pixels for its kARows tap rows; v[4*i + e].
 // spi == 0: k = (img, oh, ow) flat, k0 = ks*32 + kq*4.  spi > 0 (top_diff comes by TMA): every image's
 // pixels are padded to spi*32, so a k-stage never straddles two images.
-__device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad& w, int ks, int kq, float (&v)[8]) {
+template <int NR>
+__device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad<NR>& w, int ks, int kq, float (&v)[4 * NR]) {
   const int HoWo = p.Ho * p.Wo;
   int img, pix;
   bool in_k;
@@ -392,24 +402,39 @@ __device__ __forceinline__ void a_gather_wgrad(const GemmParams& p, const AWgrad
     in_k = false;
   }
   int oh = pix / p.Wo, ow = pix - oh * p.Wo;
-  long long uoff[4];
-  int ohs[4], ows[4];
+  int uoff[4], ohs[4], ows[4];
+  const float* src = p.a + static_cast<long long>(img) * p.Ci * p.H * p.W;   // image base (k-stage never straddles when spi > 0)
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     bool ok = in_k ? (pix + e < HoWo) : (ks * BK + kq * 4 + e < p.K);
     ohs[e] = ok ? oh * p.sv : -(1 << 28);   // out-of-range k fails the bounds test below
     ows[e] = ow * p.sh;
-    uoff[e] = static_cast<long long>(img) * p.Ci * p.H * p.W + static_cast<long long>(oh * p.sv) * p.W + ow * p.sh;
-    if (++ow == p.Wo) { ow = 0; if (++oh == p.Ho) { oh = 0; ++img; } }
+    uoff[e] = oh * p.sv * p.W + ow * p.sh;
+    if (++ow == p.Wo) {
+      ow = 0;
+      if (++oh == p.Ho) { oh = 0; uoff[e] += 0; if (!in_k) { /* next image */ } }
+    }
   }
-#pragma unroll
-  for (int i = 0; i < kARows; ++i) {
-    const float* src = p.a + w.toff[i];
+  // unpadded K (spi == 0): pixels past the end of the image belong to the next one
+  if (!in_k) {
+    int k0 = ks * BK + kq * 4;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      bool ok = w.valid[i] && static_cast<unsigned>(ohs[e] + w.dh[i]) < static_cast<unsigned>(p.H) &&
-                static_cast<unsigned>(ows[e] + w.dw[i]) < static_cast<unsigned>(p.W);
-      v[4 * i + e] = ok ? __ldg(src + uoff[e]) : 0.f;
+      int k = k0 + e, im = k / HoWo, px = k - im * HoWo, o2 = px / p.Wo, w2 = px - o2 * p.Wo;
+      uoff[e] = (im - img) * p.Ci * p.H * p.W + o2 * p.sv * p.W + w2 * p.sh;
+      ohs[e] = (k < p.K) ? o2 * p.sv : -(1 << 28);
+      ows[e] = w2 * p.sh;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const float* s2 = src + w.toff[i];
+    const int dh = w.dhw[i] >> 16, dw = static_cast<int>(static_cast<short>(w.dhw[i] & 0xffff));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      bool ok = static_cast<unsigned>(ohs[e] + dh) < static_cast<unsigned>(p.H) &&
+                static_cast<unsigned>(ows[e] + dw) < static_cast<unsigned>(p.W);
+      v[4 * i + e] = ok ? __ldg(s2 + uoff[e]) : 0.f;
     }
   }
 }
@@ -517,8 +542,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
 
   if (threadIdx.x == 0) {
-    // full: one arrive per producer warp (+ the TMA thread's arrive.expect_tx)
-    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, kProducerThreads / 32 + (BTMA ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
+    // full: TMA-fed B: the 4 warps of the slot's producer group + the TMA thread's arrive.expect_tx;
+    //       gathered B: all 16 producer warps
+    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     fence_barrier_init();
   }
@@ -637,7 +663,66 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     __syncwarp();
   } else {
     // ===================== gather producers =====================
-    constexpr int LOOK = (AM == A_IM2COL_WGRAD && !BTMA) ? 1 : 2;   // register look-ahead in k-stages (gathered wgrad stages A and B: 1 to stay spill-free)
+    if (BTMA) {
+      // Stage-interleaved warp groups: group g (4 warps = 128 threads, one thread per tile row, all 32 k
+      // of the stage) owns ring slot g, i.e. every 4th k-stage.  A group's loads for its next stage are
+      // issued right after it hands the current one over and have three other stages' time to land, so
+      // L2 latency is covered by thread-level parallelism rather than by one warp's scoreboard (a warp's
+      // outstanding LDGs share scoreboard slots: register look-ahead inside one warp does not overlap).
+      const int pw = warp - kProducerWarp0;                 // 0..15
+      const int grp = pw >> 2;                              // ring slot owned by this group
+      const int gt = threadIdx.x - kProducerWarp0 * 32 - grp * 128;   // 0..127: tile row (MC) / chunk id (KC)
+      const int kc_kq = gt & 7, kc_row0 = gt >> 3;          // KC mapping: rows kc_row0 + 16*i, chunk column kc_kq
+      const uint32_t slot_full = full0 + 8 * grp, slot_empty = empty0 + 8 * grp;
+      const uint32_t a_tile = smem_base + grp * kStageBytes;
+      uint32_t uses = 0;                                    // completed uses of this slot -> wait parity
+      uint32_t cnt = 0;                                     // global k-stage counter at tile start
+      float va[32];
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord t = decode_tile(p, tile);
+        const int nks = t.ks_end - t.ks_begin;
+        int ks = t.ks_begin + ((grp - static_cast<int>(cnt & 3u)) & 3);   // this group's first stage in the tile
+        cnt += static_cast<uint32_t>(nks);
+        if (ks >= t.ks_end) continue;
+        ARow arow = {};
+        AWgrad<8> awg;
+        if (AM == A_IM2COL_WGRAD) awg = a_wgrad_setup<8>(p, t.mt * BM, kc_row0, 16);
+        else arow = a_row_setup<AM>(p, t.mt * BM + gt);
+        const float* srcr = p.a + arow.base;
+        uint32_t m0 = 0, m1 = 0;
+        if (AM == A_IM2COL_FWD && p.use_ktab && arow.valid) {
+          if (p.use_ktab == 1) {   // combined mask: bit kh*fw + kw
+            for (int kh = 0; kh < p.fh; ++kh)
+              if ((arow.mh >> kh) & 1u) m0 |= (arow.mw & ((1u << p.fw) - 1u)) << (kh * p.fw);
+          } else {
+            m0 = arow.mh; m1 = arow.mw;
+          }
+        }
+        auto load = [&](int k) {
+          if (AM == A_IM2COL_WGRAD) a_gather_wgrad<8>(p, awg, k, kc_kq, va);
+          else if (AM == A_IM2COL_FWD && p.use_ktab == 1) a_gatherN_ktab<1, 32>(srcr, m0, m1, ktab0 + 4 * (k * BK), va);
+          else if (AM == A_IM2COL_FWD && p.use_ktab == 2) a_gatherN_ktab<2, 32>(srcr, m0, m1, ktab0 + 4 * (k * BK), va);
+          else a_gatherN<AM, 32>(p, arow, k * BK, va);
+        };
+        load(ks);
+        for (; ks < t.ks_end; ks += 4) {
+          mbar_wait(slot_empty, (uses & 1u) ^ 1u);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(kc_row0 + 16 * q, kc_kq) : sw128_off(gt, q);
+            st_shared_v4(a_tile + off, to_tf32(va[4 * q]), to_tf32(va[4 * q + 1]), to_tf32(va[4 * q + 2]), to_tf32(va[4 * q + 3]));
+          }
+          fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive_relaxed(slot_full);
+          ++uses;
+          if (ks + 4 < t.ks_end) load(ks + 4);   // lands while the other three groups' stages are consumed
+        }
+      }
+    } else {
+    // register look-ahead in k-stages: the gathers are latency-bound on L2 when the ring is not full, so the
+    // TMA-fed variants (8 staging registers per stage) look 4 stages ahead; gathered-B variants stage A and B.
+    constexpr int LOOK = (AM == A_IM2COL_WGRAD) ? 1 : 2;
     const int pt = threadIdx.x - kProducerWarp0 * 32;   // 0..511
     const int a_row = pt & 127, a_q = pt >> 7;          // MC mapping: 8 consecutive k: [a_q*8, +8)
     const int b_kq = pt & 7, b_row0 = pt >> 3;          // KC mapping: rows b_row0 + 64*i, chunk column b_kq
@@ -648,8 +733,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
       ARow arow = {};
-      AWgrad awg;
-      if (AM == A_IM2COL_WGRAD) awg = a_wgrad_setup(p, t.mt * BM, b_row0);
+      AWgrad<2> awg;
+      if (AM == A_IM2COL_WGRAD) awg = a_wgrad_setup<2>(p, t.mt * BM, b_row0, 64);
       else arow = a_row_setup<AM>(p, t.mt * BM + a_row);
       // k-table path: byte pointer of the row's window origin + validity mask(s)
       const float* srcr = p.a + arow.base;
@@ -664,10 +749,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       }
       const int n_base = t.nt * p.bn;
       auto load = [&](int l, int ks) {
-        if (AM == A_IM2COL_WGRAD) a_gather_wgrad(p, awg, ks, b_kq, va[l]);
-        else if (AM == A_IM2COL_FWD && p.use_ktab == 1) a_gather8_ktab<1>(srcr, m0, m1, ktab0 + 4 * (ks * BK + a_q * 8), va[l]);
-        else if (AM == A_IM2COL_FWD && p.use_ktab == 2) a_gather8_ktab<2>(srcr, m0, m1, ktab0 + 4 * (ks * BK + a_q * 8), va[l]);
-        else a_gather8<AM>(p, arow, ks * BK + a_q * 8, va[l]);
+        if (AM == A_IM2COL_WGRAD) a_gather_wgrad<2>(p, awg, ks, b_kq, va[l]);
+        else if (AM == A_IM2COL_FWD && p.use_ktab == 1) a_gatherN_ktab<1, 8>(srcr, m0, m1, ktab0 + 4 * (ks * BK + a_q * 8), va[l]);
+        else if (AM == A_IM2COL_FWD && p.use_ktab == 2) a_gatherN_ktab<2, 8>(srcr, m0, m1, ktab0 + 4 * (ks * BK + a_q * 8), va[l]);
+        else a_gatherN<AM, 8>(p, arow, ks * BK + a_q * 8, va[l]);
         if (!BTMA) b_gather<BMD>(p, n_base, b_row0, b_iters, ks * BK + b_kq * 4, vb[BTMA ? 0 : l]);
       };
       auto store = [&](int l) {
@@ -701,12 +786,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             store(l);
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * stage);
+            if (lane == 0) mbar_arrive_relaxed(full0 + 8 * stage);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             if (ks + l + LOOK < t.ks_end) load(l, ks + l + LOOK);  // flies while the ring drains
           }
         }
       }
+    }
     }
   }
 
