@@ -21,6 +21,17 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
 
 WORKLOADS = {
     "alexnet": dict(builder="build_alexnet", batch=256, classes=1000,
@@ -175,12 +186,22 @@ def run_reference(args):
                                    "Minerva implements on CPU: %s" % (sample, steps, used_ref)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # a wedged collective must not burn the GPU lease: hard exit after 15 minutes
+    watchdog = threading.Timer(900.0, lambda: os._exit(3))
+    watchdog.daemon = True
+    watchdog.start()
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) are
+    # pointed at stderr for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -292,11 +313,13 @@ def main():
     # ---- per-launch device times of the dominant kernel (rank 0) -------------------------------------
     roofline, optable = None, None
     pk = peaks()
+    # every rank takes the two instrumented steps (they contain the gradient all-reduce); rank 0 records
     if rank == 0:
         rt.profiler = rt.EventProfiler()
-        for _ in range(2):
-            trainer.step()
-        sync_all_local = (owl.wait_for_all(), torch.cuda.synchronize())
+    for _ in range(2):
+        trainer.step()
+    sync_all()
+    if rank == 0:
         table = rt.profiler.table()
         rt.profiler = None
         per = {}
@@ -354,7 +377,7 @@ def main():
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,
             "peaks": {k: pk.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

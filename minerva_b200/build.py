@@ -53,7 +53,33 @@ def build(force=False, verbose=False):
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
         subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
+    build_host(force)
     return LIB
+
+
+HOST = os.path.join(CSRC, "host", "minerva")
+HOST_SRCS = [os.path.join(HOST, "op", "impl", "cuda.cpp"), os.path.join(HOST, "device", "gpu_device.cpp")]
+HOST_TEST = os.path.join(OUT_DIR, "test_host_plugin")
+
+
+def build_host(force=False):
+    """The C++ host side above the C ABI (minerva/op plug-in surface + GpuDevice) -> libminerva_b200_host.so,
+    and the C++ plug-in test binary (links the CPU oracle as its checker)."""
+    deps = HOST_SRCS + [os.path.join(HOST, "op", "hotpath.h"), os.path.join(HOST, "device", "gpu_device.h"), LIB]
+    inc = ["-I" + HOST, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"]
+    if force or _stale(HOST_LIB, deps):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-o", HOST_LIB] + inc + HOST_SRCS +
+                              ["-L" + OUT_DIR, "-lmnv_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    test_src = os.path.join(ROOT, "tests", "cpp", "test_host_plugin.cpp")
+    oracle_c = os.path.join(ROOT, "oracle", "mnv_oracle.c")
+    if force or _stale(HOST_TEST, [test_src, oracle_c, HOST_LIB]):
+        oracle_o = os.path.join(OUT_DIR, "mnv_oracle_test.o")
+        subprocess.check_call(["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-c", oracle_c, "-o", oracle_o])
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-o", HOST_TEST, test_src, oracle_o] + inc +
+                              ["-L" + OUT_DIR, "-lminerva_b200_host", "-lmnv_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+                               "-fopenmp", "-lm", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return HOST_LIB
 
 
 if __name__ == "__main__":
