@@ -817,14 +817,16 @@ __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams 
 // w[co][ci][r][s] -> wt[ci][co][r'][s']: backward-data reads the filter as B[n=ci][k=(co,r,s)].
 // flip = 1 additionally rotates the taps by 180 degrees (r' = fh-1-r, s' = fw-1-s), which turns a
 // stride-1 backward-data into a forward convolution of top_diff with pad' = f-1-pad.
-__global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci, int ff, int flip) {
+__global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci, int ff, int flip, int round) {
   size_t total = static_cast<size_t>(Co) * Ci * ff;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
     int rs = static_cast<int>(t % ff);
     size_t rest = t / ff;
     int co = static_cast<int>(rest % Co), ci = static_cast<int>(rest / Co);
-    wt[t] = __ldg(w + (static_cast<size_t>(co) * Ci + ci) * ff + (flip ? ff - 1 - rs : rs));
+    // rounded to TF32 here because the tensor core only truncates what TMA delivers
+    float v = __ldg(w + (static_cast<size_t>(co) * Ci + ci) * ff + (flip ? ff - 1 - rs : rs));
+    wt[t] = round ? to_tf32(v) : v;
   }
 }
 
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
   for (size_t r = warp; r < rows; r += nwarps) {
     const float* s = src + r * inner;
     float* d = dst + r * pitch;
-    for (int i = lane; i < inner; i += 32) d[i] = __ldg(s + i);
+    for (int i = lane; i < inner; i += 32) d[i] = to_tf32(__ldg(s + i));   // TF32 round-to-nearest on the way
   }
 }
 
@@ -943,6 +945,22 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
     p.splits = 1; p.partial = nullptr;
     simt_gemm_kernel<AM, BMD><<<stream_grid(static_cast<size_t>(p.M) * p.N), 256, 0, s>>>(p);
     return finish_launch();
+  }
+  // A K-major B whose rows are not 16-byte pitched/aligned (conv1: K = 363; odd GEMM k) is re-pitched into the
+  // workspace once (B is the small operand: filters, or the batch-side matrix of an FC layer) so that it can
+  // still come through TMA and the kernel can run the grouped-producer path.
+  if (BMD == B_KMAJOR && !p.b_vec && ws && !g_opt_no_tma.load()) {
+    int pitch = (p.K + 3) / 4 * 4;
+    size_t need = (static_cast<size_t>(p.N) * pitch * sizeof(float) + 255) / 256 * 256;
+    if (ws_bytes >= need) {
+      float* packed = static_cast<float*>(ws);
+      repitch_kernel<<<stream_grid(static_cast<size_t>(p.N) * 32), kBlock, 0, s>>>(p.b, packed, p.K, pitch, static_cast<size_t>(p.N));
+      int rc0 = finish_launch();
+      if (rc0) return rc0;
+      p.b = packed; p.ldb = pitch; p.b_vec = 1;
+      ws = static_cast<uint8_t*>(ws) + need;
+      ws_bytes -= need;
+    }
   }
   plan_tiles(p, ws ? ws_bytes : 0);
   p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
@@ -1052,7 +1070,7 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
   // filter and pad' = f-1-pad, so it runs on the (fast) forward gather.
   const bool as_forward = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && !g_opt_no_fwd_bwd.load();
   filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(
-      filter, wt, Co, Ci, fh * fw, as_forward ? 1 : 0);
+      filter, wt, Co, Ci, fh * fw, as_forward ? 1 : 0, g_opt_simt.load() ? 0 : 1);
   rc = finish_launch();
   if (rc) return rc;
   GemmParams p;

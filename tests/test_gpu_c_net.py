@@ -70,7 +70,8 @@ def test_training_step_matches_cpu_oracle(gpu_owl):
         net.backward("TRAIN")
         nets.append(net)
     cpu, gpu = nets
-    assert abs(cpu.get_loss_units()[0].getloss() - gpu.get_loss_units()[0].getloss()) < 2e-3
+    lc, lg = cpu.get_loss_units()[0].getloss(), gpu.get_loss_units()[0].getloss()
+    assert abs(lc - lg) <= 5e-3 * abs(lc), (lc, lg)          # TF32 conv/GEMM tolerance carried to the loss
     for uid in cpu.get_weighted_unit_ids():
         for attr in ("weight", "weightgrad", "biasgrad"):
             a = getattr(cpu.units[uid], attr).to_numpy().astype(np.float64)
