@@ -360,6 +360,119 @@ __global__ void __launch_bounds__(kBlock) avgpool_bwd_smem_kernel(const float* _
   }
 }
 
+// ---- 3x3 / stride 2 / pad 0 max pooling (AlexNet pool1/2/5, GoogLeNet pool1-4): unrolled variants --------
+// Forward: 9 unrolled LDS per output; bounds tests only when the last window overhangs (CHECK).
+template <bool CHECK>
+__global__ void __launch_bounds__(kBlock) maxpool332_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, PoolGeom g,
+                                                                 int G, FastDiv d_howo, FastDiv d_wo) {
+  extern __shared__ float sm[];
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo, W = g.W;
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    float* sx = sm + misalign4(xsrc);
+    stage_in(sx, xsrc, cnt * HW);
+    __syncthreads();
+    float* yp = y + static_cast<size_t>(p0) * HoWo;
+    for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {
+      int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * g.Wo;
+      const float* xp = sx + gq * HW + (2 * i) * W + 2 * j;
+      float best = -CUDART_INF_F;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if (!CHECK || (2 * i + kh < g.H && 2 * j + kw < W)) {
+            float v = xp[kh * W + kw];
+            if (v > best) best = v;
+          }
+        }
+      yp[o] = best;
+    }
+    __syncthreads();
+  }
+}
+
+// Backward: phase A as the generic kernel (arg-max plane), phase B one thread per 2x2 input block (2i..2i+1,
+// 2j..2j+1): the four windows that can own those elements are (i-1..i, j-1..j), so 4 arg + 4 dy LDS serve four
+// outputs.  Contributions are added in (i-major, j-minor) window order => bit-identical to the oracle.
+template <bool CHECK>
+__global__ void __launch_bounds__(kBlock) maxpool332_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 float* __restrict__ dx, int planes, PoolGeom g, int G,
+                                                                 FastDiv d_howo, FastDiv d_wo, FastDiv d_blk, FastDiv d_bw) {
+  extern __shared__ float sm[];
+  const int H = g.H, W = g.W, HW = H * W, Ho = g.Ho, Wo = g.Wo, HoWo = Ho * Wo;
+  const int BH = (H + 1) >> 1, BW = (W + 1) >> 1, BLK = BH * BW;   // 2x2 blocks per plane
+  float* sx_base = sm;
+  float* sdy_base = sm + ((G * HW + 4 + 3) & ~3);
+  int* sarg = reinterpret_cast<int*>(sdy_base + ((G * HoWo + 4 + 3) & ~3));
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    const float* dysrc = dy + static_cast<size_t>(p0) * HoWo;
+    float* sx = sx_base + misalign4(xsrc);
+    float* sdy = sdy_base + misalign4(dysrc);
+    stage_in(sx, xsrc, cnt * HW);
+    stage_in(sdy, dysrc, cnt * HoWo);
+    __syncthreads();
+    for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {   // phase A: arg-max of every window
+      int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * Wo;
+      const int base = (2 * i) * W + 2 * j;
+      const float* xp = sx + gq * HW + base;
+      float best = -CUDART_INF_F;
+      int arg = -1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if (!CHECK || (2 * i + kh < H && 2 * j + kw < W)) {
+            float v = xp[kh * W + kw];
+            if (v > best) { best = v; arg = base + kh * W + kw; }
+          }
+        }
+      sarg[o] = arg;
+    }
+    __syncthreads();
+    float* dxp = dx + static_cast<size_t>(p0) * HW;
+    for (int b = threadIdx.x; b < cnt * BLK; b += blockDim.x) {    // phase B: one 2x2 input block per thread
+      int gq = fdiv(b, d_blk), rb = b - gq * BLK, bi = fdiv(rb, d_bw), bj = rb - bi * BW;
+      const int* ap = sarg + gq * HoWo;
+      const float* dyp = sdy + gq * HoWo;
+      // windows (bi-1, bj-1), (bi-1, bj), (bi, bj-1), (bi, bj); invalid ones get arg -2 (matches nothing)
+      const bool iu = bi >= 1 && bi - 1 < Ho, id = bi < Ho, jl = bj >= 1 && bj - 1 < Wo, jr = bj < Wo;
+      int a00 = -2, a01 = -2, a10 = -2, a11 = -2;
+      float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+      if (iu && jl) { a00 = ap[(bi - 1) * Wo + bj - 1]; d00 = dyp[(bi - 1) * Wo + bj - 1]; }
+      if (iu && jr) { a01 = ap[(bi - 1) * Wo + bj]; d01 = dyp[(bi - 1) * Wo + bj]; }
+      if (id && jl) { a10 = ap[bi * Wo + bj - 1]; d10 = dyp[bi * Wo + bj - 1]; }
+      if (id && jr) { a11 = ap[bi * Wo + bj]; d11 = dyp[bi * Wo + bj]; }
+      const int h = 2 * bi, w = 2 * bj, r00 = h * W + w;
+      float* out = dxp + gq * HW + r00;
+      // (h, w): in all four windows
+      float acc = 0.f;
+      if (a00 == r00) acc = __fadd_rn(acc, d00);
+      if (a01 == r00) acc = __fadd_rn(acc, d01);
+      if (a10 == r00) acc = __fadd_rn(acc, d10);
+      if (a11 == r00) acc = __fadd_rn(acc, d11);
+      out[0] = acc;
+      if (w + 1 < W) {   // (h, w+1): windows (bi-1, bj), (bi, bj)
+        acc = 0.f;
+        if (a01 == r00 + 1) acc = __fadd_rn(acc, d01);
+        if (a11 == r00 + 1) acc = __fadd_rn(acc, d11);
+        out[1] = acc;
+      }
+      if (h + 1 < H) {   // (h+1, w): windows (bi, bj-1), (bi, bj)
+        acc = 0.f;
+        if (a10 == r00 + W) acc = __fadd_rn(acc, d10);
+        if (a11 == r00 + W) acc = __fadd_rn(acc, d11);
+        out[W] = acc;
+        if (w + 1 < W) out[W + 1] = (a11 == r00 + W + 1) ? __fadd_rn(0.f, d11) : 0.f;   // (h+1, w+1): window (bi, bj)
+      }
+    }
+    __syncthreads();
+  }
+}
+
 constexpr int kPoolSmemMax = 96 * 1024;      // opt-in dynamic shared memory ceiling for the staged kernels
 constexpr int kPoolSmemTarget = 24 * 1024;   // aim: ~6K floats per CTA pass, several CTAs per SM
 
@@ -689,6 +802,21 @@ static int launch_pool_fwd(const float* x, float* y, size_t planes, const PoolGe
     size_t bytes = (per * G + 4) * sizeof(float);
     int rc = pool_smem_attr(pool_fwd_smem_kernel<IS_MAX>, bytes);
     if (rc) return rc;
+    if (IS_MAX && g.wh == 3 && g.ww == 3 && g.sv == 2 && g.sh == 2 && g.ph == 0 && g.pw == 0) {
+      const bool fit = (g.Ho - 1) * 2 + 3 <= g.H && (g.Wo - 1) * 2 + 3 <= g.W;
+      if (fit) {
+        rc = pool_smem_attr(maxpool332_fwd_kernel<false>, bytes);
+        if (rc) return rc;
+        maxpool332_fwd_kernel<false><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
+                                                                                  make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
+      } else {
+        rc = pool_smem_attr(maxpool332_fwd_kernel<true>, bytes);
+        if (rc) return rc;
+        maxpool332_fwd_kernel<true><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
+                                                                                 make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
+      }
+      return finish_launch();
+    }
     pool_fwd_smem_kernel<IS_MAX><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
                                                                             make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
     return finish_launch();
@@ -782,7 +910,20 @@ int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, fl
     if (rc) return rc;                                                                                            \
     maxpool_bwd_smem_kernel<WH_, WW_, SV_, SH_><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f1, f2, f3, f4, f5, f6); \
   } while (0)
-      if (wh == 3 && ww == 3 && sv == 2 && sh == 2) MNV_POOL_BWD(3, 3, 2, 2);
+      if (wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0) {
+        const bool fit = (g.Ho - 1) * 2 + 3 <= H && (g.Wo - 1) * 2 + 3 <= W;
+        const FastDiv fb = make_fastdiv(((H + 1) / 2) * ((W + 1) / 2)), fbw = make_fastdiv((W + 1) / 2);
+        if (fit) {
+          rc = pool_smem_attr(maxpool332_bwd_kernel<false>, bytes);
+          if (rc) return rc;
+          maxpool332_bwd_kernel<false><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f3, f4, fb, fbw);
+        } else {
+          rc = pool_smem_attr(maxpool332_bwd_kernel<true>, bytes);
+          if (rc) return rc;
+          maxpool332_bwd_kernel<true><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f3, f4, fb, fbw);
+        }
+      }
+      else if (wh == 3 && ww == 3 && sv == 2 && sh == 2) MNV_POOL_BWD(3, 3, 2, 2);
       else if (wh == 2 && ww == 2 && sv == 2 && sh == 2) MNV_POOL_BWD(2, 2, 2, 2);
       else if (wh == 3 && ww == 3 && sv == 3 && sh == 3) MNV_POOL_BWD(3, 3, 3, 3);
       else if (wh == 3 && ww == 3 && sv == 1 && sh == 1) MNV_POOL_BWD(3, 3, 1, 1);
