@@ -61,6 +61,10 @@ struct GemmParams {
   int bn, m_tiles, n_tiles, splits, stages_per_split, k_stages;
   int use_ktab;         // A_IM2COL_FWD: k -> (offset, kh, kw) table in shared memory
   int spi;              // backward-filter with TMA-fed top_diff: k-stages per image (K padded per image), else 0
+  unsigned wait_hint;   // mbarrier.try_wait suspend-time hint (ns)
+  int stages;           // smem ring depth: 4 (bn <= 256) or 3 (wide tile, 256 < bn <= 384)
+  int stage_bytes;      // A tile + B tile bytes per ring slot
+  int wide;             // 1: one 128 x bn tile as two UMMA halves of bn/2 columns sharing the A tile, single accumulator
 };
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -102,7 +106,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint = 0x989680u) {
   // try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires, so a
   // long hint keeps the poll loop out of the issue slots the gather warps need.
   uint32_t done = 0;
@@ -113,7 +117,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "r"(bar), "r"(parity), "r"(hint)
         : "memory");
     if (done) return;
     uint64_t now = globaltimer_ns();
@@ -524,9 +528,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-template <int AM, int BMD, bool BTMA>
+template <int AM, int BMD, bool BTMA, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p,
                                                                 const __grid_constant__ CUtensorMap tmap_b) {
+  // WIDE: one 128 x bn tile (256 < bn <= 384) as two UMMA halves sharing the A tile, single TMEM accumulator,
+  // 3-deep ring of 64 KB slots; otherwise bn <= 256, two accumulators, 4-deep ring of 48 KB slots.
+  constexpr int kNStages = WIDE ? 3 : kStages;
+  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : kStageBytes;
+  constexpr int kNAcc = WIDE ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of address bits [7,10)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     // full: TMA-fed B: the 4 warps of the slot's producer group + the TMA thread's arrive.expect_tx;
     //       gathered B: all 16 producer warps
-    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }   // kNStages of them are used
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     fence_barrier_init();
   }
@@ -573,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
-      mbar_wait(tfull0 + 8 * acc_stage, acc_phase);
+      mbar_wait(tfull0 + 8 * acc_stage, acc_phase, p.wait_hint);
       tc_fence_after();
       const int m = t.mt * BM + warp * 32 + lane;
       const int n0 = t.nt * p.bn;
@@ -606,57 +615,66 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc_stage);
-      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      if (++acc_stage == kNAcc) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     // The whole warp walks the pipeline (so every lane reaches the final __syncthreads together);
     // lane 0 alone issues tcgen05.mma / tcgen05.commit.
-    const uint32_t idesc = make_idesc(p.bn);
+    const int bnh = WIDE ? p.bn / 2 : p.bn;           // columns per UMMA instruction
+    const uint32_t idesc = make_idesc(bnh);
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
-      mbar_wait(tempty0 + 8 * acc_stage, acc_phase ^ 1);  // epilogue drained this accumulator
+      mbar_wait(tempty0 + 8 * acc_stage, acc_phase ^ 1, p.wait_hint);  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc_stage * BN_MAX);
       for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
-        mbar_wait(full0 + 8 * stage, phase);
+        mbar_wait(full0 + 8 * stage, phase, p.wait_hint);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_base + stage * kStageBytes;
+          const uint32_t a_addr = smem_base + stage * kSBytes;
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes inside the swizzle span
-            umma_tf32(tmem_d, make_sw128_desc(a_addr + kk * 32), make_sw128_desc(b_addr + kk * 32), idesc,
-                      (ks > t.ks_begin || kk > 0) ? 1u : 0u);
+            const uint32_t acc = (ks > t.ks_begin || kk > 0) ? 1u : 0u;
+            const uint64_t adesc = make_sw128_desc(a_addr + kk * 32);
+            umma_tf32(tmem_d, adesc, make_sw128_desc(b_addr + kk * 32), idesc, acc);
+            if (WIDE)   // second half of the columns: same A tile, B rows bnh.., TMEM columns bnh..
+              umma_tf32(tmem_d + bnh, adesc, make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
           }
           umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
           if (ks + 1 == t.ks_end) umma_commit(tfull0 + 8 * acc_stage);  // accumulator complete
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kNStages) { stage = 0; phase ^= 1; }
       }
-      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      if (++acc_stage == kNAcc) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else if (warp == 5) {
     // ===================== TMA producer for B =====================
     if (BTMA && lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4;   // the whole box, OOB rows/cols arrive as zeros
+      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4;   // the whole box(es), OOB rows/cols arrive as zeros
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         TileCoord t = decode_tile(p, tile);
         for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          mbar_wait(empty0 + 8 * stage, phase ^ 1, p.wait_hint);
           mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
-          const uint32_t dst = smem_base + stage * kStageBytes + kABytes;
-          if (p.spi > 0) {   // top_diff as (pixel, channel, image): one image's 32-pixel slab per stage
-            int img = ks / p.spi;
-            tma_load_3d(dst, &tmap_b, full0 + 8 * stage, (ks - img * p.spi) * BK, t.nt * p.bn, img);
-          } else {
-            tma_load_2d(dst, &tmap_b, full0 + 8 * stage, ks * BK, t.nt * p.bn);
+          const uint32_t dst = smem_base + stage * kSBytes + kABytes;
+          const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;   // a TMA box has at most 256 rows
+          for (int h = 0; h < halves; ++h) {
+            const uint32_t d2 = dst + h * rows * 128;
+            const int n0 = t.nt * p.bn + h * rows;
+            if (p.spi > 0) {   // top_diff as (pixel, channel, image): one image's 32-pixel slab per stage
+              int img = ks / p.spi;
+              tma_load_3d(d2, &tmap_b, full0 + 8 * stage, (ks - img * p.spi) * BK, n0, img);
+            } else {
+              tma_load_2d(d2, &tmap_b, full0 + 8 * stage, ks * BK, n0);
+            }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kNStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -670,18 +688,19 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       // L2 latency is covered by thread-level parallelism rather than by one warp's scoreboard (a warp's
       // outstanding LDGs share scoreboard slots: register look-ahead inside one warp does not overlap).
       const int pw = warp - kProducerWarp0;                 // 0..15
-      const int grp = pw >> 2;                              // ring slot owned by this group
+      const int grp = pw >> 2;                              // ring slot owned by this group (groups >= kNStages idle)
+      constexpr int ngrp = kNStages;
       const int gt = threadIdx.x - kProducerWarp0 * 32 - grp * 128;   // 0..127: tile row (MC) / chunk id (KC)
       const int kc_kq = gt & 7, kc_row0 = gt >> 3;          // KC mapping: rows kc_row0 + 16*i, chunk column kc_kq
       const uint32_t slot_full = full0 + 8 * grp, slot_empty = empty0 + 8 * grp;
-      const uint32_t a_tile = smem_base + grp * kStageBytes;
+      const uint32_t a_tile = smem_base + grp * kSBytes;
       uint32_t uses = 0;                                    // completed uses of this slot -> wait parity
       uint32_t cnt = 0;                                     // global k-stage counter at tile start
       float va[32];
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; grp < ngrp && tile < total_tiles; tile += gridDim.x) {
         TileCoord t = decode_tile(p, tile);
         const int nks = t.ks_end - t.ks_begin;
-        int ks = t.ks_begin + ((grp - static_cast<int>(cnt & 3u)) & 3);   // this group's first stage in the tile
+        int ks = t.ks_begin + (grp + ngrp - static_cast<int>(cnt % static_cast<uint32_t>(ngrp))) % ngrp;   // this group's first stage in the tile
         cnt += static_cast<uint32_t>(nks);
         if (ks >= t.ks_end) continue;
         ARow arow = {};
@@ -705,8 +724,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           else a_gatherN<AM, 32>(p, arow, k * BK, va);
         };
         load(ks);
-        for (; ks < t.ks_end; ks += 4) {
-          mbar_wait(slot_empty, (uses & 1u) ^ 1u);
+        for (; ks < t.ks_end; ks += ngrp) {
+          mbar_wait(slot_empty, (uses & 1u) ^ 1u, p.wait_hint);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(kc_row0 + 16 * q, kc_kq) : sw128_off(gt, q);
@@ -716,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive_relaxed(slot_full);
           ++uses;
-          if (ks + 4 < t.ks_end) load(ks + 4);   // lands while the other three groups' stages are consumed
+          if (ks + ngrp < t.ks_end) load(ks + ngrp);   // lands while the other groups' stages are consumed
         }
       }
     } else {
@@ -756,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
         if (!BTMA) b_gather<BMD>(p, n_base, b_row0, b_iters, ks * BK + b_kq * 4, vb[BTMA ? 0 : l]);
       };
       auto store = [&](int l) {
-        const uint32_t a_tile = smem_base + stage * kStageBytes;
+        const uint32_t a_tile = smem_base + stage * kSBytes;
         const uint32_t b_tile = a_tile + kABytes;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -782,12 +801,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
 #pragma unroll
         for (int l = 0; l < LOOK; ++l) {
           if (ks + l < t.ks_end) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, p.wait_hint);
             store(l);
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive_relaxed(full0 + 8 * stage);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == kNStages) { stage = 0; phase ^= 1; }
             if (ks + l + LOOK < t.ks_end) load(l, ks + l + LOOK);  // flies while the ring drains
           }
         }
@@ -833,6 +852,8 @@ __global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static std::atomic<int> g_opt_wait_hint{100};  // mbarrier.try_wait suspend hint in ns (tuning)
+static std::atomic<int> g_opt_no_wide{0};     // 1: never use the wide (bn > 256) tile (tuning)
 static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
 static std::atomic<int> g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
 static std::atomic<int> g_opt_no_tma{0};     // 1: gather B with threads even where TMA applies (debug)
@@ -895,11 +916,23 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
   }
 }
 
-static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials) {
+static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_wide = false) {
   p.m_tiles = (p.M + BM - 1) / BM;
-  int n_tiles = (p.N + BN_MAX - 1) / BN_MAX;
-  int bn = (p.N + n_tiles - 1) / n_tiles;
-  bn = (bn + 15) / 16 * 16;
+  p.wide = 0; p.stages = kStages; p.stage_bytes = kStageBytes;
+  int n_tiles, bn;
+  if (allow_wide && p.N > BN_MAX && !g_opt_no_wide.load()) {
+    // 256 < N: tiles of up to 384 columns (two UMMA halves share one gathered A tile) in a 3-deep ring of
+    // 64 KB slots -- the same 192 KB of shared memory as the 4 x 48 KB ring of the narrow tile
+    constexpr int kWideMax = 384;
+    n_tiles = (p.N + kWideMax - 1) / kWideMax;
+    bn = (p.N + n_tiles - 1) / n_tiles;
+    bn = (bn + 31) / 32 * 32;
+    if (bn > BN_MAX) { p.wide = 1; p.stages = 3; p.stage_bytes = kABytes + kWideMax * BK * 4; }
+  } else {
+    n_tiles = (p.N + BN_MAX - 1) / BN_MAX;
+    bn = (p.N + n_tiles - 1) / n_tiles;
+    bn = (bn + 15) / 16 * 16;
+  }
   if (bn < 16) bn = 16;
   p.bn = bn;
   p.n_tiles = (p.N + bn - 1) / bn;
@@ -920,23 +953,31 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials) {
   }
   p.stages_per_split = (p.k_stages + splits - 1) / splits;
   p.splits = (p.k_stages + p.stages_per_split - 1) / p.stages_per_split;  // no empty split
+  // The wide tile has a single TMEM accumulator, so its epilogue is not hidden behind the next tile's
+  // mainloop: worth it only when a tile's mainloop is long (measured break-even ~70 k-stages).
+  if (p.wide && p.stages_per_split < 96) plan_tiles(p, ws_bytes_for_partials, false);
 }
 
-template <int AM, int BMD, bool BTMA>
-static int launch_umma(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s) {
+template <int AM, int BMD, bool BTMA, bool WIDE>
+static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s) {
   // opt in to >48 KB dynamic shared memory once per (device, instantiation)
   static std::atomic<uint64_t> attr_done{0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD, BTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD, BTMA, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
   int grid = static_cast<int>(total < kNumSMs ? total : kNumSMs);
-  umma_gemm_kernel<AM, BMD, BTMA><<<grid, kThreads, kSmemBytes, s>>>(p, tm);
+  umma_gemm_kernel<AM, BMD, BTMA, WIDE><<<grid, kThreads, kSmemBytes, s>>>(p, tm);
   return finish_launch();
+}
+template <int AM, int BMD, bool BTMA>
+static int launch_umma(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s) {
+  if (BTMA && p.wide) return launch_umma_w<AM, BMD, BTMA, BTMA>(p, tm, s);   // the wide tile exists on the TMA-fed path only
+  return launch_umma_w<AM, BMD, BTMA, false>(p, tm, s);
 }
 
 template <int AM, int BMD>
@@ -962,8 +1003,8 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
       ws_bytes -= need;
     }
   }
-  plan_tiles(p, ws ? ws_bytes : 0);
-  p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
+  const bool tma_ok = BMD == B_KMAJOR && p.b_vec && !g_opt_no_tma.load() && get_encode_fn() != nullptr;
+  plan_tiles(p, ws ? ws_bytes : 0, tma_ok);
   p.use_ktab = 0;
   if (AM == A_IM2COL_FWD && p.k_stages * BK <= kKtabMax && !g_opt_no_ktab.load()) {
     long long img = static_cast<long long>(p.Ci) * p.H * p.W;
@@ -973,7 +1014,11 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   bool tma = false;
-  if (BMD == B_KMAJOR && p.b_vec && !g_opt_no_tma.load()) tma = make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.bn);
+  if (tma_ok) {
+    tma = make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.wide ? p.bn / 2 : p.bn);
+    if (!tma && p.wide) plan_tiles(p, ws ? ws_bytes : 0, false);   // the wide tile needs the TMA-fed path
+  }
+  p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
   int rc;
   if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
   else rc = launch_umma<AM, BMD, false>(p, tm, s);
@@ -985,7 +1030,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0;
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -1015,6 +1060,8 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_tma") return g_opt_no_tma.exchange(value);
   if (k == "no_fwd_bwd") return g_opt_no_fwd_bwd.exchange(value);
   if (k == "no_ktab") return g_opt_no_ktab.exchange(value);
+  if (k == "wait_hint") return g_opt_wait_hint.exchange(value);
+  if (k == "no_wide") return g_opt_no_wide.exchange(value);
   return -1;
 }
 
@@ -1137,11 +1184,11 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
   long long kpad = static_cast<long long>(N) * p.spi * BK;
   if (!fits_int(kpad)) return MNV_EUNSUPPORTED;
   p.K = static_cast<int>(kpad);          // k-stages = N * spi; validity is per-pixel inside the gathers
-  plan_tiles(p, ws_left);
+  plan_tiles(p, ws_left, true);
   p.partial = p.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  if (!make_dy_tmap(&tm, dy_tma, P, pitch, Co, N, p.bn)) {
+  if (!make_dy_tmap(&tm, dy_tma, P, pitch, Co, N, p.wide ? p.bn / 2 : p.bn)) {
     p.spi = 0; p.K = static_cast<int>(K);
     return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, ws, ws_left, s);
   }

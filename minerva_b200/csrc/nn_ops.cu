@@ -776,7 +776,9 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd5_kernel(const float* __restric
       for (int u = 0; u < kLrnChunk; ++u) {
         int head = c0 + u;
         float tdh = ctd[u], sch = csc[u];
-        float r = __fdiv_rn(__fmul_rn(tdh, ctp[u]), sch);      // +0 past C (0*0/1)
+        // scale >= 1, so the approximate divide (<= 2 ulp, no special-operand slow path -- half of top_diff*top is
+        // exactly 0 after ReLU/pooling and IEEE division takes its slow path on those) is safe here
+        float r = __fdividef(__fmul_rn(tdh, ctp[u]), sch);     // +0 past C (0*0/1)
         acc = __fadd_rn(acc, r);
         acc = __fsub_rn(acc, r4);
         r4 = r3; r3 = r2; r2 = r1; r1 = r0; r0 = r;
