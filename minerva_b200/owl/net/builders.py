@@ -78,25 +78,25 @@ def build_mnist_mlp(backend=None):
 
 
 def _inception(net, name, btm, c1, c3r, c3, c5r, c5, cp):
-    a = _conv_relu(net, name + "/1x1", btm, c1, 1, std=0.03, bias=0.2)
-    b = _conv_relu(net, name + "/3x3_reduce", btm, c3r, 1, std=0.09, bias=0.2)
-    b = _conv_relu(net, name + "/3x3", b, c3, 3, 1, 1, std=0.03, bias=0.2)
-    c = _conv_relu(net, name + "/5x5_reduce", btm, c5r, 1, std=0.2, bias=0.2)
-    c = _conv_relu(net, name + "/5x5", c, c5, 5, 1, 2, std=0.03, bias=0.2)
+    a = _conv_relu(net, name + "/1x1", btm, c1, 1, std=0.03, bias=0.2, filler="xavier")
+    b = _conv_relu(net, name + "/3x3_reduce", btm, c3r, 1, std=0.09, bias=0.2, filler="xavier")
+    b = _conv_relu(net, name + "/3x3", b, c3, 3, 1, 1, std=0.03, bias=0.2, filler="xavier")
+    c = _conv_relu(net, name + "/5x5_reduce", btm, c5r, 1, std=0.2, bias=0.2, filler="xavier")
+    c = _conv_relu(net, name + "/5x5", c, c5, 5, 1, 2, std=0.03, bias=0.2, filler="xavier")
     net.add_unit(PoolingUnit(name + "/pool", btm, name + "/pool", 3, 1, 1))
-    d = _conv_relu(net, name + "/pool_proj", name + "/pool", cp, 1, std=0.1, bias=0.2)
+    d = _conv_relu(net, name + "/pool_proj", name + "/pool", cp, 1, std=0.1, bias=0.2, filler="xavier")
     net.add_unit(ConcatUnit(name + "/output", [a, b, c, d], name + "/output"))
     return name + "/output"
 
 
 def _aux_head(net, name, btm, num_classes):
     net.add_unit(PoolingUnit(name + "/ave_pool", btm, name + "/ave_pool", 5, 3, 0, pool="avg"))
-    t = _conv_relu(net, name + "/conv", name + "/ave_pool", 128, 1, std=0.08, bias=0.2)
-    net.add_unit(FullyConnection(name + "/fc", t, name + "/fc", 1024, weight_std=0.02, bias_value=0.2))
+    t = _conv_relu(net, name + "/conv", name + "/ave_pool", 128, 1, std=0.08, bias=0.2, filler="xavier")
+    net.add_unit(FullyConnection(name + "/fc", t, name + "/fc", 1024, weight_std=0.02, bias_value=0.2, weight_filler="xavier"))
     net.add_unit(ReluUnit(name + "/relu_fc", name + "/fc", name + "/fc_r"))
     net.add_unit(DropoutUnit(name + "/drop_fc", name + "/fc_r", name + "/fc_d", 0.7))
     net.add_unit(FullyConnection(name + "/classifier", name + "/fc_d", name + "/classifier", num_classes,
-                                 weight_std=0.0009765625, bias_value=0.0))
+                                 weight_std=0.0009765625, bias_value=0.0, weight_filler="xavier"))
     net.add_unit(SoftmaxUnit(name + "/loss", name + "/classifier", "label", name + "/prob", loss_weight=0.3))
 
 
@@ -105,12 +105,12 @@ def build_googlenet(backend=None, num_classes=1000):
     data{224,224,3,N}."""
     net = Net(backend)
     net.add_unit(DataUnit("data", ["data", "label"]))
-    t = _conv_relu(net, "conv1/7x7_s2", "data", 64, 7, 2, 3, std=0.015, bias=0.2)
+    t = _conv_relu(net, "conv1/7x7_s2", "data", 64, 7, 2, 3, std=0.015, bias=0.2, filler="xavier")
     net.units[1].need_bp = False
     net.add_unit(PoolingUnit("pool1/3x3_s2", t, "pool1", 3, 2))
     net.add_unit(LRNUnit("pool1/norm1", "pool1", "norm1", 5, 1e-4, 0.75))
-    t = _conv_relu(net, "conv2/3x3_reduce", "norm1", 64, 1, std=0.1, bias=0.2)
-    t = _conv_relu(net, "conv2/3x3", t, 192, 3, 1, 1, std=0.03, bias=0.2)
+    t = _conv_relu(net, "conv2/3x3_reduce", "norm1", 64, 1, std=0.1, bias=0.2, filler="xavier")
+    t = _conv_relu(net, "conv2/3x3", t, 192, 3, 1, 1, std=0.03, bias=0.2, filler="xavier")
     net.add_unit(LRNUnit("conv2/norm2", t, "norm2", 5, 1e-4, 0.75))
     net.add_unit(PoolingUnit("pool2/3x3_s2", "norm2", "pool2", 3, 2))
     t = _inception(net, "inception_3a", "pool2", 64, 96, 128, 16, 32, 32)
@@ -128,7 +128,7 @@ def build_googlenet(backend=None, num_classes=1000):
     t = _inception(net, "inception_5b", t, 384, 192, 384, 48, 128, 128)
     net.add_unit(PoolingUnit("pool5/7x7_s1", t, "pool5", 7, 1, 0, pool="avg"))
     net.add_unit(DropoutUnit("pool5/drop", "pool5", "pool5_d", 0.4))
-    net.add_unit(FullyConnection("loss3/classifier", "pool5_d", "loss3/classifier", num_classes, weight_std=0.01))
+    net.add_unit(FullyConnection("loss3/classifier", "pool5_d", "loss3/classifier", num_classes, weight_std=0.01, weight_filler="xavier"))
     net.add_unit(SoftmaxUnit("loss3/loss3", "loss3/classifier", "label", "prob"))
     net.base_lr = net.current_lr = 0.01
     net.momentum, net.base_weight_decay = 0.9, 2e-4

@@ -110,3 +110,29 @@ def test_small_configs_train(gpu_owl, builder, shape, batch):
         tr.step()
     l1 = net.get_loss_units()[0].getloss()
     assert np.isfinite(l0) and np.isfinite(l1) and l1 < 0.7 * l0, (l0, l1)
+
+
+def test_googlenet_graph_runs(gpu_owl):
+    """BASELINE config 5 (GoogLeNet, 3 loss heads, inception concat/slice, avg pools) at reduced batch: one
+    full training step runs, every weighted unit gets finite gradients, and the loss is ~ln(1000) at init."""
+    import minerva_b200.owl.net as onet
+    gpu_owl.set_seed(3)
+    net = onet.build_googlenet()
+    batch = 4
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((batch, 3, 224, 224)).astype(np.float32)
+    onehot = np.zeros((batch, 1000), np.float32)
+    onehot[np.arange(batch), rs.randint(0, 1000, batch)] = 1
+    du = net.get_data_unit()
+    du.data, du.label = gpu_owl.from_numpy(x), gpu_owl.from_numpy(onehot)
+    net.batch_size = batch
+    tr = onet.NetTrainer(net, None)
+    net.forward("TRAIN")
+    net.backward("TRAIN")
+    for uid in net.get_weighted_unit_ids():
+        u = net.units[uid]
+        g = u.weightgrad.to_numpy()
+        assert np.isfinite(g).all() and np.abs(g).max() > 0, u.name
+    losses = [lu.getloss() for lu in net.get_loss_units()]
+    assert len(losses) == 3 and all(np.isfinite(l) and np.log(1000) - 1.0 < l < np.log(1000) + 3.0 for l in losses), losses
+    tr.step()
