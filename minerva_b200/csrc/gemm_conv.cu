@@ -40,7 +40,14 @@ namespace mnv {
 // ------------------------------------------------------------------------------------------------
 // problem description shared by the tcgen05 kernel, the SIMT checker and the split-K reducer
 // ------------------------------------------------------------------------------------------------
-enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD = 3 };
+enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD = 3, A_TMA = 4 };
+// A_TMA sub-modes (GemmParams::a_mode): how the TMA thread fetches the 128 x 32 A tile of a k-stage
+//   TMA_A_IM2COL_K : channels-last activation copy through an im2col tensor map; one box of 128 output pixels
+//                    x 32 channels of one filter tap => K-major tile (forward conv, stride-1 backward-data)
+//   TMA_A_TILED_MN : column-major matrix; 4 boxes of 32 m x 32 k => MN-major tile (MatMult)
+//   TMA_A_IM2COL_MN: im2col map again, but the 32 pixels are the k axis and 4 boxes of 32 channels (each box its
+//                    own (tap, channel chunk)) the m axis => MN-major tile (backward-filter)
+enum : int { TMA_A_IM2COL_K = 1, TMA_A_TILED_MN = 2, TMA_A_IM2COL_MN = 3 };
 enum : int { B_KMAJOR = 0, B_DY_WGRAD = 1 };
 
 struct GemmParams {
@@ -65,6 +72,9 @@ struct GemmParams {
   int stages;           // smem ring depth: 4 (bn <= 256) or 3 (wide tile, 256 < bn <= 384)
   int stage_bytes;      // A tile + B tile bytes per ring slot
   int wide;             // 1: one 128 x bn tile as two UMMA halves of bn/2 columns sharing the A tile, single accumulator
+  int a_mode;           // A_TMA sub-mode (TMA_A_*), 0 otherwise
+  int cpt;              // 32-channel chunks per filter tap (TMA_A_IM2COL_K: k-stage = tap * cpt + chunk)
+  int out_mode;         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
 };
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -186,8 +196,22 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
 // B=TF32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major ? 1u << 15 : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(BM >> 4) << 24);
+}
+// MN-major tf32 operand.  32-bit MN-major operands exist in one shared-memory layout only, SWIZZLE_128B_BASE32B
+// (32-byte chunks swizzled inside the 128 B span by row & 3; TMA writes it as CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// a row is 32 consecutive m of one k (128 B), 4 k rows make a 512 B swizzle atom (SBO = 512 B between atoms
+// along k), the next 32-m chunk starts LBO = 4096 B later.  One tf32 UMMA (K = 8) reads two atoms per chunk.
+__device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(4096 >> 4) << 16;         // LBO
+  d |= static_cast<uint64_t>(512 >> 4) << 32;          // SBO
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;                 // SWIZZLE_128B_BASE32B
+  return d;
 }
 // byte offset of 16-byte chunk `kq` of row `r` inside a swizzled tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int kq) { return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(kq ^ (r & 7)) << 4); }
@@ -234,7 +258,15 @@ __device__ __forceinline__ float b_elem(const GemmParams& p, int n, int k) {
   int img = k / hw, pix = k - img * hw;
   return __ldg(p.b + (static_cast<size_t>(img) * p.Co + n) * hw + pix);
 }
+__device__ __forceinline__ bool out_row_ok(const GemmParams& p, int m) {
+  if (m >= p.M) return false;
+  return p.out_mode == 0 || ((m >> 5) % p.cpt) * 32 + (m & 31) < p.Ci;   // padded channels of a tap carry no output
+}
 __device__ __forceinline__ size_t out_index(const GemmParams& p, int m, int n) {
+  if (p.out_mode == 1) {   // filter_diff[co = n][ci][r][s]; tap (kh,kw) of the correlation is filter element ff-1-tap
+    int chunk = m >> 5, tap = chunk / p.cpt, ci = (chunk - tap * p.cpt) * 32 + (m & 31), ff = p.fh * p.fw;
+    return static_cast<size_t>(n) * p.col_stride + static_cast<size_t>(ci) * ff + (ff - 1 - tap);
+  }
   int img = m / p.P, pix = m - img * p.P;
   return static_cast<size_t>(img) * p.img_stride + pix + static_cast<size_t>(n) * p.col_stride;
 }
@@ -513,37 +545,65 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// im2col-mode load: the box starts at pixel (w, h, n) of the (C, W, H, N) tensor -- a position of the filter
+// window's origin inside the bounding box the map was encoded with -- shifted by the tap offsets (kw, kh), and
+// walks `pixelsPerColumn` window positions along W, then H, then N; out-of-tensor elements arrive as zeros.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c, int w, int h,
+                                                   int n, int kw, int kh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(static_cast<uint16_t>(kw)), "h"(static_cast<uint16_t>(kh))
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kRasterM = 16;
 struct TileCoord { int mt, nt, split, ks_begin, ks_end; };
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
   TileCoord t;
-  t.nt = tile % p.n_tiles;
-  int rest = tile / p.n_tiles;
-  t.mt = rest % p.m_tiles;
-  t.split = rest / p.m_tiles;
+  // Grouped rasterisation: inside one K split the tile index walks kRasterM m-tiles down, then one n-tile
+  // across, so a wave of 148 CTAs covers a ~16 x 9 block of tiles instead of 4.6 full rows: the operand rows
+  // a wave touches drop from (4.6*128 + N) to (16*128 + 9*bn), which is what keeps an 8192^3 GEMM's B
+  // (268 MB > L2) from being re-fetched from HBM every wave.
+  const int per_split = p.m_tiles * p.n_tiles;
+  t.split = tile / per_split;
+  int id = tile - t.split * per_split;
+  const int band = kRasterM * p.n_tiles;
+  const int g = id / band;
+  id -= g * band;
+  const int first_m = g * kRasterM;
+  const int gm = min(kRasterM, p.m_tiles - first_m);
+  t.nt = id / gm;
+  t.mt = first_m + (id - t.nt * gm);
   t.ks_begin = t.split * p.stages_per_split;
   t.ks_end = min(p.k_stages, t.ks_begin + p.stages_per_split);
   return t;
 }
 
-template <int AM, int BMD, bool BTMA, bool WIDE>
+template <int AM, int BMD, bool BTMA, int RING>
 __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p,
-                                                                const __grid_constant__ CUtensorMap tmap_b) {
+                                                                const __grid_constant__ CUtensorMap tmap_b,
+                                                                const __grid_constant__ CUtensorMap tmap_a) {
   // WIDE: one 128 x bn tile (256 < bn <= 384) as two UMMA halves sharing the A tile, single TMEM accumulator,
   // 3-deep ring of 64 KB slots; otherwise bn <= 256, two accumulators, 4-deep ring of 48 KB slots.
-  constexpr int kNStages = WIDE ? 3 : kStages;
-  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : kStageBytes;
+  // RING 2 (both operands through TMA, bn <= 128): 6-deep ring of 32 KB slots -- a 128 x 96 tile consumes a stage
+  // in ~200 cycles, so four stages in flight do not cover the TMA round trip.
+  constexpr bool WIDE = RING == 1, DEEP = RING == 2;
+  constexpr int kNStages = WIDE ? 3 : DEEP ? 6 : kStages;
+  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : DEEP ? kABytes + 128 * BK * 4 : kStageBytes;
   constexpr int kNAcc = WIDE ? 1 : 2;
+  constexpr int kMaxStages = 6;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of address bits [7,10)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty, then the TMEM base slot
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
-  const uint32_t tfull0 = smem_u32(bars + 2 * kStages), tempty0 = smem_u32(bars + 2 * kStages + 2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
+  const uint32_t tfull0 = smem_u32(bars + 2 * kMaxStages), tempty0 = smem_u32(bars + 2 * kMaxStages + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   const uint32_t ktab0 = smem_u32(smem + kStages * kStageBytes + 256);   // uint32 ktab[kKtabMax]
   const uint32_t smem_base = smem_u32(smem);
 
@@ -553,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) {
     // full: TMA-fed B: the 4 warps of the slot's producer group + the TMA thread's arrive.expect_tx;
     //       gathered B: all 16 producer warps
-    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }   // kNStages of them are used
+    for (int s = 0; s < kNStages; ++s) { mbar_init(full0 + 8 * s, AM == A_TMA ? 1 : BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }   // kNStages of them are used
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     fence_barrier_init();
   }
@@ -586,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       tc_fence_after();
       const int m = t.mt * BM + warp * 32 + lane;
       const int n0 = t.nt * p.bn;
-      const bool row_ok = m < p.M;
+      const bool row_ok = out_row_ok(p, m);
       float* dst;
       long long cstride;
       if (p.splits > 1) {  // partial[split][n][m]
@@ -622,7 +682,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     // The whole warp walks the pipeline (so every lane reaches the final __syncthreads together);
     // lane 0 alone issues tcgen05.mma / tcgen05.commit.
     const int bnh = WIDE ? p.bn / 2 : p.bn;           // columns per UMMA instruction
-    const uint32_t idesc = make_idesc(bnh);
+    const bool a_mn = AM == A_TMA && p.a_mode != TMA_A_IM2COL_K;
+    const uint32_t idesc = make_idesc(bnh, a_mn);
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -639,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes inside the swizzle span
             const uint32_t acc = (ks > t.ks_begin || kk > 0) ? 1u : 0u;
-            const uint64_t adesc = make_sw128_desc(a_addr + kk * 32);
+            const uint64_t adesc = a_mn ? make_sw128_desc_mn(a_addr + kk * 1024) : make_sw128_desc(a_addr + kk * 32);
             umma_tf32(tmem_d, adesc, make_sw128_desc(b_addr + kk * 32), idesc, acc);
             if (WIDE)   // second half of the columns: same A tile, B rows bnh.., TMEM columns bnh..
               umma_tf32(tmem_d + bnh, adesc, make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
@@ -656,12 +717,46 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     // ===================== TMA producer for B =====================
     if (BTMA && lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4;   // the whole box(es), OOB rows/cols arrive as zeros
+      // the whole box(es), OOB rows/cols arrive as zeros
+      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4 + (AM == A_TMA ? kABytes : 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         TileCoord t = decode_tile(p, tile);
+        // A_TMA: position of the tile's first row
+        int a_w = 0, a_h = 0, a_n = 0;
+        int a_kw[4] = {0, 0, 0, 0}, a_kh[4] = {0, 0, 0, 0}, a_c[4] = {0, 0, 0, 0};
+        if (AM == A_TMA) {
+          const int m0 = t.mt * BM;
+          if (p.a_mode == TMA_A_IM2COL_K) {
+            a_n = m0 / p.P;
+            const int pix = m0 - a_n * p.P, oh = pix / p.Wo;
+            a_h = oh * p.sv - p.ph; a_w = (pix - oh * p.Wo) * p.sh - p.pw;
+          } else if (p.a_mode == TMA_A_IM2COL_MN) {
+            const int last = p.fh * p.fw * p.cpt - 1;   // rows past M still receive a (masked) box
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = min(t.mt * 4 + j, last), tap = chunk / p.cpt;
+              a_c[j] = (chunk - tap * p.cpt) * 32; a_kh[j] = tap / p.fw; a_kw[j] = tap - a_kh[j] * p.fw;
+            }
+          }
+        }
         for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1, p.wait_hint);
           mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
+          if (AM == A_TMA) {
+            const uint32_t a_dst = smem_base + stage * kSBytes, bar = full0 + 8 * stage;
+            if (p.a_mode == TMA_A_IM2COL_K) {
+              const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
+              tma_load_im2col_4d(a_dst, &tmap_a, bar, cc * BK, a_w, a_h, a_n, tap - kh * p.fw, kh);
+            } else if (p.a_mode == TMA_A_TILED_MN) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tma_load_2d(a_dst + j * 4096, &tmap_a, bar, t.mt * BM + 32 * j, ks * BK);
+            } else {   // k-stage = 32 output pixels of one image (p.spi stages per image)
+              const int img = ks / p.spi, pix = (ks - img * p.spi) * BK, oh = pix / p.Wo;
+              const int h = oh * p.sv - p.ph, w = (pix - oh * p.Wo) * p.sh - p.pw;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tma_load_im2col_4d(a_dst + j * 4096, &tmap_a, bar, a_c[j], w, h, img, a_kw[j], a_kh[j]);
+            }
+          }
           const uint32_t dst = smem_base + stage * kSBytes + kABytes;
           const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;   // a TMA box has at most 256 rows
           for (int h = 0; h < halves; ++h) {
@@ -681,7 +776,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     __syncwarp();
   } else {
     // ===================== gather producers =====================
-    if (BTMA) {
+    if constexpr (AM == A_TMA) {
+      // both operands come through TMA: these warps have nothing to do
+    } else if (BTMA) {
       // Stage-interleaved warp groups: group g (4 warps = 128 threads, one thread per tile row, all 32 k
       // of the stage) owns ring slot g, i.e. every 4th k-stage.  A group's loads for its next stage are
       // issued right after it hands the current one over and have three other stages' time to land, so
@@ -826,6 +923,7 @@ __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams 
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < mn;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
     int m = static_cast<int>(t % p.M), n = static_cast<int>(t / p.M);
+    if (!out_row_ok(p, m)) continue;
     float acc = __ldg(p.partial + t);
     for (int s = 1; s < p.splits; ++s) acc += __ldg(p.partial + static_cast<size_t>(s) * mn + t);
     if (p.bias) acc += __ldg(p.bias + n);
@@ -858,6 +956,12 @@ static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead 
 static std::atomic<int> g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
 static std::atomic<int> g_opt_no_tma{0};     // 1: gather B with threads even where TMA applies (debug)
 static std::atomic<int> g_opt_no_fwd_bwd{0};
+static std::atomic<int> g_opt_no_tma_a{0};   // bit 0: no TMA-im2col fprop/dgrad, bit 1: no TMA MatMult A, bit 2: no TMA wgrad (debug / tuning)
+static std::atomic<int> g_opt_tma_tf32{1};   // operand maps typed TFLOAT32: TMA then rounds fp32 -> tf32 to nearest on the way in (measured:
+                                             // norm-rel error vs fp64 2.9e-4 unbiased, against 7.7e-4 with a -7e-4 bias for FLOAT32 maps,
+                                             // whose low mantissa bits the tensor core just drops); 0 = FLOAT32 maps (debug)
+static std::atomic<int> g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it applies, ignoring the profitability rule (tuning)
+static std::atomic<int> g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
 static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug) // 1: use the generic backward-data gather for stride 1 too (debug)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -874,6 +978,12 @@ static EncodeTiledFn get_encode_fn() {
   cached.store(fn, std::memory_order_release);
   return fn;
 }
+// Operands staged by a pre-pass are rounded to TF32 there only when the tensor maps are plain FLOAT32 (rounding
+// twice would double-round); the SIMT checker reads them unrounded.
+static int prepass_round() { return (g_opt_tma_tf32.load() || g_opt_simt.load()) ? 0 : 1; }
+static CUtensorMapDataType tmap_dtype() {
+  return g_opt_tma_tf32.load() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
 // K-major fp32 matrix [rows][ld] seen as a 2-D tensor (k fastest); box = 32 k x bn rows, 128B swizzle.
 static bool make_b_tmap(CUtensorMap* tm, const float* b, int rows, int K, int ld, int bn) {
   EncodeTiledFn fn = get_encode_fn();
@@ -882,10 +992,114 @@ static bool make_b_tmap(CUtensorMap* tm, const float* b, int rows, int K, int ld
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(b), dims, strides, box, estr,
+  CUresult r = fn(tm, tmap_dtype(), 2, const_cast<float*>(b), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// column-major fp32 matrix [K][ld] (m fastest) as a 2-D tensor; box = 32 m x 32 k, 128B swizzle: the MN-major
+// operand slab of one 32-row chunk.
+static bool make_a_mn_tmap(CUtensorMap* tm, const float* a, int M, int K, int ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(M), static_cast<cuuint64_t>(K)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {32, BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, tmap_dtype(), 2, const_cast<float*>(a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn get_im2col_fn() {
+  static std::atomic<EncodeIm2colFn> cached{nullptr};
+  EncodeIm2colFn fn = cached.load(std::memory_order_acquire);
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr) return nullptr;
+  fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  cached.store(fn, std::memory_order_release);
+  return fn;
+}
+// Channels-last activation copy x[N][H][W][Cp] as a (C, W, H, N) im2col tensor.  The bounding box of the filter
+// window's origin is [-pad, dim + pad - (f-1)) per spatial axis, traversed with the convolution stride; one load
+// is 32 channels x `pixels` window positions (rows of 128 B, 128B swizzle).
+static bool make_im2col_tmap(CUtensorMap* tm, const float* x, int Cp, int W, int H, int N, int pw, int ph, int fw, int fh, int sh,
+                             int sv, int pixels, bool mn_major) {
+  EncodeIm2colFn fn = get_im2col_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cp), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cp) * 4, static_cast<cuuint64_t>(W) * Cp * 4, static_cast<cuuint64_t>(H) * W * Cp * 4};
+  int lower[2] = {-pw, -ph};
+  int upper[2] = {pw - (fw - 1), ph - (fh - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sh), static_cast<cuuint32_t>(sv), 1};
+  CUresult r = fn(tm, tmap_dtype(), 4, const_cast<float*>(x), dims, strides, lower, upper, BK, static_cast<cuuint32_t>(pixels), estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  // Drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KB (same correction as CUTLASS's
+  // make_im2col_tma_copy_desc applies).
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 &&
+      static_cast<unsigned long long>(N) * H * W * Cp * 4ull < 131072ull)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return true;
+}
+
+// x[n][c][hw] -> y[n][hw][Cp]: channels-last copy for the im2col tensor maps, channels C..Cp-1 zero (rounding to
+// TF32 is done by the TFLOAT32-typed tensor map).  Tiles go through shared memory so both sides stay coalesced.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cp, int HW,
+                                                           int tiles_c, int tiles_hw, long long total_tiles) {
+  // tile = 32 channels x 128 pixels: 16 independent 128-byte-per-warp loads per thread before the barrier
+  __shared__ float tile[32][129];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int tc = static_cast<int>(t % tiles_c);
+    const long long r = t / tiles_c;
+    const int th = static_cast<int>(r % tiles_hw);
+    const size_t n = static_cast<size_t>(r / tiles_hw);
+    const int c0 = tc * 32, h0 = th * 128;
+    const float* src = x + (n * C + c0) * HW + h0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = wid + 8 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int hw = lane + 32 * j;
+        tile[c][hw] = (c0 + c < C && h0 + hw < HW) ? __ldg(src + static_cast<size_t>(c) * HW + hw) : 0.f;
+      }
+    }
+    __syncthreads();
+    if (c0 + lane < Cp) {
+      float* dst = y + (n * HW + h0) * Cp + c0 + lane;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int hw = wid + 8 * i;
+        if (h0 + hw < HW) dst[static_cast<size_t>(hw) * Cp] = tile[lane][hw];
+      }
+    }
+    __syncthreads();
+  }
+}
+// B operand of the TMA-im2col convolutions: out[n][tap][c] (c < Kc = 32-channel chunks per tap, zero past C)
+//   = w[n*sn + c*sc + (flip ? ff-1-tap : tap)], TF32-rounded.
+__global__ void __launch_bounds__(kBlock) filter_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int C, int ff,
+                                                             int Kc, long long sn, long long sc, int flip, int round) {
+  size_t total = static_cast<size_t>(rows) * ff * Kc;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int c = static_cast<int>(t % Kc);
+    size_t rest = t / Kc;
+    int tap = static_cast<int>(rest % ff);
+    size_t n = rest / ff;
+    float v = c < C ? __ldg(w + n * sn + static_cast<size_t>(c) * sc + (flip ? ff - 1 - tap : tap)) : 0.f;
+    out[t] = round ? to_tf32(v) : v;
+  }
 }
 
 // top_diff[img][co][pitch] (pitch % 4 == 0, only the first P pixels of a row are real) as a 3-D tensor;
@@ -897,14 +1111,14 @@ static bool make_dy_tmap(CUtensorMap* tm, const float* dy, int P, int pitch, int
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * sizeof(float), static_cast<cuuint64_t>(pitch) * Co * sizeof(float)};
   cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(bn), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dy), dims, strides, box, estr,
+  CUresult r = fn(tm, tmap_dtype(), 3, const_cast<float*>(dy), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 // row-pitch repack for TMA: dst[r][0..inner) = src[r][0..inner), dst rows `pitch` floats apart
-__global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int inner, int pitch, size_t rows) {
+__global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int inner, int pitch, size_t rows, int round) {
   // one warp per row keeps both sides coalesced without integer division
   size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
@@ -912,7 +1126,8 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
   for (size_t r = warp; r < rows; r += nwarps) {
     const float* s = src + r * inner;
     float* d = dst + r * pitch;
-    for (int i = lane; i < inner; i += 32) d[i] = to_tf32(__ldg(s + i));   // TF32 round-to-nearest on the way
+    if (round) for (int i = lane; i < inner; i += 32) d[i] = to_tf32(__ldg(s + i));
+    else for (int i = lane; i < inner; i += 32) d[i] = __ldg(s + i);
   }
 }
 
@@ -958,26 +1173,37 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
   if (p.wide && p.stages_per_split < 96) plan_tiles(p, ws_bytes_for_partials, false);
 }
 
-template <int AM, int BMD, bool BTMA, bool WIDE>
-static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s) {
+static const CUtensorMap& null_tmap() { static CUtensorMap z = {}; return z; }
+template <int AM, int BMD, bool BTMA, int RING>
+static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s, const CUtensorMap& tm_a = null_tmap()) {
   // opt in to >48 KB dynamic shared memory once per (device, instantiation)
   static std::atomic<uint64_t> attr_done{0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD, BTMA, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<AM, BMD, BTMA, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
   int grid = static_cast<int>(total < kNumSMs ? total : kNumSMs);
-  umma_gemm_kernel<AM, BMD, BTMA, WIDE><<<grid, kThreads, kSmemBytes, s>>>(p, tm);
+  umma_gemm_kernel<AM, BMD, BTMA, RING><<<grid, kThreads, kSmemBytes, s>>>(p, tm, tm_a);
   return finish_launch();
 }
 template <int AM, int BMD, bool BTMA>
 static int launch_umma(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s) {
   if (BTMA && p.wide) return launch_umma_w<AM, BMD, BTMA, BTMA>(p, tm, s);   // the wide tile exists on the TMA-fed path only
   return launch_umma_w<AM, BMD, BTMA, false>(p, tm, s);
+}
+
+// both operands through TMA
+static int launch_umma_tma(const GemmParams& p, const CUtensorMap& tm_a, const CUtensorMap& tm_b, cudaStream_t s) {
+  int rc = p.wide      ? launch_umma_w<A_TMA, B_KMAJOR, true, 1>(p, tm_b, s, tm_a)
+           : (p.bn <= 128 && !g_opt_no_deep.load()) ? launch_umma_w<A_TMA, B_KMAJOR, true, 2>(p, tm_b, s, tm_a)
+                          : launch_umma_w<A_TMA, B_KMAJOR, true, 0>(p, tm_b, s, tm_a);
+  if (rc || p.splits == 1) return rc;
+  splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
+  return finish_launch();
 }
 
 template <int AM, int BMD>
@@ -995,7 +1221,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
     size_t need = (static_cast<size_t>(p.N) * pitch * sizeof(float) + 255) / 256 * 256;
     if (ws_bytes >= need) {
       float* packed = static_cast<float*>(ws);
-      repitch_kernel<<<stream_grid(static_cast<size_t>(p.N) * 32), kBlock, 0, s>>>(p.b, packed, p.K, pitch, static_cast<size_t>(p.N));
+      repitch_kernel<<<stream_grid(static_cast<size_t>(p.N) * 32), kBlock, 0, s>>>(p.b, packed, p.K, pitch, static_cast<size_t>(p.N), prepass_round());
       int rc0 = finish_launch();
       if (rc0) return rc0;
       p.b = packed; p.ldb = pitch; p.b_vec = 1;
@@ -1020,6 +1246,15 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   }
   p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
   int rc;
+  if (AM == A_COLMAJOR && BMD == B_KMAJOR && tma && !(g_opt_no_tma_a.load() & 2) && p.lda % 4 == 0 && aligned16(p.a)) {
+    // column-major A is an MN-major UMMA operand as it lies in memory: no gather warps at all
+    CUtensorMap tm_a;
+    memset(&tm_a, 0, sizeof(tm_a));
+    if (make_a_mn_tmap(&tm_a, p.a, p.M, p.K, p.lda)) {
+      p.a_mode = TMA_A_TILED_MN;
+      return launch_umma_tma(p, tm_a, tm, s);
+    }
+  }
   if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
   else rc = launch_umma<AM, BMD, false>(p, tm, s);
   if (rc || p.splits == 1) return rc;
@@ -1030,7 +1265,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.cpt = 1; p.out_mode = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -1042,6 +1277,71 @@ static int check_conv(int N, int Ci, int Co, int H, int W, int ph, int pw, int s
   return MNV_OK;
 }
 static bool fits_int(long long v) { return v > 0 && v < 0x7fffffffLL; }
+
+static size_t round256(size_t v) { return (v + 255) / 256 * 256; }
+static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, cudaStream_t s) {
+  const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
+  const long long total = static_cast<long long>(N) * tiles_c * tiles_hw;
+  const long long cap = static_cast<long long>(kNumSMs) * 16;
+  nchw_to_nhwc_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(x, y, C, Cp, HW, tiles_c, tiles_hw, total);
+  return finish_launch();
+}
+
+// Cross-correlation of x[N][Ci][H][W] with `ff` taps as a GEMM whose two operands both arrive through TMA:
+//   A[m = (n,oh,ow)][k = (tap, c)]  channels-last copy of x through an im2col tensor map (no gather warps, padding
+//                                   is the map's out-of-bounds zero fill),
+//   B[n = co][k = (tap, c)]         = w[co*w_sn + c*w_sc + (flip ? ff-1-tap : tap)], packed once per call.
+// Both copies are TF32-rounded pre-passes into the workspace (one streaming pass each, << the GEMM).
+// *done stays false when the path does not apply (tiny channel counts, no workspace): the caller falls back to
+// the gather kernel.
+static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long long w_sc, int flip, const float* bias, float* out, int N,
+                          int Ci, int Co, int H, int W, int Ho, int Wo, int ph, int pw, int sv, int sh, int fh, int fw, void* ws,
+                          size_t ws_bytes, cudaStream_t s, bool* done) {
+  *done = false;
+  if ((g_opt_no_tma_a.load() & 1) || g_opt_simt.load() || g_opt_no_tma.load() || !ws) return MNV_OK;
+  const int cpt = (Ci + BK - 1) / BK, ff = fh * fw;
+  if (cpt * BK * 2 > Ci * 3) return MNV_OK;                       // > 1.5x channel padding: the gather kernel wastes less
+  if (ph > 127 || pw > 127 || fh - 1 - ph > 128 || fw - 1 - pw > 128 || sv > 8 || sh > 8) return MNV_OK;
+  if (!get_im2col_fn() || !get_encode_fn()) return MNV_OK;
+  const int Cp = (Ci + 3) / 4 * 4;
+  const long long M = static_cast<long long>(N) * Ho * Wo, K = static_cast<long long>(ff) * cpt * BK;
+  if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * H * W * Cp)) return MNV_OK;
+  const size_t x_bytes = round256(static_cast<size_t>(N) * H * W * Cp * sizeof(float));
+  const size_t b_bytes = round256(static_cast<size_t>(Co) * K * sizeof(float));
+  if (ws_bytes < x_bytes + b_bytes) return MNV_OK;
+  float* xh = static_cast<float*>(ws);
+  float* wb = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + x_bytes);
+  void* ws2 = static_cast<uint8_t*>(ws) + x_bytes + b_bytes;
+  const size_t ws2_bytes = ws_bytes - x_bytes - b_bytes;
+
+  GemmParams p;
+  zero_conv(p);
+  p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
+  p.a = xh; p.b = wb; p.bias = bias; p.out = out;
+  p.M = static_cast<int>(M); p.N = Co; p.K = static_cast<int>(K);
+  p.ldb = p.K; p.b_vec = 1;
+  p.P = Ho * Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
+  p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt;
+  plan_tiles(p, ws2_bytes, true);
+  // Measured on AlexNet's layers (tools/tma_diag.py): the all-TMA kernel itself is 10-25% faster than the gather
+  // kernel, but the channels-last pre-pass costs one pass over the input, so the path pays only when the GEMM does
+  // enough work per input element (Co * taps >= ~3000 / 2 flop per byte) and the gather kernel is not on its best
+  // configuration (the wide tile).  "force_tma_a" overrides for experiments.
+  if (!g_opt_force_tma_a.load() && (p.wide || static_cast<long long>(Co) * ff < 1500)) return MNV_OK;
+  p.partial = p.splits > 1 ? static_cast<float*>(ws2) : nullptr;
+  CUtensorMap tm_a, tm_b;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_b, 0, sizeof(tm_b));
+  if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
+  if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
+  int rc = launch_nhwc(x, xh, N, Ci, Cp, H * W, s);
+  if (rc) return rc;
+  filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
+  rc = finish_launch();
+  if (rc) return rc;
+  *done = true;
+  return launch_umma_tma(p, tm_a, tm_b, s);
+}
 
 }  // namespace mnv
 
@@ -1062,6 +1362,10 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_ktab") return g_opt_no_ktab.exchange(value);
   if (k == "wait_hint") return g_opt_wait_hint.exchange(value);
   if (k == "no_wide") return g_opt_no_wide.exchange(value);
+  if (k == "no_tma_a") return g_opt_no_tma_a.exchange(value);
+  if (k == "tma_tf32") return g_opt_tma_tf32.exchange(value);
+  if (k == "no_deep") return g_opt_no_deep.exchange(value);
+  if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   return -1;
 }
 
@@ -1088,6 +1392,13 @@ int mnv_conv_forward(const float* bottom, const float* filter, const float* bias
   if (rc) return rc;
   if (N == 0) return MNV_OK;
   if (!bottom || !filter || !bias || !top) return MNV_EINVAL;
+  {  // both operands through TMA when the channel count makes 32-channel k-stages worthwhile
+    bool done = false;
+    rc = conv_tma_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, top, N, Ci, Co, H, W,
+                        (H + 2 * ph - fh) / sv + 1, (W + 2 * pw - fw) / sh + 1, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes,
+                        as_stream(stream), &done);
+    if (rc || done) return rc;
+  }
   GemmParams p;
   zero_conv(p);
   p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
@@ -1116,8 +1427,16 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
   // stride 1: backward-data == forward convolution of top_diff with the swapped, 180-degree-rotated
   // filter and pad' = f-1-pad, so it runs on the (fast) forward gather.
   const bool as_forward = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && !g_opt_no_fwd_bwd.load();
+  if (as_forward) {
+    // B[n = ci][k = (tap, co)] = filter[co][ci][tap]: the two 180-degree rotations (true convolution, transposed
+    // operator) cancel
+    bool done = false;
+    rc = conv_tma_fprop(top_diff, filter, fh * fw, static_cast<long long>(Ci) * fh * fw, 0, nullptr, bottom_diff, N, Co, Ci, Ho, Wo, H, W,
+                        fh - 1 - ph, fw - 1 - pw, 1, 1, fh, fw, workspace, workspace_bytes, as_stream(stream), &done);
+    if (rc || done) return rc;
+  }
   filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(
-      filter, wt, Co, Ci, fh * fw, as_forward ? 1 : 0, g_opt_simt.load() ? 0 : 1);
+      filter, wt, Co, Ci, fh * fw, as_forward ? 1 : 0, prepass_round());
   rc = finish_launch();
   if (rc) return rc;
   GemmParams p;
@@ -1174,7 +1493,7 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
     if (ws_left < need) return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, s);
     float* packed = reinterpret_cast<float*>(ws);
     size_t rows = static_cast<size_t>(N) * Co;
-    repitch_kernel<<<stream_grid(rows * 32), kBlock, 0, s>>>(top_diff, packed, P, pitch, rows);
+    repitch_kernel<<<stream_grid(rows * 32), kBlock, 0, s>>>(top_diff, packed, P, pitch, rows, prepass_round());
     rc = finish_launch();
     if (rc) return rc;
     dy_tma = packed;
@@ -1184,6 +1503,28 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
   long long kpad = static_cast<long long>(N) * p.spi * BK;
   if (!fits_int(kpad)) return MNV_EUNSUPPORTED;
   p.K = static_cast<int>(kpad);          // k-stages = N * spi; validity is per-pixel inside the gathers
+  {  // A through TMA as well: channels-last copy of the bottom read by an im2col map, pixels as the k axis
+    const int cpt = (Ci + BK - 1) / BK, Cp = (Ci + 3) / 4 * 4;
+    const size_t x_bytes = round256(static_cast<size_t>(N) * H * W * Cp * sizeof(float));
+    if (!(g_opt_no_tma_a.load() & 4) && cpt * BK * 2 <= Ci * 3 && ph <= 127 && pw <= 127 && fh - 1 - ph <= 128 && fw - 1 - pw <= 128 &&
+        sv <= 8 && sh <= 8 && get_im2col_fn() && ws_left >= x_bytes && fits_int(static_cast<long long>(N) * H * W * Cp)) {
+      GemmParams q = p;
+      float* xh = reinterpret_cast<float*>(ws);
+      q.a = xh; q.M = fh * fw * cpt * BK; q.a_mode = TMA_A_IM2COL_MN; q.cpt = cpt; q.out_mode = 1;
+      q.P = q.M; q.col_stride = static_cast<long long>(Ci) * fh * fw;
+      plan_tiles(q, ws_left - x_bytes, true);
+      q.partial = q.splits > 1 ? reinterpret_cast<float*>(ws + x_bytes) : nullptr;
+      CUtensorMap tm_a, tm_b;
+      memset(&tm_a, 0, sizeof(tm_a));
+      memset(&tm_b, 0, sizeof(tm_b));
+      if (make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true) &&
+          make_dy_tmap(&tm_b, dy_tma, P, pitch, Co, N, q.wide ? q.bn / 2 : q.bn)) {
+        rc = launch_nhwc(bottom, xh, N, Ci, Cp, H * W, s);
+        if (rc) return rc;
+        return launch_umma_tma(q, tm_a, tm_b, s);
+      }
+    }
+  }
   plan_tiles(p, ws_left, true);
   p.partial = p.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
   CUtensorMap tm;
