@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--unfused-update", action="store_true", help="use the reference's ten-op SGD chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mnv-opt", action="append", default=[], metavar="KEY=INT",
+                    help="tuning: set a mnv_debug_set_option key before the run (recorded in config.tuning)")
     return ap.parse_args()
 
 
@@ -225,6 +227,12 @@ def main():
     from minerva_b200.owl import _runtime as rt
     from minerva_b200 import _lib
     lib = _lib.load()
+    for kv in args.mnv_opt:
+        import ctypes
+        k, v = kv.split("=")
+        lib.mnv_debug_set_option.restype = ctypes.c_int
+        lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        lib.mnv_debug_set_option(k.encode(), int(v))
 
     dev_id = owl.create_gpu_device(local)
     owl.set_device(dev_id)
@@ -372,7 +380,8 @@ def main():
             "config": {"workload": wl["name"], "global_batch": batch * world, "per_gpu_batch": batch,
                        "parallelism": "dp%d" % world, "update": "chain" if args.unfused_update else "fused momentum-SGD kernel",
                        "l2": "working set per step (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                       "gradient_merge": "NCCL all-reduce per weighted unit, overlapped with backward" if world > 1 else "none (1 GPU)"},
+                       "gradient_merge": "NCCL all-reduce per weighted unit, overlapped with backward" if world > 1 else "none (1 GPU)",
+                       **({"tuning": args.mnv_opt} if args.mnv_opt else {})},
             "clocks": sampler.summary(), "gpu_launches": int(launches), "loss": float(loss),
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,
             "peaks": {k: pk.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},

@@ -72,6 +72,7 @@ struct GemmParams {
   int stages;           // smem ring depth: 4 (bn <= 256) or 3 (wide tile, 256 < bn <= 384)
   int stage_bytes;      // A tile + B tile bytes per ring slot
   int wide;             // 1: one 128 x bn tile as two UMMA halves of bn/2 columns sharing the A tile, single accumulator
+  int tall;             // 1: 256 x bn tile as two UMMA halves of 128 rows sharing the B tile (all-TMA path only)
   int a_mode;           // A_TMA sub-mode (TMA_A_*), 0 otherwise
   int cpt;              // 32-channel chunks per filter tap (TMA_A_IM2COL_K: k-stage = tap * cpt + chunk)
   int out_mode;         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
@@ -591,10 +592,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   // 3-deep ring of 64 KB slots; otherwise bn <= 256, two accumulators, 4-deep ring of 48 KB slots.
   // RING 2 (both operands through TMA, bn <= 128): 6-deep ring of 32 KB slots -- a 128 x 96 tile consumes a stage
   // in ~200 cycles, so four stages in flight do not cover the TMA round trip.
-  constexpr bool WIDE = RING == 1, DEEP = RING == 2;
-  constexpr int kNStages = WIDE ? 3 : DEEP ? 6 : kStages;
-  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : DEEP ? kABytes + 128 * BK * 4 : kStageBytes;
-  constexpr int kNAcc = WIDE ? 1 : 2;
+  // RING 3 (both operands through TMA): a 256 x bn tile as two UMMA halves of 128 rows sharing the B tile, one
+  // accumulator per half (all 512 TMEM columns), 3-deep ring of 64 KB slots.  The kernel is bound by L2 -> SM
+  // operand traffic (48 KB per 128x256x32 stage = 44 flop/B); the tall tile moves 64 KB for twice the math.
+  constexpr bool WIDE = RING == 1, DEEP = RING == 2, TALL = RING == 3;
+  constexpr int kTileM = TALL ? 2 * BM : BM;
+  constexpr int kATile = TALL ? 2 * kABytes : kABytes;
+  constexpr int kNStages = (WIDE || TALL) ? 3 : DEEP ? 6 : kStages;
+  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : DEEP ? kABytes + 128 * BK * 4 : TALL ? 2 * kABytes + kBBytes : kStageBytes;
+  constexpr int kNAcc = (WIDE || TALL) ? 1 : 2;
   constexpr int kMaxStages = 6;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of address bits [7,10)
@@ -644,30 +650,33 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       TileCoord t = decode_tile(p, tile);
       mbar_wait(tfull0 + 8 * acc_stage, acc_phase, p.wait_hint);
       tc_fence_after();
-      const int m = t.mt * BM + warp * 32 + lane;
       const int n0 = t.nt * p.bn;
-      const bool row_ok = out_row_ok(p, m);
-      float* dst;
-      long long cstride;
-      if (p.splits > 1) {  // partial[split][n][m]
-        dst = p.partial + static_cast<size_t>(t.split) * p.M * p.N + (row_ok ? m : 0);
-        cstride = p.M;
-      } else {
-        dst = p.out + (row_ok ? out_index(p, m, 0) : 0);
-        cstride = p.col_stride;
-      }
       const bool add_bias = p.bias != nullptr && p.splits == 1;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc_stage * BN_MAX + c0), r);
-        if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            int n = n0 + c0 + j;
-            if (n < p.N) {
-              float val = __uint_as_float(r[j]);
-              if (add_bias) val += __ldg(p.bias + n);
-              dst[static_cast<size_t>(n) * cstride] = val;
+      for (int half = 0; half < (TALL ? 2 : 1); ++half) {
+        const int m = t.mt * kTileM + half * BM + warp * 32 + lane;
+        const bool row_ok = out_row_ok(p, m);
+        float* dst;
+        long long cstride;
+        if (p.splits > 1) {  // partial[split][n][m]
+          dst = p.partial + static_cast<size_t>(t.split) * p.M * p.N + (row_ok ? m : 0);
+          cstride = p.M;
+        } else {
+          dst = p.out + (row_ok ? out_index(p, m, 0) : 0);
+          cstride = p.col_stride;
+        }
+        for (int c0 = 0; c0 < p.bn; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc_stage * BN_MAX + half * BN_MAX + c0), r);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              int n = n0 + c0 + j;
+              if (n < p.N) {
+                float val = __uint_as_float(r[j]);
+                if (add_bias) val += __ldg(p.bias + n);
+                dst[static_cast<size_t>(n) * cstride] = val;
+              }
             }
           }
         }
@@ -696,14 +705,18 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_base + stage * kSBytes;
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t b_addr = a_addr + kATile;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes inside the swizzle span
             const uint32_t acc = (ks > t.ks_begin || kk > 0) ? 1u : 0u;
             const uint64_t adesc = a_mn ? make_sw128_desc_mn(a_addr + kk * 1024) : make_sw128_desc(a_addr + kk * 32);
-            umma_tf32(tmem_d, adesc, make_sw128_desc(b_addr + kk * 32), idesc, acc);
+            const uint64_t bdesc = make_sw128_desc(b_addr + kk * 32);
+            umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
             if (WIDE)   // second half of the columns: same A tile, B rows bnh.., TMEM columns bnh..
               umma_tf32(tmem_d + bnh, adesc, make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
+            if (TALL)   // rows 128..255: second A half, same B tile, second accumulator
+              umma_tf32(tmem_d + BN_MAX, a_mn ? make_sw128_desc_mn(a_addr + kABytes + kk * 1024) : make_sw128_desc(a_addr + kABytes + kk * 32),
+                        bdesc, idesc, acc);
           }
           umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
           if (ks + 1 == t.ks_end) umma_commit(tfull0 + 8 * acc_stage);  // accumulator complete
@@ -718,23 +731,27 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     if (BTMA && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       // the whole box(es), OOB rows/cols arrive as zeros
-      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4 + (AM == A_TMA ? kABytes : 0);
+      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4 + (AM == A_TMA ? kATile : 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         TileCoord t = decode_tile(p, tile);
         // A_TMA: position of the tile's first row
-        int a_w = 0, a_h = 0, a_n = 0;
-        int a_kw[4] = {0, 0, 0, 0}, a_kh[4] = {0, 0, 0, 0}, a_c[4] = {0, 0, 0, 0};
+        constexpr int kHalves = TALL ? 2 : 1, kChunks = 4 * kHalves;
+        int a_w[kHalves] = {}, a_h[kHalves] = {}, a_n[kHalves] = {};
+        int a_kw[kChunks] = {}, a_kh[kChunks] = {}, a_c[kChunks] = {};
         if (AM == A_TMA) {
-          const int m0 = t.mt * BM;
           if (p.a_mode == TMA_A_IM2COL_K) {
-            a_n = m0 / p.P;
-            const int pix = m0 - a_n * p.P, oh = pix / p.Wo;
-            a_h = oh * p.sv - p.ph; a_w = (pix - oh * p.Wo) * p.sh - p.pw;
+#pragma unroll
+            for (int h = 0; h < kHalves; ++h) {   // rows past M land in image >= N: zero-filled
+              const int m0 = t.mt * kTileM + h * BM;
+              a_n[h] = m0 / p.P;
+              const int pix = m0 - a_n[h] * p.P, oh = pix / p.Wo;
+              a_h[h] = oh * p.sv - p.ph; a_w[h] = (pix - oh * p.Wo) * p.sh - p.pw;
+            }
           } else if (p.a_mode == TMA_A_IM2COL_MN) {
             const int last = p.fh * p.fw * p.cpt - 1;   // rows past M still receive a (masked) box
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int chunk = min(t.mt * 4 + j, last), tap = chunk / p.cpt;
+            for (int j = 0; j < kChunks; ++j) {
+              const int chunk = min(t.mt * kChunks + j, last), tap = chunk / p.cpt;
               a_c[j] = (chunk - tap * p.cpt) * 32; a_kh[j] = tap / p.fw; a_kw[j] = tap - a_kh[j] * p.fw;
             }
           }
@@ -746,18 +763,20 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             const uint32_t a_dst = smem_base + stage * kSBytes, bar = full0 + 8 * stage;
             if (p.a_mode == TMA_A_IM2COL_K) {
               const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
-              tma_load_im2col_4d(a_dst, &tmap_a, bar, cc * BK, a_w, a_h, a_n, tap - kh * p.fw, kh);
+#pragma unroll
+              for (int h = 0; h < kHalves; ++h)
+                tma_load_im2col_4d(a_dst + h * kABytes, &tmap_a, bar, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
             } else if (p.a_mode == TMA_A_TILED_MN) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) tma_load_2d(a_dst + j * 4096, &tmap_a, bar, t.mt * BM + 32 * j, ks * BK);
+              for (int j = 0; j < kChunks; ++j) tma_load_2d(a_dst + j * 4096, &tmap_a, bar, t.mt * kTileM + 32 * j, ks * BK);
             } else {   // k-stage = 32 output pixels of one image (p.spi stages per image)
               const int img = ks / p.spi, pix = (ks - img * p.spi) * BK, oh = pix / p.Wo;
               const int h = oh * p.sv - p.ph, w = (pix - oh * p.Wo) * p.sh - p.pw;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) tma_load_im2col_4d(a_dst + j * 4096, &tmap_a, bar, a_c[j], w, h, img, a_kw[j], a_kh[j]);
+              for (int j = 0; j < kChunks; ++j) tma_load_im2col_4d(a_dst + j * 4096, &tmap_a, bar, a_c[j], w, h, img, a_kw[j], a_kh[j]);
             }
           }
-          const uint32_t dst = smem_base + stage * kSBytes + kABytes;
+          const uint32_t dst = smem_base + stage * kSBytes + kATile;
           const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;   // a TMA box has at most 256 rows
           for (int h = 0; h < halves; ++h) {
             const uint32_t d2 = dst + h * rows * 128;
@@ -873,7 +892,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       };
       auto store = [&](int l) {
         const uint32_t a_tile = smem_base + stage * kSBytes;
-        const uint32_t b_tile = a_tile + kABytes;
+        const uint32_t b_tile = a_tile + kATile;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint32_t off = (AM == A_IM2COL_WGRAD) ? sw128_off(b_row0 + 64 * q, b_kq) : sw128_off(a_row, a_q * 2 + q);
@@ -961,7 +980,10 @@ static std::atomic<int> g_opt_tma_tf32{1};   // operand maps typed TFLOAT32: TMA
                                              // norm-rel error vs fp64 2.9e-4 unbiased, against 7.7e-4 with a -7e-4 bias for FLOAT32 maps,
                                              // whose low mantissa bits the tensor core just drops); 0 = FLOAT32 maps (debug)
 static std::atomic<int> g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it applies, ignoring the profitability rule (tuning)
-static std::atomic<int> g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
+static std::atomic<int> g_opt_no_deep{0};
+static std::atomic<int> g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
+static std::atomic<int> g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
+static std::atomic<int> g_opt_tall_fprop{0}; // 1: allow the 256-row tile for conv forward / backward-data too (tuning)    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
 static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug) // 1: use the generic backward-data gather for stride 1 too (debug)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1131,9 +1153,34 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
   }
 }
 
-static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_wide = false) {
+// split-K for a tile grid that does not fill the machine (needs the caller's workspace for the partials)
+static void plan_splits(GemmParams& p, size_t ws_bytes_for_partials) {
+  long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  int splits = 1;
+  if (tiles * 4 < kNumSMs * 3) {  // fewer than 3/4 of a wave: split K
+    splits = static_cast<int>(kNumSMs / tiles);
+    int max_by_k = p.k_stages / 4;  // at least 4 stages per split
+    if (splits > max_by_k) splits = max_by_k;
+    size_t per_split = static_cast<size_t>(p.M) * p.N * sizeof(float);
+    size_t max_by_ws = per_split ? ws_bytes_for_partials / per_split : 0;
+    if (static_cast<size_t>(splits) > max_by_ws) splits = static_cast<int>(max_by_ws);
+    int clamp = g_opt_max_splits.load();
+    if (clamp > 0 && splits > clamp) splits = clamp;
+    if (splits < 1) splits = 1;
+  }
+  p.stages_per_split = (p.k_stages + splits - 1) / splits;
+  p.splits = (p.k_stages + p.stages_per_split - 1) / p.stages_per_split;  // no empty split
+}
+// fraction of the machine's CTA slots the tile grid keeps busy over its whole run
+static double wave_fill(const GemmParams& p) {
+  long long ctas = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+  long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+  return static_cast<double>(ctas) / static_cast<double>(waves * kNumSMs);
+}
+
+static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_wide = false, bool allow_tall = false) {
   p.m_tiles = (p.M + BM - 1) / BM;
-  p.wide = 0; p.stages = kStages; p.stage_bytes = kStageBytes;
+  p.wide = 0; p.tall = 0; p.stages = kStages; p.stage_bytes = kStageBytes;
   int n_tiles, bn;
   if (allow_wide && p.N > BN_MAX && !g_opt_no_wide.load()) {
     // 256 < N: tiles of up to 384 columns (two UMMA halves share one gathered A tile) in a 3-deep ring of
@@ -1153,24 +1200,23 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
   p.n_tiles = (p.N + bn - 1) / bn;
   p.k_stages = (p.K + BK - 1) / BK;
   if (p.k_stages < 1) p.k_stages = 1;
-  long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
-  int splits = 1;
-  if (tiles * 4 < kNumSMs * 3) {  // fewer than 3/4 of a wave: split K
-    splits = static_cast<int>(kNumSMs / tiles);
-    int max_by_k = p.k_stages / 4;  // at least 4 stages per split
-    if (splits > max_by_k) splits = max_by_k;
-    size_t per_split = static_cast<size_t>(p.M) * p.N * sizeof(float);
-    size_t max_by_ws = per_split ? ws_bytes_for_partials / per_split : 0;
-    if (static_cast<size_t>(splits) > max_by_ws) splits = static_cast<int>(max_by_ws);
-    int clamp = g_opt_max_splits.load();
-    if (clamp > 0 && splits > clamp) splits = clamp;
-    if (splits < 1) splits = 1;
-  }
-  p.stages_per_split = (p.k_stages + splits - 1) / splits;
-  p.splits = (p.k_stages + p.stages_per_split - 1) / p.stages_per_split;  // no empty split
+  plan_splits(p, ws_bytes_for_partials);
   // The wide tile has a single TMEM accumulator, so its epilogue is not hidden behind the next tile's
   // mainloop: worth it only when a tile's mainloop is long (measured break-even ~70 k-stages).
-  if (p.wide && p.stages_per_split < 96) plan_tiles(p, ws_bytes_for_partials, false);
+  if (p.wide && p.stages_per_split < 96) plan_tiles(p, ws_bytes_for_partials, false, allow_tall);
+  if (allow_tall && !g_opt_no_tall.load()) {
+    // 256-row tile (all-TMA path): halves the B traffic per flop.  Like the wide tile it has no second accumulator
+    // set, so it wants a long mainloop, and it must not cost machine fill.
+    GemmParams q = p;
+    q.tall = 1; q.wide = 0; q.stages = 3; q.stage_bytes = 2 * kABytes + kBBytes;
+    q.m_tiles = (p.M + 2 * BM - 1) / (2 * BM);
+    q.n_tiles = (p.N + BN_MAX - 1) / BN_MAX;
+    q.bn = ((p.N + q.n_tiles - 1) / q.n_tiles + 15) / 16 * 16;
+    if (q.bn < 16) q.bn = 16;
+    q.n_tiles = (p.N + q.bn - 1) / q.bn;
+    plan_splits(q, ws_bytes_for_partials);
+    if (q.stages_per_split >= g_opt_tall_min_stages.load() && (wave_fill(q) >= 0.85 || wave_fill(q) >= wave_fill(p))) p = q;
+  }
 }
 
 static const CUtensorMap& null_tmap() { static CUtensorMap z = {}; return z; }
@@ -1198,7 +1244,8 @@ static int launch_umma(const GemmParams& p, const CUtensorMap& tm, cudaStream_t 
 
 // both operands through TMA
 static int launch_umma_tma(const GemmParams& p, const CUtensorMap& tm_a, const CUtensorMap& tm_b, cudaStream_t s) {
-  int rc = p.wide      ? launch_umma_w<A_TMA, B_KMAJOR, true, 1>(p, tm_b, s, tm_a)
+  int rc = p.tall      ? launch_umma_w<A_TMA, B_KMAJOR, true, 3>(p, tm_b, s, tm_a)
+           : p.wide    ? launch_umma_w<A_TMA, B_KMAJOR, true, 1>(p, tm_b, s, tm_a)
            : (p.bn <= 128 && !g_opt_no_deep.load()) ? launch_umma_w<A_TMA, B_KMAJOR, true, 2>(p, tm_b, s, tm_a)
                           : launch_umma_w<A_TMA, B_KMAJOR, true, 0>(p, tm_b, s, tm_a);
   if (rc || p.splits == 1) return rc;
@@ -1230,7 +1277,9 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
     }
   }
   const bool tma_ok = BMD == B_KMAJOR && p.b_vec && !g_opt_no_tma.load() && get_encode_fn() != nullptr;
-  plan_tiles(p, ws ? ws_bytes : 0, tma_ok);
+  // column-major A is an MN-major UMMA operand as it lies in memory: with B on TMA too there are no gather warps
+  const bool tma_a_ok = AM == A_COLMAJOR && tma_ok && !(g_opt_no_tma_a.load() & 2) && p.lda % 4 == 0 && aligned16(p.a);
+  plan_tiles(p, ws ? ws_bytes : 0, tma_ok, tma_a_ok);
   p.use_ktab = 0;
   if (AM == A_IM2COL_FWD && p.k_stages * BK <= kKtabMax && !g_opt_no_ktab.load()) {
     long long img = static_cast<long long>(p.Ci) * p.H * p.W;
@@ -1242,18 +1291,22 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   bool tma = false;
   if (tma_ok) {
     tma = make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.wide ? p.bn / 2 : p.bn);
-    if (!tma && p.wide) plan_tiles(p, ws ? ws_bytes : 0, false);   // the wide tile needs the TMA-fed path
+    if (!tma && (p.wide || p.tall)) plan_tiles(p, ws ? ws_bytes : 0, false);   // the wide / tall tiles need the TMA-fed path
   }
   p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
   int rc;
-  if (AM == A_COLMAJOR && BMD == B_KMAJOR && tma && !(g_opt_no_tma_a.load() & 2) && p.lda % 4 == 0 && aligned16(p.a)) {
-    // column-major A is an MN-major UMMA operand as it lies in memory: no gather warps at all
+  if (tma_a_ok && tma) {
     CUtensorMap tm_a;
     memset(&tm_a, 0, sizeof(tm_a));
     if (make_a_mn_tmap(&tm_a, p.a, p.M, p.K, p.lda)) {
       p.a_mode = TMA_A_TILED_MN;
       return launch_umma_tma(p, tm_a, tm, s);
     }
+  }
+  if (p.tall) {   // planned for the all-TMA path, which did not materialise
+    plan_tiles(p, ws ? ws_bytes : 0, tma);
+    p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
+    if (tma && !make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.wide ? p.bn / 2 : p.bn)) return MNV_EINVAL;
   }
   if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
   else rc = launch_umma<AM, BMD, false>(p, tm, s);
@@ -1322,12 +1375,16 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   p.ldb = p.K; p.b_vec = 1;
   p.P = Ho * Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
   p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt;
-  plan_tiles(p, ws2_bytes, true);
+  // 256-row tiles when the output is narrow (Co <= 128: the 128 x Co tile starves on operand traffic; measured on
+  // AlexNet conv2 backward-data, 128 x 96: 307 TF/s, 256 x 96: 394 TF/s).  With 256 output columns the forward
+  // tiles are short (72-108 k-stages) and the unhidden epilogue of the tall tile costs more than it saves.
+  plan_tiles(p, ws2_bytes, true, g_opt_tall_fprop.load() != 0 || Co <= 128);
   // Measured on AlexNet's layers (tools/tma_diag.py): the all-TMA kernel itself is 10-25% faster than the gather
   // kernel, but the channels-last pre-pass costs one pass over the input, so the path pays only when the GEMM does
-  // enough work per input element (Co * taps >= ~3000 / 2 flop per byte) and the gather kernel is not on its best
+  // enough work per input element (Co * taps >= ~3000, i.e. ~1500 flop per input byte) and the gather kernel is not on its best
   // configuration (the wide tile).  "force_tma_a" overrides for experiments.
-  if (!g_opt_force_tma_a.load() && (p.wide || static_cast<long long>(Co) * ff < 1500)) return MNV_OK;
+  // Narrow outputs (bn <= 128) are the gather kernel's worst case and get the 6-deep ring here: always taken.
+  if (!g_opt_force_tma_a.load() && (p.wide || (static_cast<long long>(Co) * ff < 3000 && p.bn > 128))) return MNV_OK;
   p.partial = p.splits > 1 ? static_cast<float*>(ws2) : nullptr;
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
@@ -1365,6 +1422,9 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_tma_a") return g_opt_no_tma_a.exchange(value);
   if (k == "tma_tf32") return g_opt_tma_tf32.exchange(value);
   if (k == "no_deep") return g_opt_no_deep.exchange(value);
+  if (k == "no_tall") return g_opt_no_tall.exchange(value);
+  if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
+  if (k == "tall_fprop") return g_opt_tall_fprop.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   return -1;
 }
@@ -1512,7 +1572,7 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
       float* xh = reinterpret_cast<float*>(ws);
       q.a = xh; q.M = fh * fw * cpt * BK; q.a_mode = TMA_A_IM2COL_MN; q.cpt = cpt; q.out_mode = 1;
       q.P = q.M; q.col_stride = static_cast<long long>(Ci) * fh * fw;
-      plan_tiles(q, ws_left - x_bytes, true);
+      plan_tiles(q, ws_left - x_bytes, true, true);
       q.partial = q.splits > 1 ? reinterpret_cast<float*>(ws + x_bytes) : nullptr;
       CUtensorMap tm_a, tm_b;
       memset(&tm_a, 0, sizeof(tm_a));

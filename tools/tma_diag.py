@@ -42,36 +42,42 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
+VARIANTS = [("gather", {"no_tma_a": None}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tall", {"force_tma_a": 1, "tall_fprop": 1})]
+ALL_KEYS = ("no_tma_a", "force_tma_a", "no_tall", "tall_fprop")
+
+
 def compare(name, fn, out, flops, iters, bit):
-    """fn() fills `out`; run with the TMA path on and off."""
+    """fn() fills `out`; run it on the gather path, the all-TMA path and the all-TMA path with the 256-row tile."""
     res = {}
-    for label, v in (("gather", bit), ("tma", 0)):
-        opt("no_tma_a", v)
+    for label, opts in VARIANTS:
+        for k in ALL_KEYS:
+            opt(k, 0)
+        for k, v in opts.items():
+            opt(k, bit if v is None else v)
         out.fill_(float("nan"))
         try:
             fn()
             torch.cuda.synchronize()
             res[label] = out.clone()
-            ms = timed(fn, iters) if iters else float("nan")
+            res[label + "_ms"] = timed(fn, iters) if iters else float("nan")
         except Exception as e:  # noqa: BLE001
             print("  %s %s FAILED: %s" % (name, label, e), flush=True)
-            opt("no_tma_a", 0)
-            return
-        res[label + "_ms"] = ms
-    opt("no_tma_a", 0)
-    a, b = res["gather"].double(), res["tma"].double()
-    err = float((a - b).norm() / max(float(a.norm()), 1e-30))
-    nan = int(torch.isnan(res["tma"]).sum())
-    line = "%-46s err(tma vs gather)=%.2e nan=%d" % (name, err, nan)
+            break
+    for k in ALL_KEYS:
+        opt(k, 0)
+    if "gather" not in res:
+        return
+    a = res["gather"].double()
+    line = "%-44s" % name
+    for label, _ in VARIANTS[1:]:
+        if label not in res:
+            continue
+        b = res[label].double()
+        err = float((a - b).norm() / max(float(a.norm()), 1e-30))
+        line += " %s: err %.1e nan %d" % (label, err, int(torch.isnan(res[label]).sum()))
     if iters:
-        line += "  gather %.3f ms (%.0f TF/s)  tma %.3f ms (%.0f TF/s)" % (
-            res["gather_ms"], flops / res["gather_ms"] / 1e9, res["tma_ms"], flops / res["tma_ms"] / 1e9)
+        line += " |" + "".join("  %s %.3f ms (%.0f TF/s)" % (l, res[l + "_ms"], flops / res[l + "_ms"] / 1e9) for l, _ in VARIANTS if l in res)
     print(line, flush=True)
-    if err > 1e-4 or nan:
-        d = (a - b).abs()
-        d[torch.isnan(d)] = 1e30
-        idx = torch.nonzero(d > 1e-3 * float(a.abs().max()))[:8].ravel().tolist()
-        print("   #bad=%d first=%s" % (int((d > 1e-3 * float(a.abs().max())).sum()), idx))
 
 
 ws = g.workspace()
