@@ -602,6 +602,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : DEEP ? kABytes + 128 * BK * 4 : TALL ? 2 * kABytes + kBBytes : kStageBytes;
   constexpr int kNAcc = (WIDE || TALL) ? 1 : 2;
   constexpr int kMaxStages = 6;
+  // With both operands on TMA the 16 gather warps have no mainloop work: they join the epilogue, five warps per
+  // TMEM lane quarter (a warp reaches lanes 32 * (warp % 4) .. +31 only), each draining every fifth 16-column chunk.
+  constexpr int kEpiSlots = AM == A_TMA ? 5 : 1;
+  constexpr int kEpiWarps = 4 * kEpiSlots;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern is a function of address bits [7,10)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -620,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     // full: TMA-fed B: the 4 warps of the slot's producer group + the TMA thread's arrive.expect_tx;
     //       gathered B: all 16 producer warps
     for (int s = 0; s < kNStages; ++s) { mbar_init(full0 + 8 * s, AM == A_TMA ? 1 : BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }   // kNStages of them are used
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -643,8 +647,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ===================== epilogue =====================
+  // ===================== epilogue (run by warps 0-3, and by the idle producer warps on the all-TMA path) ==========
+  auto epilogue = [&](const int quarter, const int slot) {
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile);
@@ -654,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       const bool add_bias = p.bias != nullptr && p.splits == 1;
 #pragma unroll
       for (int half = 0; half < (TALL ? 2 : 1); ++half) {
-        const int m = t.mt * kTileM + half * BM + warp * 32 + lane;
+        const int m = t.mt * kTileM + half * BM + quarter * 32 + lane;
         const bool row_ok = out_row_ok(p, m);
         float* dst;
         long long cstride;
@@ -665,9 +669,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           dst = p.out + (row_ok ? out_index(p, m, 0) : 0);
           cstride = p.col_stride;
         }
-        for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        for (int c0 = 16 * slot; c0 < p.bn; c0 += 16 * kEpiSlots) {
           uint32_t r[16];
-          tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc_stage * BN_MAX + half * BN_MAX + c0), r);
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc_stage * BN_MAX + half * BN_MAX + c0), r);
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -686,6 +690,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc_stage);
       if (++acc_stage == kNAcc) { acc_stage = 0; acc_phase ^= 1; }
     }
+  };
+  if (warp < 4) {
+    epilogue(warp, 0);
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     // The whole warp walks the pipeline (so every lane reaches the final __syncthreads together);
@@ -796,7 +803,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   } else {
     // ===================== gather producers =====================
     if constexpr (AM == A_TMA) {
-      // both operands come through TMA: these warps have nothing to do
+      // both operands come through TMA: no gather to do, help drain the accumulators
+      epilogue(warp & 3, 1 + (warp - kProducerWarp0) / 4);
     } else if (BTMA) {
       // Stage-interleaved warp groups: group g (4 warps = 128 threads, one thread per tile row, all 32 k
       // of the stage) owns ring slot g, i.e. every 4th k-stage.  A group's loads for its next stage are
@@ -974,17 +982,16 @@ static std::atomic<int> g_opt_no_wide{0};     // 1: never use the wide (bn > 256
 static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
 static std::atomic<int> g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
 static std::atomic<int> g_opt_no_tma{0};     // 1: gather B with threads even where TMA applies (debug)
-static std::atomic<int> g_opt_no_fwd_bwd{0};
+static std::atomic<int> g_opt_no_fwd_bwd{0};  // 1: use the generic backward-data gather for stride 1 too (debug)
 static std::atomic<int> g_opt_no_tma_a{0};   // bit 0: no TMA-im2col fprop/dgrad, bit 1: no TMA MatMult A, bit 2: no TMA wgrad (debug / tuning)
 static std::atomic<int> g_opt_tma_tf32{1};   // operand maps typed TFLOAT32: TMA then rounds fp32 -> tf32 to nearest on the way in (measured:
                                              // norm-rel error vs fp64 2.9e-4 unbiased, against 7.7e-4 with a -7e-4 bias for FLOAT32 maps,
                                              // whose low mantissa bits the tensor core just drops); 0 = FLOAT32 maps (debug)
 static std::atomic<int> g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it applies, ignoring the profitability rule (tuning)
-static std::atomic<int> g_opt_no_deep{0};
+static std::atomic<int> g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
 static std::atomic<int> g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
 static std::atomic<int> g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
-static std::atomic<int> g_opt_tall_fprop{0}; // 1: allow the 256-row tile for conv forward / backward-data too (tuning)    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
-static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug) // 1: use the generic backward-data gather for stride 1 too (debug)
+static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1375,16 +1382,13 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   p.ldb = p.K; p.b_vec = 1;
   p.P = Ho * Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
   p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt;
-  // 256-row tiles when the output is narrow (Co <= 128: the 128 x Co tile starves on operand traffic; measured on
-  // AlexNet conv2 backward-data, 128 x 96: 307 TF/s, 256 x 96: 394 TF/s).  With 256 output columns the forward
-  // tiles are short (72-108 k-stages) and the unhidden epilogue of the tall tile costs more than it saves.
-  plan_tiles(p, ws2_bytes, true, g_opt_tall_fprop.load() != 0 || Co <= 128);
-  // Measured on AlexNet's layers (tools/tma_diag.py): the all-TMA kernel itself is 10-25% faster than the gather
-  // kernel, but the channels-last pre-pass costs one pass over the input, so the path pays only when the GEMM does
-  // enough work per input element (Co * taps >= ~3000, i.e. ~1500 flop per input byte) and the gather kernel is not on its best
-  // configuration (the wide tile).  "force_tma_a" overrides for experiments.
-  // Narrow outputs (bn <= 128) are the gather kernel's worst case and get the 6-deep ring here: always taken.
-  if (!g_opt_force_tma_a.load() && (p.wide || (static_cast<long long>(Co) * ff < 3000 && p.bn > 128))) return MNV_OK;
+  plan_tiles(p, ws2_bytes, true, true);
+  // Measured on AlexNet's layers (tools/tma_diag.py, profiles/r01_tma_diag_*.log): the all-TMA kernel is 10-35%
+  // faster than the gather kernel, but the channels-last pre-pass costs one pass over the input, so the path pays
+  // only when the GEMM does enough work per input element (Co * taps >= ~3000, i.e. ~1500 flop per input byte).
+  // Narrow outputs (bn <= 128) are the gather kernel's worst case (128 x 96 tile: 270 TF/s, against 402 TF/s for
+  // the 256 x 96 tile here): always taken.  "force_tma_a" overrides for experiments.
+  if (!g_opt_force_tma_a.load() && static_cast<long long>(Co) * ff < 3000 && p.bn > 128) return MNV_OK;
   p.partial = p.splits > 1 ? static_cast<float*>(ws2) : nullptr;
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
@@ -1424,7 +1428,6 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_deep") return g_opt_no_deep.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
-  if (k == "tall_fprop") return g_opt_tall_fprop.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   return -1;
 }

@@ -42,8 +42,8 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-VARIANTS = [("gather", {"no_tma_a": None}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tall", {"force_tma_a": 1, "tall_fprop": 1})]
-ALL_KEYS = ("no_tma_a", "force_tma_a", "no_tall", "tall_fprop")
+VARIANTS = [("gather", {"no_tma_a": None}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tall", {"force_tma_a": 1})]
+ALL_KEYS = ("no_tma_a", "force_tma_a", "no_tall")
 
 
 def compare(name, fn, out, flops, iters, bit):
