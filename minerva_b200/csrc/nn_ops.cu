@@ -4,6 +4,7 @@
 // the stream per call (minerva/op/impl/cuda/cuda_perform.cu:339-615); here each op is one
 // enqueue-only launch (two for bias-grad with a workspace).
 #include <math_constants.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mnv {
@@ -517,27 +518,39 @@ static int make_geom(PoolGeom* g, int N, int C, int H, int W, int sv, int sh, in
 __global__ void __launch_bounds__(kBlock) bias_grad_partial_kernel(const float* __restrict__ dy, float* __restrict__ partial,
                                                                    int N, int C, int hw, int splits) {
   __shared__ float red[32];
-  int c = blockIdx.x, sp = blockIdx.y;
-  int n_per = (N + splits - 1) / splits;
-  int n0 = sp * n_per, n1 = min(N, n0 + n_per);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // independent chains: 4 loads in flight per thread
-  // 4 images at a time (one accumulator each), threads striding the plane: small planes (13x13) still
-  // keep 4 independent loads in flight per thread
+  const int c = blockIdx.x, sp = blockIdx.y;
+  const int n_per = (N + splits - 1) / splits;
+  const int n0 = sp * n_per, n1 = min(N, n0 + n_per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // A warp walks whole (image, channel) planes, lanes along the contiguous pixels: two planes and four 32-pixel runs
+  // per step keep 8 independent 128-byte-per-warp loads in flight per lane whatever the plane size (13 x 13 planes
+  // leave most of a 256-thread block idle when the block strides one plane).
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
   const size_t img_stride = static_cast<size_t>(C) * hw;
   const float* base = dy + static_cast<size_t>(c) * hw;
-  int n = n0;
-  for (; n + 3 < n1; n += 4) {
+  int n = n0 + 2 * warp;
+  for (; n + 1 < n1; n += 2 * nwarps) {
     const float* p0 = base + n * img_stride;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-      float v0 = __ldg(p0 + i), v1 = __ldg(p0 + img_stride + i), v2 = __ldg(p0 + 2 * img_stride + i), v3 = __ldg(p0 + 3 * img_stride + i);
+    const float* p1 = p0 + img_stride;
+    int i = lane;
+    for (; i + 96 < hw; i += 128) {
+      float v0 = __ldg(p0 + i), v1 = __ldg(p0 + i + 32), v2 = __ldg(p0 + i + 64), v3 = __ldg(p0 + i + 96);
+      float w0 = __ldg(p1 + i), w1 = __ldg(p1 + i + 32), w2 = __ldg(p1 + i + 64), w3 = __ldg(p1 + i + 96);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+      b0 += w0; b1 += w1; b2 += w2; b3 += w3;
+    }
+    for (; i < hw; i += 32) { a0 += __ldg(p0 + i); b0 += __ldg(p1 + i); }
+  }
+  if (n < n1) {   // odd plane out
+    const float* p0 = base + n * img_stride;
+    int i = lane;
+    for (; i + 96 < hw; i += 128) {
+      float v0 = __ldg(p0 + i), v1 = __ldg(p0 + i + 32), v2 = __ldg(p0 + i + 64), v3 = __ldg(p0 + i + 96);
       a0 += v0; a1 += v1; a2 += v2; a3 += v3;
     }
+    for (; i < hw; i += 32) a0 += __ldg(p0 + i);
   }
-  for (; n < n1; ++n) {
-    const float* p0 = base + n * img_stride;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) a0 += __ldg(p0 + i);
-  }
-  float acc = block_reduce((a0 + a1) + (a2 + a3), false, red);
+  float acc = block_reduce(((a0 + a1) + (a2 + a3)) + ((b0 + b1) + (b2 + b3)), false, red);
   if (threadIdx.x == 0) partial[static_cast<size_t>(sp) * C + c] = acc;
 }
 __global__ void bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ db, int C, int splits) {
@@ -691,46 +704,70 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd_kernel(const float* __restrict
 // the reference's add-then-subtract rounding sequence bit for bit.
 constexpr int kLrnChunk = 8;
 
+// scale^(-beta) on the SFU: beta = 0.75 as r * r * rsqrt(r) with r = rsqrt(s) (two MUFU.RSQ), any other beta as
+// ex2(-beta * lg2(s)).  A few ulp from powf (the parity bound for LRN outputs is 1e-5 relative).
 template <bool BETA075>
+__device__ __forceinline__ float pow_neg_beta_sfu(float s, float neg_beta) {
+  float r;
+  if (BETA075) {
+    float q;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(r));
+    return __fmul_rn(r, __fmul_rn(r, q));
+  }
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(s));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(l, neg_beta)));
+  return r;
+}
+
+// Window of 5 (AlexNet, GoogLeNet).  One thread per pixel walking the channels; 32-bit element offsets (the host
+// checks the tensor has < 2^31 elements), one running offset for the loads (8 channels ahead, in registers) and one
+// for the two stores; same add / subtract order as the generic kernel, so `scale` stays bit-identical.
+template <bool BETA075, int CHUNK, int STORE>
 __global__ void __launch_bounds__(kBlock) lrn_fwd5_kernel(const float* __restrict__ in, float* __restrict__ scale, float* __restrict__ out,
-                                                          int num, int C, size_t step, float alpha_over_size, float neg_beta) {
-  size_t total = static_cast<size_t>(num) * step;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    size_t n = t / step, p = t - n * step, off = n * C * step + p;
-    const float* sin = in + off;
-    float* ssc = scale + off;
-    float* sout = out + off;
-    float cur[kLrnChunk], nxt[kLrnChunk];
+                                                          int num, int C, unsigned step, float alpha_over_size, float neg_beta) {
+  const unsigned total = static_cast<unsigned>(num) * step;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned n = t / step, p = t - n * step;
+    unsigned ld = n * static_cast<unsigned>(C) * step + p;   // offset of the next channel to load
+    unsigned st = ld;                                         // offset of the next channel to store
+    float cur[CHUNK], nxt[CHUNK];
 #pragma unroll
-    for (int u = 0; u < kLrnChunk; ++u) cur[u] = u < C ? __ldg(sin + u * step) : 0.f;
+    for (int u = 0; u < CHUNK; ++u) {
+      cur[u] = u < C ? __ldg(in + ld) : 0.f;
+      ld += step;
+    }
     float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sq4 = 0.f;   // squares of x[head-1..head-5]
     float x1 = 0.f, x2 = 0.f;                                        // x[head-1], x[head-2]
     float acc = 0.f;
-    for (int c0 = 0; c0 < C + 2; c0 += kLrnChunk) {
+    for (int c0 = 0; c0 < C + 2; c0 += CHUNK) {
+      const int left = C - (c0 + CHUNK);   // channels still to load
 #pragma unroll
-      for (int u = 0; u < kLrnChunk; ++u) {
-        int hn = c0 + kLrnChunk + u;
-        nxt[u] = hn < C ? __ldg(sin + hn * step) : 0.f;
+      for (int u = 0; u < CHUNK; ++u) {
+        nxt[u] = u < left ? __ldg(in + ld) : 0.f;
+        ld += step;
       }
 #pragma unroll
-      for (int u = 0; u < kLrnChunk; ++u) {
-        int head = c0 + u;
-        float xin = cur[u];                      // 0 past C
-        float add = __fmul_rn(xin, xin);
+      for (int u = 0; u < CHUNK; ++u) {
+        const float xin = cur[u];                // 0 past C
+        const float add = __fmul_rn(xin, xin);
         acc = __fadd_rn(acc, add);
         acc = __fsub_rn(acc, sq4);               // x[head-5]^2, +0 while the window is filling
         sq4 = sq3; sq3 = sq2; sq2 = sq1; sq1 = sq0; sq0 = add;
-        int o = head - 2;
+        const int o = c0 + u - 2;
         if (o >= 0 && o < C) {
-          float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
-          ssc[o * step] = sc;
-          sout[o * step] = __fmul_rn(x2, pow_neg_beta<BETA075>(sc, neg_beta));
+          const float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
+          const float ov = __fmul_rn(x2, pow_neg_beta_sfu<BETA075>(sc, neg_beta));
+          if (STORE == 1) { __stcs(scale + st, sc); __stcs(out + st, ov); }
+          else if (STORE == 2) { __stwt(scale + st, sc); __stwt(out + st, ov); }
+          else { scale[st] = sc; out[st] = ov; }
+          st += step;
         }
         x2 = x1; x1 = xin;
       }
 #pragma unroll
-      for (int u = 0; u < kLrnChunk; ++u) cur[u] = nxt[u];
+      for (int u = 0; u < CHUNK; ++u) cur[u] = nxt[u];
     }
   }
 }
@@ -738,55 +775,56 @@ __global__ void __launch_bounds__(kBlock) lrn_fwd5_kernel(const float* __restric
 template <bool BETA075>
 __global__ void __launch_bounds__(kBlock) lrn_bwd5_kernel(const float* __restrict__ bottom, const float* __restrict__ top,
                                                           const float* __restrict__ scale, const float* __restrict__ top_diff,
-                                                          float* __restrict__ bottom_diff, int num, int C, size_t step,
+                                                          float* __restrict__ bottom_diff, int num, int C, unsigned step,
                                                           float neg_beta, float cache_ratio) {
-  size_t total = static_cast<size_t>(num) * step;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    size_t n = t / step, p = t - n * step, off = n * C * step + p;
-    const float* b = bottom + off;
-    const float* tp = top + off;
-    const float* s = scale + off;
-    const float* td = top_diff + off;
-    float* bd = bottom_diff + off;
+  // 32-bit element offsets as in lrn_fwd5_kernel: `ld` runs 8 channels ahead of the head for top_diff / top / scale,
+  // the bottom value of output channel head-2 is fetched at ld - 2*step, `st` is the output channel.
+  const unsigned total = static_cast<unsigned>(num) * step;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned n = t / step, p = t - n * step;
+    unsigned ld = n * static_cast<unsigned>(C) * step + p;
+    unsigned st = ld;
+    const unsigned two = 2u * step;
     float ctd[kLrnChunk], ctp[kLrnChunk], csc[kLrnChunk], cb[kLrnChunk];
     float ntd[kLrnChunk], ntp[kLrnChunk], nsc[kLrnChunk], nb[kLrnChunk];
 #pragma unroll
     for (int u = 0; u < kLrnChunk; ++u) {
-      bool ok = u < C;
-      ctd[u] = ok ? __ldg(td + u * step) : 0.f;
-      ctp[u] = ok ? __ldg(tp + u * step) : 0.f;
-      csc[u] = ok ? __ldg(s + u * step) : 1.f;
-      cb[u] = (u >= 2 && u - 2 < C) ? __ldg(b + (u - 2) * step) : 0.f;   // bottom of the output channel head-2
+      const bool ok = u < C;
+      ctd[u] = ok ? __ldg(top_diff + ld) : 0.f;
+      ctp[u] = ok ? __ldg(top + ld) : 0.f;
+      csc[u] = ok ? __ldg(scale + ld) : 1.f;
+      cb[u] = (u >= 2 && u - 2 < C) ? __ldg(bottom + (ld - two)) : 0.f;   // bottom of the output channel head-2
+      ld += step;
     }
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;   // td*top/scale of head-1..head-5
     float td1 = 0.f, td2 = 0.f, sc1 = 1.f, sc2 = 1.f;
     float acc = 0.f;
     for (int c0 = 0; c0 < C + 2; c0 += kLrnChunk) {
+      const int left = C - (c0 + kLrnChunk);   // channels still to load
 #pragma unroll
       for (int u = 0; u < kLrnChunk; ++u) {
-        int hn = c0 + kLrnChunk + u;
-        bool ok = hn < C;
-        ntd[u] = ok ? __ldg(td + hn * step) : 0.f;
-        ntp[u] = ok ? __ldg(tp + hn * step) : 0.f;
-        nsc[u] = ok ? __ldg(s + hn * step) : 1.f;
-        nb[u] = (hn - 2 < C) ? __ldg(b + (hn - 2) * step) : 0.f;
+        const bool ok = u < left;
+        ntd[u] = ok ? __ldg(top_diff + ld) : 0.f;
+        ntp[u] = ok ? __ldg(top + ld) : 0.f;
+        nsc[u] = ok ? __ldg(scale + ld) : 1.f;
+        nb[u] = (u < left + 2) ? __ldg(bottom + (ld - two)) : 0.f;
+        ld += step;
       }
 #pragma unroll
       for (int u = 0; u < kLrnChunk; ++u) {
-        int head = c0 + u;
-        float tdh = ctd[u], sch = csc[u];
+        const float tdh = ctd[u], sch = csc[u];
         // scale >= 1, so the approximate divide (<= 2 ulp, no special-operand slow path -- half of top_diff*top is
         // exactly 0 after ReLU/pooling and IEEE division takes its slow path on those) is safe here
-        float r = __fdividef(__fmul_rn(tdh, ctp[u]), sch);     // +0 past C (0*0/1)
+        const float r = __fdividef(__fmul_rn(tdh, ctp[u]), sch);     // +0 past C (0*0/1)
         acc = __fadd_rn(acc, r);
         acc = __fsub_rn(acc, r4);
         r4 = r3; r3 = r2; r2 = r1; r1 = r0; r0 = r;
-        int o = head - 2;
+        const int o = c0 + u - 2;
         if (o >= 0 && o < C) {
-          float lhs = __fmul_rn(td2, pow_neg_beta<BETA075>(sc2, neg_beta));
-          float rhs = __fmul_rn(__fmul_rn(cache_ratio, cb[u]), acc);
-          bd[o * step] = __fsub_rn(lhs, rhs);
+          const float lhs = __fmul_rn(td2, pow_neg_beta_sfu<BETA075>(sc2, neg_beta));
+          const float rhs = __fmul_rn(__fmul_rn(cache_ratio, cb[u]), acc);
+          bottom_diff[st] = __fsub_rn(lhs, rhs);
+          st += step;
         }
         td2 = td1; td1 = tdh; sc2 = sc1; sc1 = sch;
       }
@@ -968,8 +1006,10 @@ int mnv_conv_backward_bias(const float* dy, float* db, int N, int C, int H, int 
   if (C == 0) return MNV_OK;
   if (!dy || !db) return MNV_EINVAL;
   int hw = H * W;
-  // enough CTAs for ~4 per SM, bounded by the images available and the workspace
-  int splits = (kNumSMs * 8 + C - 1) / C;
+  // 16 images per CTA (8 warps x 2 planes, one pass), but no fewer CTAs than ~8 per SM; bounded by the workspace
+  int splits = (N + 15) / 16;
+  const int want = (kNumSMs * 8 + C - 1) / C;
+  if (splits < want) splits = want;
   if (splits > N) splits = N > 0 ? N : 1;
   size_t max_splits = workspace ? workspace_bytes / (sizeof(float) * C) : 0;
   if (static_cast<size_t>(splits) > max_splits) splits = static_cast<int>(max_splits);
@@ -994,9 +1034,13 @@ int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_siz
   const float aos = alpha / local_size;
   const bool b075 = beta == 0.75f;
   const int grid = stream_grid(work);
-  if (local_size == 5 && channel >= 5) {
-    if (b075) lrn_fwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, aos, -beta);
-    else lrn_fwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, aos, -beta);
+  // the size-5 kernel keeps 32-bit element offsets (its loads run up to 16 channels past the tensor's end, unissued)
+  if (local_size == 5 && channel >= 5 && (static_cast<unsigned long long>(channel) + 32) * work < (1ull << 31)) {
+    const unsigned step32 = static_cast<unsigned>(step);
+    // 16 channels of register look-ahead: measured 3960 GB/s on 256x96x55x55 against 3600 with 8 (the kernel is bound by
+    // DRAM latency under a 1-read : 2-write mix; evict-first / write-through stores made no difference)
+    if (b075) lrn_fwd5_kernel<true, 16, 0><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, aos, -beta);
+    else lrn_fwd5_kernel<false, 16, 0><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, aos, -beta);
   } else {
     if (b075) lrn_fwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
     else lrn_fwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
@@ -1013,9 +1057,10 @@ int mnv_lrn_backward(const float* bottom_data, const float* top_data, const floa
   float cache_ratio = static_cast<float>(2. * alpha * beta / local_size);  // cuda_perform.cu:665
   const bool b075 = beta == 0.75f;
   const int grid = stream_grid(work);
-  if (local_size == 5 && channel >= 5) {
-    if (b075) lrn_bwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, -beta, cache_ratio);
-    else lrn_bwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, -beta, cache_ratio);
+  if (local_size == 5 && channel >= 5 && (static_cast<unsigned long long>(channel) + 16) * work < (1ull << 31)) {
+    const unsigned step32 = static_cast<unsigned>(step);
+    if (b075) lrn_bwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step32, -beta, cache_ratio);
+    else lrn_bwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step32, -beta, cache_ratio);
   } else {
     if (b075) lrn_bwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
     else lrn_bwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
