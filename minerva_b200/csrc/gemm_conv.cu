@@ -40,7 +40,12 @@ namespace mnv {
 // ------------------------------------------------------------------------------------------------
 // problem description shared by the tcgen05 kernel, the SIMT checker and the split-K reducer
 // ------------------------------------------------------------------------------------------------
-enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD = 3, A_TMA = 4 };
+enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD = 3, A_TMA = 4,
+              // Strided convolutions (first layers: 11x11/4, 7x7/2 on 3 channels): along the output pixels the source
+              // addresses are `stride` elements apart, so lanes-along-pixels gathers touch 16 sectors per request.
+              // These two modes put the lanes along the filter taps instead, which are contiguous along kw:
+              A_IM2COL_FWD_K = 5,     // forward: a warp owns 32 tile rows, lane = k of the stage, one row per load
+              A_IM2COL_WGRAD_M = 6 }; // backward-filter: a warp owns 32 tile rows (taps), lane = row, one pixel per load
 // A_TMA sub-modes (GemmParams::a_mode): how the TMA thread fetches the 128 x 32 A tile of a k-stage
 //   TMA_A_IM2COL_K : channels-last activation copy through an im2col tensor map; one box of 128 output pixels
 //                    x 32 channels of one filter tap => K-major tile (forward conv, stride-1 backward-data)
@@ -178,6 +183,14 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-  if (AM == A_IM2COL_FWD && p.use_ktab) {
+  if ((AM == A_IM2COL_FWD || AM == A_IM2COL_FWD_K) && p.use_ktab) {
     const int ff = p.fh * p.fw, HW = p.H * p.W;
     for (int k = threadIdx.x; k < p.k_stages * BK; k += blockDim.x) {
       uint32_t e = p.use_ktab == 1 ? 31u : (31u << 22);
@@ -821,6 +834,90 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       uint32_t uses = 0;                                    // completed uses of this slot -> wait parity
       uint32_t cnt = 0;                                     // global k-stage counter at tile start
       float va[32];
+      if constexpr (AM == A_IM2COL_FWD_K || AM == A_IM2COL_WGRAD_M) {
+        // Lanes along the taps.  Warp wq of the group owns tile rows 32*wq .. 32*wq+31.
+        //   FWD_K  : lane = k of the stage (its (offset, kh, kw) comes from the k-table, one LDS per stage); the warp
+        //            walks its 32 rows, whose (base, kh-mask, kw-mask) live one per lane and are broadcast by SHFL;
+        //            each lane stores one float per row (conflict-free: a row is 32 consecutive words).
+        //   WGRAD_M: lane = tile row (tap), with a fixed source offset; the warp walks the 32 pixels of the stage,
+        //            whose (base, masks) are computed one per lane per stage and broadcast; each lane then owns a whole
+        //            128-byte row of the tile: eight conflict-free STS.128.
+        const int wq = pw & 3;
+        const int HW = p.H * p.W;
+        for (int tile = blockIdx.x; grp < ngrp && tile < total_tiles; tile += gridDim.x) {
+          TileCoord t = decode_tile(p, tile);
+          const int nks = t.ks_end - t.ks_begin;
+          int ks = t.ks_begin + (grp + ngrp - static_cast<int>(cnt % static_cast<uint32_t>(ngrp))) % ngrp;
+          cnt += static_cast<uint32_t>(nks);
+          if (ks >= t.ks_end) continue;
+          int my_off = 0;
+          uint32_t my_h = 0, my_w = 0;      // FWD_K: this lane's row masks; WGRAD_M: this lane's kh, kw (31 = row past M)
+          if (AM == A_IM2COL_FWD_K) {
+            ARow ar = a_row_setup<A_IM2COL_FWD>(p, t.mt * BM + wq * 32 + lane);
+            my_off = static_cast<int>(ar.base);
+            my_h = ar.valid ? ar.mh : 0u; my_w = ar.mw;
+          } else {
+            const int m = t.mt * BM + wq * 32 + lane, ff = p.fh * p.fw;
+            my_h = 31u; my_w = 0u;
+            if (m < p.M) {
+              const int ci = m / ff, rs = m - ci * ff, rr = rs / p.fw;
+              my_h = static_cast<uint32_t>(p.fh - 1 - rr); my_w = static_cast<uint32_t>(p.fw - 1 - (rs - rr * p.fw));
+              my_off = ci * HW + static_cast<int>(my_h) * p.W + static_cast<int>(my_w);
+            }
+          }
+          auto load = [&](int k) {
+            if (AM == A_IM2COL_FWD_K) {
+              const uint32_t e = ld_shared_u32(ktab0 + 4 * (k * BK + lane));
+              const int koff = static_cast<int>(e & 0x3FFFFFu);
+              const uint32_t kh = (e >> 22) & 31u, kw = e >> 27;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const int rb = __shfl_sync(0xffffffffu, my_off, r);
+                const uint32_t rh = __shfl_sync(0xffffffffu, my_h, r), rw = __shfl_sync(0xffffffffu, my_w, r);
+                va[r] = (((rh >> kh) & (rw >> kw)) & 1u) ? __ldg(p.a + (rb + koff)) : 0.f;
+              }
+            } else {
+              // this lane describes pixel `lane` of the stage: 32 pixels of image k / spi
+              const int img = k / p.spi, pix = (k - img * p.spi) * BK + lane;
+              int pb = 0;
+              uint32_t ph_m = 0, pw_m = 0;
+              if (pix < p.Ho * p.Wo) {
+                const int oh = pix / p.Wo, h0 = oh * p.sv - p.ph, w0 = (pix - oh * p.Wo) * p.sh - p.pw;
+                pb = img * p.Ci * HW + h0 * p.W + w0;
+                for (int kh = 0; kh < p.fh; ++kh) if (h0 + kh >= 0 && h0 + kh < p.H) ph_m |= 1u << kh;
+                for (int kw = 0; kw < p.fw; ++kw) if (w0 + kw >= 0 && w0 + kw < p.W) pw_m |= 1u << kw;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int qb = __shfl_sync(0xffffffffu, pb, j);
+                const uint32_t qh = __shfl_sync(0xffffffffu, ph_m, j), qw = __shfl_sync(0xffffffffu, pw_m, j);
+                va[j] = (((qh >> my_h) & (qw >> my_w)) & 1u) ? __ldg(p.a + (qb + my_off)) : 0.f;
+              }
+            }
+          };
+          load(ks);
+          for (; ks < t.ks_end; ks += ngrp) {
+            mbar_wait(slot_empty, (uses & 1u) ^ 1u, p.wait_hint);
+            if (AM == A_IM2COL_FWD_K) {
+              const uint32_t lane_off = static_cast<uint32_t>(lane & 3) * 4u;
+#pragma unroll
+              for (int r = 0; r < 32; ++r)   // (32*wq + r) & 7 == r & 7
+                st_shared_f32(a_tile + static_cast<uint32_t>(wq * 32 + r) * 128u + (static_cast<uint32_t>((lane >> 2) ^ (r & 7)) << 4) + lane_off,
+                              to_tf32(va[r]));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                st_shared_v4(a_tile + sw128_off(wq * 32 + lane, q), to_tf32(va[4 * q]), to_tf32(va[4 * q + 1]), to_tf32(va[4 * q + 2]),
+                             to_tf32(va[4 * q + 3]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(slot_full);
+            ++uses;
+            if (ks + ngrp < t.ks_end) load(ks + ngrp);
+          }
+        }
+      } else
       for (int tile = blockIdx.x; grp < ngrp && tile < total_tiles; tile += gridDim.x) {
         TileCoord t = decode_tile(p, tile);
         const int nks = t.ks_end - t.ks_begin;
@@ -988,6 +1085,7 @@ static std::atomic<int> g_opt_tma_tf32{1};   // operand maps typed TFLOAT32: TMA
                                              // norm-rel error vs fp64 2.9e-4 unbiased, against 7.7e-4 with a -7e-4 bias for FLOAT32 maps,
                                              // whose low mantissa bits the tensor core just drops); 0 = FLOAT32 maps (debug)
 static std::atomic<int> g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it applies, ignoring the profitability rule (tuning)
+static std::atomic<int> g_opt_no_klane{0};   // 1: strided convs keep the lanes-along-pixels gathers (debug / tuning)
 static std::atomic<int> g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
 static std::atomic<int> g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
 static std::atomic<int> g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
@@ -1315,7 +1413,11 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
     p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
     if (tma && !make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.wide ? p.bn / 2 : p.bn)) return MNV_EINVAL;
   }
-  if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
+  if (AM == A_IM2COL_FWD && BMD == B_KMAJOR && tma && (p.sv > 1 || p.sh > 1) && !g_opt_no_klane.load() &&
+      p.k_stages * BK <= kKtabMax && static_cast<long long>(p.Ci) * p.H * p.W < (1ll << 22) && !p.wide) {
+    p.use_ktab = 2;   // strided forward conv: lanes along k (taps are contiguous along kw, output pixels are not)
+    rc = launch_umma<A_IM2COL_FWD_K, B_KMAJOR, true>(p, tm, s);
+  } else if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
   else rc = launch_umma<AM, BMD, false>(p, tm, s);
   if (rc || p.splits == 1) return rc;
   splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
@@ -1426,6 +1528,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_tma_a") return g_opt_no_tma_a.exchange(value);
   if (k == "tma_tf32") return g_opt_tma_tf32.exchange(value);
   if (k == "no_deep") return g_opt_no_deep.exchange(value);
+  if (k == "no_klane") return g_opt_no_klane.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
@@ -1596,7 +1699,8 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
     p.spi = 0; p.K = static_cast<int>(K);
     return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, ws, ws_left, s);
   }
-  rc = launch_umma<A_IM2COL_WGRAD, B_KMAJOR, true>(p, tm, s);
+  if ((sv > 1 || sh > 1) && !g_opt_no_klane.load() && !p.wide) rc = launch_umma<A_IM2COL_WGRAD_M, B_KMAJOR, true>(p, tm, s);
+  else rc = launch_umma<A_IM2COL_WGRAD, B_KMAJOR, true>(p, tm, s);
   if (rc || p.splits == 1) return rc;
   splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
   return finish_launch();

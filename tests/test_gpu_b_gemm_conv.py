@@ -138,6 +138,67 @@ def test_conv_three_directions(g, case):
         assert g.norm_rel(dw, wdw) < TOL, "backward filter"
 
 
+TMA_CASES = [
+    # N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw  -- channel counts for which the all-TMA (im2col tensor map) path applies
+    (2, 32, 16, 8, 8, 1, 1, 1, 1, 3, 3),
+    (3, 48, 40, 9, 7, 1, 1, 1, 1, 3, 3),        # 48 channels: second 32-channel chunk half out of bounds
+    (2, 64, 24, 12, 10, 0, 0, 1, 1, 1, 1),      # 1x1
+    (2, 32, 32, 11, 14, 1, 2, 1, 1, 3, 5),      # asymmetric pad and filter
+    (4, 64, 32, 13, 13, 0, 0, 2, 2, 3, 3),      # stride 2 through the map's traversal strides
+    (2, 96, 64, 27, 27, 2, 2, 1, 1, 5, 5),      # AlexNet conv2 channels: 256-row tiles for backward-data (Co <= 128)
+    (2, 384, 384, 13, 13, 1, 1, 1, 1, 3, 3),    # AlexNet conv4: 108 k-stages, wide (384-column) tile
+    (5, 160, 300, 7, 7, 1, 1, 1, 1, 3, 3),
+]
+OPERAND_PATHS = [("gather", {"no_tma_a": 7}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tma+tall", {"force_tma_a": 1}),
+                 ("tma, float32 maps", {"force_tma_a": 1, "tma_tf32": 0}), ("default", {})]
+
+
+@pytest.mark.parametrize("case", TMA_CASES)
+def test_conv_operand_paths(g, case):
+    """Every way the tcgen05 kernel can be fed (gather warps, TMA im2col maps, 256-row tiles) against the oracle."""
+    N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = case
+    Ho, Wo = orc.conv_out(H, ph, fh, sv), orc.conv_out(W, pw, fw, sh)
+    x = rng.normal(0, 1, N * Ci * H * W).astype(np.float32)
+    w = rng.normal(0, 1, Co * Ci * fh * fw).astype(np.float32)
+    b = rng.normal(0, 1, Co).astype(np.float32)
+    dy = rng.normal(0, 1, N * Co * Ho * Wo).astype(np.float32)
+    geo = (N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw)
+    wy = orc.conv_forward(x, w, b, *geo)
+    wdx = orc.conv_backward_data(dy, w, *geo)
+    wdw = orc.conv_backward_filter(x, dy, *geo)
+    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1}
+    for name, opts in OPERAND_PATHS:
+        try:
+            for k, v in {**defaults, **opts}.items():
+                _set(k, v)
+            y, dx, dw = _conv_all(g, case, x, w, b, dy)
+        finally:
+            for k, v in defaults.items():
+                _set(k, v)
+        assert g.norm_rel(y, wy) < TOL, name + ": forward"
+        assert g.norm_rel(dx, wdx) < TOL, name + ": backward data"
+        assert g.norm_rel(dw, wdw) < TOL, name + ": backward filter"
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (132, 17, 36), (1000, 200, 300), (516, 260, 2100), (2048, 96, 4100)])
+def test_matmult_operand_paths(g, m, n, k):
+    """MatMult with A fetched by TMA as an MN-major operand (m % 4 == 0), with and without the 256-row tile, and gathered."""
+    a = rng.normal(0, 1, m * k).astype(np.float32)
+    b = rng.normal(0, 1, k * n).astype(np.float32)
+    want = (b.reshape(n, k).astype(np.float64) @ a.reshape(k, m).astype(np.float64)).ravel()
+    defaults = {"no_tma_a": 0, "no_tall": 0, "tma_tf32": 1}
+    for name, opts in (("gather", {"no_tma_a": 2}), ("tma", {"no_tall": 1}), ("tma+tall", {"tall_min_stages": 1}), ("float32 maps", {"tma_tf32": 0})):
+        try:
+            for key, v in {**defaults, **opts}.items():
+                _set(key, v)
+            got = _matmult(g, a, b, m, n, k)
+        finally:
+            for key, v in defaults.items():
+                _set(key, v)
+            _set("tall_min_stages", 64)
+        assert g.norm_rel(got, want) < TOL, name
+
+
 def test_conv_forward_goldens(g, golden_dir):
     """tests/unittest_conv_forward.cpp:7-68, tolerance 1e-3 absolute as in the reference."""
     ws = g.workspace()

@@ -73,7 +73,7 @@ def report(name, seconds, bytes_=None, flops=None):
 
 
 def want(name):
-    return args.filter in name
+    return args.filter in name or (args.filter != "" and name in args.filter)
 
 
 def call(name, *a):
