@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--unfused-update", action="store_true", help="use the reference's ten-op SGD chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-ctas", type=int, default=0,
+                    help="N>1: SMs left to NCCL (NCCL_MAX_CTAS) and kept out of the persistent tensor-core kernel's grid; 0 = do not manage")
     ap.add_argument("--mnv-opt", action="append", default=[], metavar="KEY=INT",
                     help="tuning: set a mnv_debug_set_option key before the run (recorded in config.tuning)")
     return ap.parse_args()
@@ -220,6 +222,14 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.nccl_ctas > 0:
+            # Experiment (off by default): the conv/GEMM kernel is persistent, one CTA per SM, so an overlapped all-reduce that
+            # holds a few SMs pushes its last CTAs into a second wave.  Giving NCCL a fixed handful of CTAs and sizing the
+            # tensor-core grid to the rest measured the same or worse at 2 GPUs (7.54 ms unmanaged; 2 CTAs 9.60, 4 CTAs 7.73,
+            # 8 CTAs 7.54): fewer NCCL CTAs expose the 151 MB fc6 all-reduce.
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
+            os.environ.setdefault("NCCL_MIN_CTAS", "1")
+            args.mnv_opt.append("sm_budget=%d" % (148 - int(os.environ["NCCL_MAX_CTAS"])))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import minerva_b200.owl as owl

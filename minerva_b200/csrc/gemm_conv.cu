@@ -1258,12 +1258,22 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
   }
 }
 
+// SMs the persistent tensor-core kernel may occupy.  It runs one CTA per SM for the whole launch, so when another
+// persistent kernel (an overlapped NCCL all-reduce) holds a few SMs, a 148-CTA grid runs its last CTAs as a second
+// wave and the launch takes up to twice as long; the data-parallel trainer therefore leaves NCCL's SMs out
+// ("sm_budget" option; default = all 148).
+static std::atomic<int> g_opt_sm_budget{kNumSMs};
+static int sm_budget() {
+  int v = g_opt_sm_budget.load();
+  return v < 1 ? 1 : v > kNumSMs ? kNumSMs : v;
+}
 // split-K for a tile grid that does not fill the machine (needs the caller's workspace for the partials)
 static void plan_splits(GemmParams& p, size_t ws_bytes_for_partials) {
   long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   int splits = 1;
-  if (tiles * 4 < kNumSMs * 3) {  // fewer than 3/4 of a wave: split K
-    splits = static_cast<int>(kNumSMs / tiles);
+  const int sms = sm_budget();
+  if (tiles * 4 < sms * 3) {  // fewer than 3/4 of a wave: split K
+    splits = static_cast<int>(sms / tiles);
     int max_by_k = p.k_stages / 4;  // at least 4 stages per split
     if (splits > max_by_k) splits = max_by_k;
     size_t per_split = static_cast<size_t>(p.M) * p.N * sizeof(float);
@@ -1279,8 +1289,9 @@ static void plan_splits(GemmParams& p, size_t ws_bytes_for_partials) {
 // fraction of the machine's CTA slots the tile grid keeps busy over its whole run
 static double wave_fill(const GemmParams& p) {
   long long ctas = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
-  long long waves = (ctas + kNumSMs - 1) / kNumSMs;
-  return static_cast<double>(ctas) / static_cast<double>(waves * kNumSMs);
+  const int sms = sm_budget();
+  long long waves = (ctas + sms - 1) / sms;
+  return static_cast<double>(ctas) / static_cast<double>(waves * sms);
 }
 
 static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_wide = false, bool allow_tall = false) {
@@ -1337,7 +1348,8 @@ static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
-  int grid = static_cast<int>(total < kNumSMs ? total : kNumSMs);
+  const int sms = sm_budget();
+  int grid = static_cast<int>(total < sms ? total : sms);
   umma_gemm_kernel<AM, BMD, BTMA, RING><<<grid, kThreads, kSmemBytes, s>>>(p, tm, tm_a);
   return finish_launch();
 }
@@ -1528,6 +1540,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_tma_a") return g_opt_no_tma_a.exchange(value);
   if (k == "tma_tf32") return g_opt_tma_tf32.exchange(value);
   if (k == "no_deep") return g_opt_no_deep.exchange(value);
+  if (k == "sm_budget") return g_opt_sm_budget.exchange(value);
   if (k == "no_klane") return g_opt_no_klane.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
