@@ -118,6 +118,12 @@ int mnv_select(float* dst, const float* src, const int* indices, size_t n_idx, s
  * kernel with fp32 accumulation in TMEM.  workspace (optional) enables split-K. */
 int mnv_matmult(const float* a, const float* b, float* c, int m, int n, int k,
                 void* workspace, size_t workspace_bytes, mnv_stream_t stream);
+/* Extension (host-path): c{m,n} = op(a) * op(b) with op = transpose when trans_x != 0 (a stored {k,m},
+ * b stored {n,k}).  The reference materialises `x.trans()` with cublasSgeam before every such product
+ * (narray.cpp:116-123 + cuda_perform.cu:72-76; owl FullyConnected.bp, owl/owl/net/net.py:612-614); both operand
+ * orders are native UMMA layouts, so owl's lazy `trans()` feeds them here without the copy. */
+int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k, int trans_a, int trans_b,
+                   void* workspace, size_t workspace_bytes, mnv_stream_t stream);
 
 /* ---- a14-a17 Convolution (cuda_perform.h:50-53; cuda_perform.cu:227-337) -------------------
  * NCHW fp32, CUDNN_CONVOLUTION mode (filter rotated 180 degrees):

@@ -52,7 +52,8 @@ enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD 
 //   TMA_A_TILED_MN : column-major matrix; 4 boxes of 32 m x 32 k => MN-major tile (MatMult)
 //   TMA_A_IM2COL_MN: im2col map again, but the 32 pixels are the k axis and 4 boxes of 32 channels (each box its
 //                    own (tap, channel chunk)) the m axis => MN-major tile (backward-filter)
-enum : int { TMA_A_IM2COL_K = 1, TMA_A_TILED_MN = 2, TMA_A_IM2COL_MN = 3 };
+//   TMA_A_TILED_K  : row-major (transposed) matrix: one 128-row x 32-k box per UMMA half => K-major tile (MatMult, A^T)
+enum : int { TMA_A_IM2COL_K = 1, TMA_A_TILED_MN = 2, TMA_A_IM2COL_MN = 3, TMA_A_TILED_K = 4 };
 enum : int { B_KMAJOR = 0, B_DY_WGRAD = 1 };
 
 struct GemmParams {
@@ -79,6 +80,7 @@ struct GemmParams {
   int wide;             // 1: one 128 x bn tile as two UMMA halves of bn/2 columns sharing the A tile, single accumulator
   int tall;             // 1: 256 x bn tile as two UMMA halves of 128 rows sharing the B tile (all-TMA path only)
   int a_mode;           // A_TMA sub-mode (TMA_A_*), 0 otherwise
+  int b_mn;             // 1: B arrives as an MN-major tile (bn/32 boxes of 32 n x 32 k; MatMult with B^T), all-TMA path only
   int cpt;              // 32-channel chunks per filter tap (TMA_A_IM2COL_K: k-stage = tap * cpt + chunk)
   int out_mode;         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
 };
@@ -210,8 +212,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
 // B=TF32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major = false) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major ? 1u << 15 : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major = false, bool b_mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major ? 1u << 15 : 0u) | (b_mn_major ? 1u << 16 : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(BM >> 4) << 24);
 }
 // MN-major tf32 operand.  32-bit MN-major operands exist in one shared-memory layout only, SWIZZLE_128B_BASE32B
@@ -711,8 +713,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     // The whole warp walks the pipeline (so every lane reaches the final __syncthreads together);
     // lane 0 alone issues tcgen05.mma / tcgen05.commit.
     const int bnh = WIDE ? p.bn / 2 : p.bn;           // columns per UMMA instruction
-    const bool a_mn = AM == A_TMA && p.a_mode != TMA_A_IM2COL_K;
-    const uint32_t idesc = make_idesc(bnh, a_mn);
+    const bool a_mn = AM == A_TMA && (p.a_mode == TMA_A_TILED_MN || p.a_mode == TMA_A_IM2COL_MN);
+    const bool b_mn = AM == A_TMA && p.b_mn != 0;
+    const uint32_t idesc = make_idesc(bnh, a_mn, b_mn);
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA K = 8 tf32 = 32 bytes inside the swizzle span
             const uint32_t acc = (ks > t.ks_begin || kk > 0) ? 1u : 0u;
             const uint64_t adesc = a_mn ? make_sw128_desc_mn(a_addr + kk * 1024) : make_sw128_desc(a_addr + kk * 32);
-            const uint64_t bdesc = make_sw128_desc(b_addr + kk * 32);
+            const uint64_t bdesc = b_mn ? make_sw128_desc_mn(b_addr + kk * 1024) : make_sw128_desc(b_addr + kk * 32);
             umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
             if (WIDE)   // second half of the columns: same A tile, B rows bnh.., TMEM columns bnh..
               umma_tf32(tmem_d + bnh, adesc, make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
@@ -789,6 +792,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             } else if (p.a_mode == TMA_A_TILED_MN) {
 #pragma unroll
               for (int j = 0; j < kChunks; ++j) tma_load_2d(a_dst + j * 4096, &tmap_a, bar, t.mt * kTileM + 32 * j, ks * BK);
+            } else if (p.a_mode == TMA_A_TILED_K) {
+#pragma unroll
+              for (int h = 0; h < kHalves; ++h) tma_load_2d(a_dst + h * kABytes, &tmap_a, bar, ks * BK, t.mt * kTileM + h * BM);
             } else {   // k-stage = 32 output pixels of one image (p.spi stages per image)
               const int img = ks / p.spi, pix = (ks - img * p.spi) * BK, oh = pix / p.Wo;
               const int h = oh * p.sv - p.ph, w = (pix - oh * p.Wo) * p.sh - p.pw;
@@ -798,6 +804,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           }
           const uint32_t dst = smem_base + stage * kSBytes + kATile;
           const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;   // a TMA box has at most 256 rows
+          if (AM == A_TMA && p.b_mn) {   // MN-major B: one 32 n x 32 k box per 32 columns (bn % 32 == 0, never wide)
+            for (int j = 0; j < p.bn / 32; ++j) tma_load_2d(dst + j * 4096, &tmap_b, full0 + 8 * stage, t.nt * p.bn + 32 * j, ks * BK);
+          } else
           for (int h = 0; h < halves; ++h) {
             const uint32_t d2 = dst + h * rows * 128;
             const int n0 = t.nt * p.bn + h * rows;
@@ -1439,7 +1448,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.cpt = 1; p.out_mode = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -1562,6 +1571,67 @@ int mnv_matmult(const float* a, const float* b, float* c, int m, int n, int k, v
   p.b_vec = (k % 4 == 0) && aligned16(b);
   p.P = m; p.img_stride = 0; p.col_stride = m;
   return launch_gemm<A_COLMAJOR, B_KMAJOR>(p, workspace, workspace_bytes, as_stream(stream));
+}
+
+// c{m,n} = op(a) * op(b).  trans_a: a is stored {k,m} (so op(a) is K-major: a plain 2-D tensor map); trans_b: b is
+// stored {n,k} (op(b) is MN-major).  Both operands go through TMA as they lie in memory; when an alignment rule of
+// the tensor maps is not met the transpose is materialised in the workspace and the plain path runs.
+int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k, int trans_a, int trans_b, void* workspace,
+                   size_t workspace_bytes, mnv_stream_t stream) {
+  if (!trans_a && !trans_b) return mnv_matmult(a, b, c, m, n, k, workspace, workspace_bytes, stream);
+  if (m < 0 || n < 0 || k < 0) return MNV_EINVAL;
+  if (m == 0 || n == 0) return MNV_OK;
+  if (!a || !b || !c) return MNV_EINVAL;
+  if (k == 0) return mnv_fill(c, static_cast<size_t>(m) * n, 0.f, stream);
+  cudaStream_t s = as_stream(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  size_t ws_left = workspace ? workspace_bytes : 0;
+  // operand-by-operand: can it be mapped in place?
+  const bool a_ok = trans_a ? (k % 4 == 0 && aligned16(a)) : (m % 4 == 0 && aligned16(a));
+  const bool b_ok = trans_b ? (n % 4 == 0 && aligned16(b)) : (k % 4 == 0 && aligned16(b));
+  const bool direct = a_ok && b_ok && !g_opt_simt.load() && !g_opt_no_tma.load() && !(g_opt_no_tma_a.load() & 2) && get_encode_fn() != nullptr;
+  if (!direct) {   // materialise the transposes (needs the workspace), then the plain path
+    const float* a2 = a;
+    const float* b2 = b;
+    if (trans_a) {
+      size_t need = round256(static_cast<size_t>(m) * k * sizeof(float));
+      if (ws_left < need) return MNV_EWORKSPACE;
+      int rc = mnv_transpose(a, reinterpret_cast<float*>(ws), k, m, stream);
+      if (rc) return rc;
+      a2 = reinterpret_cast<float*>(ws); ws += need; ws_left -= need;
+    }
+    if (trans_b) {
+      size_t need = round256(static_cast<size_t>(n) * k * sizeof(float));
+      if (ws_left < need) return MNV_EWORKSPACE;
+      int rc = mnv_transpose(b, reinterpret_cast<float*>(ws), n, k, stream);
+      if (rc) return rc;
+      b2 = reinterpret_cast<float*>(ws); ws += need; ws_left -= need;
+    }
+    return mnv_matmult(a2, b2, c, m, n, k, ws_left ? ws : nullptr, ws_left, stream);
+  }
+  GemmParams p;
+  zero_conv(p);
+  p.a = a; p.b = b; p.out = c;
+  p.M = m; p.N = n; p.K = k;
+  p.lda = trans_a ? k : m; p.ldb = trans_b ? n : k; p.b_vec = 1;
+  p.P = m; p.img_stride = 0; p.col_stride = m;
+  p.a_mode = trans_a ? TMA_A_TILED_K : TMA_A_TILED_MN;
+  p.b_mn = trans_b ? 1 : 0;
+  plan_tiles(p, ws_left, !trans_b, true);   // MN-major B: boxes of 32 columns, no wide tile
+  if (trans_b) {
+    p.bn = (p.bn + 31) / 32 * 32;
+    if (p.bn > BN_MAX) p.bn = BN_MAX;
+    p.n_tiles = (p.N + p.bn - 1) / p.bn;
+    plan_splits(p, ws_left);
+  }
+  p.partial = p.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+  CUtensorMap tm_a, tm_b;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_b, 0, sizeof(tm_b));
+  const bool ok_a = trans_a ? make_b_tmap(&tm_a, a, m, k, k, BM) : make_a_mn_tmap(&tm_a, a, m, k, m);
+  const bool ok_b = trans_b ? make_a_mn_tmap(&tm_b, b, n, k, n) : make_b_tmap(&tm_b, b, n, k, k, p.wide ? p.bn / 2 : p.bn);
+  if (!ok_a || !ok_b) return MNV_EINVAL;
+  return launch_umma_tma(p, tm_a, tm_b, s);
 }
 
 int mnv_conv_forward(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,

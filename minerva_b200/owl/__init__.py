@@ -28,6 +28,11 @@ def ones(shape):
     return NArray.ones(shape)
 
 
+def _uninit(shape):
+    """Uninitialised array for outputs an op overwrites completely (not part of the reference surface)."""
+    return NArray._new(list(shape), current_device())
+
+
 def randn(shape, mu, var):
     """N(mu, var^2): `var` is used as the standard deviation, as on both reference paths
     (minerva/op/impl/basic.cpp:275, cuda_perform.cu:621)."""

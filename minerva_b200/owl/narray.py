@@ -1,5 +1,7 @@
 """owl.NArray -- same operators and static methods as the reference binding
 (owl/owl/libowl.pyx:51-444 over minerva/narray/*.cpp); each maps to one C-ABI call."""
+import weakref
+
 import numpy as np
 import torch
 
@@ -67,10 +69,37 @@ def _check(cond, msg):
 
 
 class NArray:
-    __slots__ = ("_t", "_shape", "_dev", "__weakref__")
+    # `_buf` is the flat device buffer.  `trans()` is lazy: its result holds `_lazy_src` (the untransposed array) and
+    # no buffer until something other than a matrix product reads it (`_t`), because both operand orders are native
+    # to the tensor-core kernel (mnv_matmult_ex) and the reference's explicit transposes in FullyConnected.bp
+    # (owl/owl/net/net.py:612-614) were pure HBM traffic.  `_views` lists pending transposes of this array so that
+    # the one in-place op (sgd_update) can materialise them before it overwrites their source.
+    __slots__ = ("_buf", "_shape", "_dev", "_lazy_src", "_views", "__weakref__")
 
     def __init__(self, tensor, shape, dev):
-        self._t, self._shape, self._dev = tensor, [int(s) for s in shape], dev
+        self._buf, self._shape, self._dev = tensor, [int(s) for s in shape], dev
+        self._lazy_src, self._views = None, None
+
+    @property
+    def _t(self):
+        if self._lazy_src is not None:
+            self._materialize()
+        return self._buf
+
+    def _materialize(self):
+        src, self._lazy_src = self._lazy_src, None
+        m, n = src._shape
+        self._buf = torch.empty(max(m * n, 0), dtype=torch.float32, device=self._dev.device)
+        NArray._call("mnv_transpose", self._dev, src._on(self._dev).data_ptr(), self._buf.data_ptr(), m, n)
+
+    def _flush_views(self):
+        """Materialise pending lazy transposes of this array (called before it is modified in place)."""
+        if self._views:
+            for ref in self._views:
+                v = ref()
+                if v is not None and v._lazy_src is self:
+                    v._materialize()
+            self._views = None
 
     # ---- plumbing ---------------------------------------------------------------------------
     @property
@@ -116,6 +145,8 @@ class NArray:
         and 60 B/param per tensor) as one in-place kernel (20 B/param)."""
         dev = _rt.current_device()
         _check(w._dev is dev and delta._dev is dev, "sgd_update is in place: w and delta must live on this device")
+        w._flush_views()
+        delta._flush_views()
         NArray._call("mnv_sgd_momentum_update", dev, w._t.data_ptr(), delta._t.data_ptr(), grad._on(dev).data_ptr(),
                      w.size, float(momentum), float(lr_over_batch), float(lr_times_wd))
 
@@ -256,16 +287,33 @@ class NArray:
         dev = _rt.current_device()
         m, k, n = lhs._shape[0], lhs._shape[1], rhs._shape[1]
         out = NArray._new([m, n], dev)
+        ta, tb = lhs._lazy_src is not None, rhs._lazy_src is not None
+        if ta and tb:
+            tb = False                                           # at most one operand stays virtual
+        if ta or tb:
+            a = lhs._lazy_src if ta else lhs
+            b = rhs._lazy_src if tb else rhs
+            NArray._call("mnv_matmult_ex", dev, a._on(dev).data_ptr(), b._on(dev).data_ptr(), out._buf.data_ptr(), m, n, k,
+                         int(ta), int(tb), dev.ws_ptr, dev.ws_bytes)
+            return out
         NArray._call("mnv_matmult", dev, lhs._on(dev).data_ptr(), rhs._on(dev).data_ptr(), out._t.data_ptr(), m, n, k,
                      dev.ws_ptr, dev.ws_bytes)
         return out
 
     def trans(self):
+        """Lazy: the copy happens only if something other than a matrix product reads the result."""
         _check(len(self._shape) == 2, "eligible only for 2D")
         dev = _rt.current_device()
         m, n = self._shape
-        out = NArray._new([n, m], dev)
-        NArray._call("mnv_transpose", dev, self._on(dev).data_ptr(), out._t.data_ptr(), m, n)
+        out = NArray(None, [n, m], dev)
+        src = self
+        if src._lazy_src is not None:
+            src._materialize()
+        out._lazy_src = src
+        if src._views is None:
+            src._views = []
+        src._views = [r for r in src._views if r() is not None]
+        src._views.append(weakref.ref(out))
         return out
 
     def reshape(self, s):

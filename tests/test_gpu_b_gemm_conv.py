@@ -199,6 +199,24 @@ def test_matmult_operand_paths(g, m, n, k):
         assert g.norm_rel(got, want) < TOL, name
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (132, 20, 36), (7, 5, 3), (1000, 200, 300), (516, 260, 2100), (4096, 9216, 256), (9216, 256, 4096)])
+@pytest.mark.parametrize("ta,tb", [(1, 0), (0, 1), (1, 1)])
+def test_matmult_ex(g, m, n, k, ta, tb):
+    """c = op(a) op(b) with either operand stored transposed (mapped in place by TMA, or materialised when unaligned)."""
+    a = rng.normal(0, 1, m * k).astype(np.float32)      # op(a) as column-major {m,k}
+    b = rng.normal(0, 1, k * n).astype(np.float32)      # op(b) as column-major {k,n}
+    A, B = a.reshape(k, m), b.reshape(n, k)             # numpy views: A[kk, mm] = op(a)(mm, kk), B[nn, kk] = op(b)(kk, nn)
+    want = (B.astype(np.float64) @ A.astype(np.float64)).ravel()
+    a_st = np.ascontiguousarray(A.T).ravel() if ta else a     # stored {k,m}: element (kk, mm) at kk + mm*k
+    b_st = np.ascontiguousarray(B.T).ravel() if tb else b     # stored {n,k}: element (nn, kk) at nn + kk*n
+    ws = g.workspace()
+    for wsp, wsb in ((ws, ws.numel()),):
+        c = g.empty(m * n)
+        c.fill_(float("nan"))
+        g.run("mnv_matmult_ex", g.dev(a_st), g.dev(b_st), c, m, n, k, ta, tb, wsp, wsb)
+        assert g.norm_rel(g.host(c), want) < TOL
+
+
 def test_conv_forward_goldens(g, golden_dir):
     """tests/unittest_conv_forward.cpp:7-68, tolerance 1e-3 absolute as in the reference."""
     ws = g.workspace()

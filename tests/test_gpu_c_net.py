@@ -54,6 +54,35 @@ def test_owl_api_surface(gpu_owl):
     owl.set_device(0)
 
 
+@pytest.mark.parametrize("m,k,n", [(8, 12, 4), (7, 5, 3), (256, 128, 64), (300, 200, 36), (1000, 256, 4096)])
+def test_lazy_transpose(gpu_owl, m, k, n):
+    """`trans()` defers its copy: a product consumes it through mnv_matmult_ex, anything else materialises it, and the
+    in-place update flushes pending views of the array it overwrites.  Values must match the eager semantics."""
+    owl = gpu_owl
+    from minerva_b200.owl import NArray
+    rng = np.random.default_rng(7)
+    A = rng.normal(0, 1, (k, m)).astype(np.float32)      # owl [m,k]
+    B = rng.normal(0, 1, (n, k)).astype(np.float32)      # owl [k,n]
+    a, b = owl.from_numpy(A), owl.from_numpy(B)
+    want = (B.astype(np.float64) @ A.astype(np.float64))             # numpy view of owl a*b
+    tol = 5e-3 * np.linalg.norm(want)
+    at, bt = owl.from_numpy(np.ascontiguousarray(A.T)), owl.from_numpy(np.ascontiguousarray(B.T))   # owl [k,m], [n,k]
+    assert at.trans()._lazy_src is at
+    for got in (at.trans() * b, a * bt.trans(), at.trans() * bt.trans()):
+        assert got.shape == [m, n]
+        assert np.linalg.norm(got.to_numpy() - want) <= tol
+    # non-product consumers see the transposed values
+    np.testing.assert_array_equal(at.trans().to_numpy(), A)
+    np.testing.assert_array_equal((at.trans() + a).to_numpy(), A + A)
+    np.testing.assert_array_equal(at.trans().trans().to_numpy(), A.T)
+    # a pending view survives an in-place update of its source with the OLD values (eager semantics)
+    w = owl.from_numpy(A.copy())
+    view = w.trans()
+    NArray.sgd_update(w, owl.zeros(w.shape), owl.ones(w.shape), 0.0, 1.0, 0.0)     # w -= 1
+    np.testing.assert_array_equal(view.to_numpy(), A.T)
+    np.testing.assert_array_equal(w.to_numpy(), A - 1)
+
+
 def test_training_step_matches_cpu_oracle(gpu_owl):
     from tests.test_net_cpu import _tiny_net, _batch
     from oracle import owl_cpu
