@@ -724,28 +724,101 @@ __device__ __forceinline__ float pow_neg_beta_sfu(float s, float neg_beta) {
 // Window of 5 (AlexNet, GoogLeNet).  One thread per pixel walking the channels; 32-bit element offsets (the host
 // checks the tensor has < 2^31 elements), one running offset for the loads (8 channels ahead, in registers) and one
 // for the two stores; same add / subtract order as the generic kernel, so `scale` stays bit-identical.
-template <bool BETA075, int CHUNK, int STORE>
+template <bool BETA075, int CHUNK, int PX>
 __global__ void __launch_bounds__(kBlock) lrn_fwd5_kernel(const float* __restrict__ in, float* __restrict__ scale, float* __restrict__ out,
                                                           int num, int C, unsigned step, float alpha_over_size, float neg_beta) {
+  // A thread walks the channels of PX pixels, blockDim apart, so a CTA touches PX KB of each channel plane at a time
+  // (measured: the channel-marching access pattern is bound by DRAM locality, not by the SM -- see DESIGN 5.2).
   const unsigned total = static_cast<unsigned>(num) * step;
-  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    const unsigned n = t / step, p = t - n * step;
-    unsigned ld = n * static_cast<unsigned>(C) * step + p;   // offset of the next channel to load
-    unsigned st = ld;                                         // offset of the next channel to store
+  for (unsigned t0 = blockIdx.x * (blockDim.x * PX) + threadIdx.x; t0 < total; t0 += gridDim.x * (blockDim.x * PX)) {
+    unsigned ld[PX], st[PX];
+    bool live[PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      const unsigned t = t0 + j * blockDim.x;
+      live[j] = t < total;
+      const unsigned tt = live[j] ? t : t0;
+      const unsigned n = tt / step, p = tt - n * step;
+      ld[j] = n * static_cast<unsigned>(C) * step + p;   // offset of the next channel to load
+      st[j] = ld[j];                                      // offset of the next channel to store
+    }
+    float cur[PX][CHUNK], nxt[PX][CHUNK];
+#pragma unroll
+    for (int u = 0; u < CHUNK; ++u)
+#pragma unroll
+      for (int j = 0; j < PX; ++j) {
+        cur[j][u] = u < C ? __ldg(in + ld[j]) : 0.f;
+        ld[j] += step;
+      }
+    float sq0[PX], sq1[PX], sq2[PX], sq3[PX], sq4[PX], x1[PX], x2[PX], acc[PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) sq0[j] = sq1[j] = sq2[j] = sq3[j] = sq4[j] = x1[j] = x2[j] = acc[j] = 0.f;
+    for (int c0 = 0; c0 < C + 2; c0 += CHUNK) {
+      const int left = C - (c0 + CHUNK);   // channels still to load
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u)
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+          nxt[j][u] = u < left ? __ldg(in + ld[j]) : 0.f;
+          ld[j] += step;
+        }
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        const int o = c0 + u - 2;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+          const float xin = cur[j][u];                // 0 past C
+          const float add = __fmul_rn(xin, xin);
+          acc[j] = __fadd_rn(acc[j], add);
+          acc[j] = __fsub_rn(acc[j], sq4[j]);         // x[head-5]^2, +0 while the window is filling
+          sq4[j] = sq3[j]; sq3[j] = sq2[j]; sq2[j] = sq1[j]; sq1[j] = sq0[j]; sq0[j] = add;
+          if (o >= 0 && o < C) {
+            const float sc = __fadd_rn(1.0f, __fmul_rn(acc[j], alpha_over_size));
+            const float ov = __fmul_rn(x2[j], pow_neg_beta_sfu<BETA075>(sc, neg_beta));
+            if (live[j]) { scale[st[j]] = sc; out[st[j]] = ov; }
+            st[j] += step;
+          }
+          x2[j] = x1[j]; x1[j] = xin;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u)
+#pragma unroll
+        for (int j = 0; j < PX; ++j) cur[j][u] = nxt[j][u];
+    }
+  }
+}
+
+// The same walk with sector-aligned stores.  Planes of 55x55 / 27x27 floats start at every 4-byte phase, so a warp
+// that stores "its" 32 pixels writes two partial 32-byte sectors out of five, and the write-heavy forward pass ran at
+// 64 % of HBM peak where 56x56 planes reach 83 % (tools/lrn_align_probe.py).  Here a CTA owns 256 consecutive pixels
+// of ONE image; each chunk of CHUNK channels is parked in shared memory and written back rotated by the plane's
+// misalignment d: thread i stores element (i - d) mod 256, so every warp but one writes whole sectors.
+template <bool BETA075, int CHUNK>
+__global__ void __launch_bounds__(256) lrn_fwd5_aligned_kernel(const float* __restrict__ in, float* __restrict__ scale, float* __restrict__ out,
+                                                               int num, int C, unsigned step, unsigned blocks_per_img, float alpha_over_size,
+                                                               float neg_beta) {
+  __shared__ float buf[2][2][CHUNK][256];
+  const unsigned tid = threadIdx.x;
+  int pp = 0;
+  for (unsigned work = blockIdx.x; work < static_cast<unsigned>(num) * blocks_per_img; work += gridDim.x) {
+    const unsigned n = work / blocks_per_img, pb = work - n * blocks_per_img;
+    const unsigned p0 = pb * 256u, cnt = min(256u, step - p0);
+    const bool live = tid < cnt;
+    const unsigned base = n * static_cast<unsigned>(C) * step + p0;   // channel 0 of this CTA's pixel range
+    unsigned ld = base + tid;
     float cur[CHUNK], nxt[CHUNK];
 #pragma unroll
     for (int u = 0; u < CHUNK; ++u) {
-      cur[u] = u < C ? __ldg(in + ld) : 0.f;
+      cur[u] = (live && u < C) ? __ldg(in + ld) : 0.f;
       ld += step;
     }
-    float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sq4 = 0.f;   // squares of x[head-1..head-5]
-    float x1 = 0.f, x2 = 0.f;                                        // x[head-1], x[head-2]
-    float acc = 0.f;
+    float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sq4 = 0.f, x1 = 0.f, x2 = 0.f, acc = 0.f;
     for (int c0 = 0; c0 < C + 2; c0 += CHUNK) {
       const int left = C - (c0 + CHUNK);   // channels still to load
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) {
-        nxt[u] = u < left ? __ldg(in + ld) : 0.f;
+        nxt[u] = (live && u < left) ? __ldg(in + ld) : 0.f;
         ld += step;
       }
 #pragma unroll
@@ -758,14 +831,25 @@ __global__ void __launch_bounds__(kBlock) lrn_fwd5_kernel(const float* __restric
         const int o = c0 + u - 2;
         if (o >= 0 && o < C) {
           const float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
-          const float ov = __fmul_rn(x2, pow_neg_beta_sfu<BETA075>(sc, neg_beta));
-          if (STORE == 1) { __stcs(scale + st, sc); __stcs(out + st, ov); }
-          else if (STORE == 2) { __stwt(scale + st, sc); __stwt(out + st, ov); }
-          else { scale[st] = sc; out[st] = ov; }
-          st += step;
+          buf[pp][0][u][tid] = sc;
+          buf[pp][1][u][tid] = __fmul_rn(x2, pow_neg_beta_sfu<BETA075>(sc, neg_beta));
         }
         x2 = x1; x1 = xin;
       }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < CHUNK; ++u) {
+        const int o = c0 + u - 2;
+        if (o >= 0 && o < C) {
+          const unsigned g0 = base + static_cast<unsigned>(o) * step;
+          const unsigned e = (tid - (g0 & 31u)) & 255u;   // whole 128-byte lines per warp
+          if (e < cnt) {
+            scale[g0 + e] = buf[pp][0][u][e];
+            out[g0 + e] = buf[pp][1][u][e];
+          }
+        }
+      }
+      pp ^= 1;   // the other buffer is rewritten only after the next barrier, by which time these reads are done
 #pragma unroll
       for (int u = 0; u < CHUNK; ++u) cur[u] = nxt[u];
     }
@@ -1039,8 +1123,19 @@ int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_siz
     const unsigned step32 = static_cast<unsigned>(step);
     // 16 channels of register look-ahead: measured 3960 GB/s on 256x96x55x55 against 3600 with 8 (the kernel is bound by
     // DRAM latency under a 1-read : 2-write mix; evict-first / write-through stores made no difference)
-    if (b075) lrn_fwd5_kernel<true, 16, 0><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, aos, -beta);
-    else lrn_fwd5_kernel<false, 16, 0><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, aos, -beta);
+    if ((step32 & 7u) != 0 && step32 >= 128) {
+      // planes that do not start on sector boundaries (odd sizes): stores rotated through shared memory (4400 vs 3940 GB/s
+      // on 55x55, 4060 vs 3760 on 27x27)
+      const unsigned bpi = (step32 + 255u) / 256u;
+      const size_t items = static_cast<size_t>(num_img) * bpi;
+      const int g2 = static_cast<int>(items < static_cast<size_t>(kNumSMs) * 6 ? items : static_cast<size_t>(kNumSMs) * 6);
+      if (b075) lrn_fwd5_aligned_kernel<true, 8><<<g2, 256, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, bpi, aos, -beta);
+      else lrn_fwd5_aligned_kernel<false, 8><<<g2, 256, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, bpi, aos, -beta);
+      return finish_launch();
+    }
+    // sector-aligned planes: 16 channels of register look-ahead, one pixel per thread (5.2-5.6 TB/s on 28x28 / 32x32 / 56x56)
+    if (b075) lrn_fwd5_kernel<true, 16, 1><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, aos, -beta);
+    else lrn_fwd5_kernel<false, 16, 1><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step32, aos, -beta);
   } else {
     if (b075) lrn_fwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
     else lrn_fwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
