@@ -61,6 +61,19 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tensor-core kernel, averaged over the launches of one
+    ncu launch-list capture of this command (profiles/r01_launch_list_summary.json, tools/launch_summary.py); null for
+    workloads that have no committed capture."""
+    if workload != "alexnet":
+        return None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_launch_list_summary.json")) as f:
+            return float(json.load(f)["umma_gemm_kernel"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     try:
@@ -358,7 +371,7 @@ def main():
         tf32_peak = pk["bf16_tflops_sustained"] / 2.0
         achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf32_peak, "traffic": None,
+                    "frac": achieved / tf32_peak, "traffic": ncu_traffic(args.workload),
                     "kernel": "mnv::umma_gemm_kernel (tcgen05 TF32: MatMult + conv fwd/bwd-data/bwd-filter)",
                     "launches_timed": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
                     "share_of_step": g_ms / total_ms if total_ms else None,
