@@ -137,6 +137,15 @@ int mnv_conv_forward(const float* bottom, const float* filter, const float* bias
                      int stride_vertical, int stride_horizontal, int filter_height,
                      int filter_width, void* workspace, size_t workspace_bytes,
                      mnv_stream_t stream);
+/* Extension (fusion): the same convolution with max(x, 0) applied in the epilogue -- bit-identical to
+ * mnv_conv_forward followed by mnv_relu_forward.  owl.net uses it when a ConvConnection's only consumer is a ReluUnit
+ * (owl/owl/net/net.py:621-716 + :281-296 run them as two ops and re-read the activation from HBM). */
+int mnv_conv_forward_relu(const float* bottom, const float* filter, const float* bias, float* top,
+                     int num_images, int bottom_num_channels, int top_num_channels,
+                     int bottom_height, int bottom_width, int pad_height, int pad_width,
+                     int stride_vertical, int stride_horizontal, int filter_height,
+                     int filter_width, void* workspace, size_t workspace_bytes,
+                     mnv_stream_t stream);
 /* Adjoint w.r.t. bottom.  The reference derives bottom_h from top_h (cuda_perform.cu:277),
  * which is wrong when (H+2p-f)%s != 0; NArray passes the true bottom shape
  * (convolution.cpp:29-48), so it is explicit here. */

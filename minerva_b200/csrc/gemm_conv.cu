@@ -80,9 +80,12 @@ struct GemmParams {
   int wide;             // 1: one 128 x bn tile as two UMMA halves of bn/2 columns sharing the A tile, single accumulator
   int tall;             // 1: 256 x bn tile as two UMMA halves of 128 rows sharing the B tile (all-TMA path only)
   int a_mode;           // A_TMA sub-mode (TMA_A_*), 0 otherwise
+  int relu;             // 1: epilogue applies max(x, 0) after the bias (conv + ReLU units fused by owl.net)
   int b_mn;             // 1: B arrives as an MN-major tile (bn/32 boxes of 32 n x 32 k; MatMult with B^T), all-TMA path only
   int cpt;              // 32-channel chunks per filter tap (TMA_A_IM2COL_K: k-stage = tap * cpt + chunk)
   int out_mode;         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
+                        // 2: the same over a space-to-depth view (below): virtual (tap, channel) -> real filter element
+  int r_ci, r_fh, r_fw, r_sv, r_sh;   // out_mode 2: the real convolution's channels, filter and strides
 };
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -276,12 +279,23 @@ __device__ __forceinline__ float b_elem(const GemmParams& p, int n, int k) {
 }
 __device__ __forceinline__ bool out_row_ok(const GemmParams& p, int m) {
   if (m >= p.M) return false;
+  if (p.out_mode == 2) {   // virtual channel (c, dy, dx) of virtual tap (a, b) is real tap (a*sv + dy, b*sh + dx) of channel c
+    const int chunk = m >> 5, tap = chunk / p.cpt, ch = (chunk - tap * p.cpt) * 32 + (m & 31);
+    const int a = tap / p.fw, b = tap - a * p.fw, r = ch / p.r_sh;   // r = c * sv + dy
+    return ch < p.Ci && a * p.r_sv + r % p.r_sv < p.r_fh && b * p.r_sh + (ch - r * p.r_sh) < p.r_fw;
+  }
   return p.out_mode == 0 || ((m >> 5) % p.cpt) * 32 + (m & 31) < p.Ci;   // padded channels of a tap carry no output
 }
 __device__ __forceinline__ size_t out_index(const GemmParams& p, int m, int n) {
   if (p.out_mode == 1) {   // filter_diff[co = n][ci][r][s]; tap (kh,kw) of the correlation is filter element ff-1-tap
     int chunk = m >> 5, tap = chunk / p.cpt, ci = (chunk - tap * p.cpt) * 32 + (m & 31), ff = p.fh * p.fw;
     return static_cast<size_t>(n) * p.col_stride + static_cast<size_t>(ci) * ff + (ff - 1 - tap);
+  }
+  if (p.out_mode == 2) {
+    const int chunk = m >> 5, tap = chunk / p.cpt, ch = (chunk - tap * p.cpt) * 32 + (m & 31);
+    const int a = tap / p.fw, b = tap - a * p.fw, r = ch / p.r_sh, c = r / p.r_sv;
+    const int kh = a * p.r_sv + (r - c * p.r_sv), kw = b * p.r_sh + (ch - r * p.r_sh), ff = p.r_fh * p.r_fw;
+    return static_cast<size_t>(n) * p.col_stride + static_cast<size_t>(c) * ff + (ff - 1 - (kh * p.r_fw + kw));
   }
   int img = m / p.P, pix = m - img * p.P;
   return static_cast<size_t>(img) * p.img_stride + pix + static_cast<size_t>(n) * p.col_stride;
@@ -297,7 +311,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmParams p) {
     int m = static_cast<int>(t % p.M), n = static_cast<int>(t / p.M);
     float acc = 0.f;
     for (int k = 0; k < p.K; ++k) acc = fmaf(a_elem<AM>(p, m, k), b_elem<BMD>(p, n, k), acc);
-    p.out[out_index(p, m, n)] = acc + (p.bias ? __ldg(p.bias + n) : 0.f);
+    float v = acc + (p.bias ? __ldg(p.bias + n) : 0.f);
+    p.out[out_index(p, m, n)] = (p.relu && !(v > 0.f)) ? 0.f : v;
   }
 }
 
@@ -671,6 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       tc_fence_after();
       const int n0 = t.nt * p.bn;
       const bool add_bias = p.bias != nullptr && p.splits == 1;
+      const bool relu = p.relu != 0 && p.splits == 1;
 #pragma unroll
       for (int half = 0; half < (TALL ? 2 : 1); ++half) {
         const int m = t.mt * kTileM + half * BM + quarter * 32 + lane;
@@ -694,6 +710,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
               if (n < p.N) {
                 float val = __uint_as_float(r[j]);
                 if (add_bias) val += __ldg(p.bias + n);
+                if (relu) val = val > 0.f ? val : 0.f;
                 dst[static_cast<size_t>(n) * cstride] = val;
               }
             }
@@ -1060,6 +1077,7 @@ __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams 
     float acc = __ldg(p.partial + t);
     for (int s = 1; s < p.splits; ++s) acc += __ldg(p.partial + static_cast<size_t>(s) * mn + t);
     if (p.bias) acc += __ldg(p.bias + n);
+    if (p.relu) acc = acc > 0.f ? acc : 0.f;
     p.out[out_index(p, m, n)] = acc;
   }
 }
@@ -1099,6 +1117,7 @@ static std::atomic<int> g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for b
 static std::atomic<int> g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
 static std::atomic<int> g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
 static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
+static std::atomic<int> g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1236,6 +1255,81 @@ __global__ void __launch_bounds__(kBlock) filter_pack_kernel(const float* __rest
     float v = c < C ? __ldg(w + n * sn + static_cast<size_t>(c) * sc + (flip ? ff - 1 - tap : tap)) : 0.f;
     out[t] = round ? to_tf32(v) : v;
   }
+}
+
+// ---- space-to-depth view of strided few-channel convolutions (AlexNet conv1: 3 channels, 11x11 / 4) -----------------
+// A stride-(sv,sh) cross-correlation over Ci channels is a stride-1 one over Ci*sv*sh channels:
+//   xv[n][Y][X][(c,dy,dx)] = x[n][c][Y*sv + dy - ph][X*sh + dx - pw]          (zero outside the image)
+//   wv[co][(a,b)][(c,dy,dx)] = w[co][c][a*sv + dy][b*sh + dx]                 (zero past the real filter)
+//   y[oy][ox] = sum_{a,b,(c,dy,dx)} xv[oy + a][ox + b][.] * wv[(a,b)][.],    a < ceil(fh/sv), b < ceil(fw/sh)
+// xv is channels-last with >= 32 channels, so the im2col tensor maps feed the tensor core (no gather warps, whose
+// 12-k-stage tiles were latency-bound: 128 TF/s) at the price of multiplying some zeros (AlexNet conv1: K 363 -> 576).
+struct S2D {
+  int Ci, H, W, ph, pw, sv, sh, fh, fw;   // the real convolution
+  int Civ, Hv, Wv, fhv, fwv;              // the stride-1 view (pad 0)
+};
+static bool s2d_plan(S2D* v, int Ci, int H, int W, int Ho, int Wo, int ph, int pw, int sv, int sh, int fh, int fw) {
+  if (sv == 1 && sh == 1) return false;
+  v->Ci = Ci; v->H = H; v->W = W; v->ph = ph; v->pw = pw; v->sv = sv; v->sh = sh; v->fh = fh; v->fw = fw;
+  v->Civ = Ci * sv * sh; v->fhv = (fh + sv - 1) / sv; v->fwv = (fw + sh - 1) / sh;
+  v->Hv = Ho + v->fhv - 1; v->Wv = Wo + v->fwv - 1;
+  if (Ci >= BK || v->Civ > 1024) return false;                            // enough channels already: the direct map is better
+  const int cpt = (v->Civ + BK - 1) / BK;
+  if (cpt * BK * 2 > v->Civ * 3) return false;                            // same padding rule as conv_tma_fprop
+  if (static_cast<size_t>(Ci) * sv * (static_cast<size_t>(v->Wv) * sh + 1) * sizeof(float) > 48 * 1024) return false;   // staging rows
+  return true;
+}
+// One CTA per (image, virtual row Y): the Ci*sv source rows are staged in shared memory (coalesced reads along x),
+// then the Wv * Cp output floats of the row are written in order (coalesced), channels Civ..Cp-1 zero.
+__global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const S2D v, int Cp) {
+  extern __shared__ float rows[];
+  const int L = v.Wv * v.sh, pitch = L + 1, R = v.Ci * v.sv;
+  const int Y = blockIdx.x % v.Hv;
+  const size_t n = blockIdx.x / v.Hv;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int r = wid; r < R; r += 8) {
+    const int c = r / v.sv, yy = Y * v.sv + (r - c * v.sv) - v.ph;
+    const bool row_ok = yy >= 0 && yy < v.H;
+    const float* src = x + ((n * v.Ci + c) * v.H + (row_ok ? yy : 0)) * v.W;
+    for (int i = lane; i < L; i += 32) {
+      const int xx = i - v.pw;
+      rows[r * pitch + i] = (row_ok && xx >= 0 && xx < v.W) ? __ldg(src + xx) : 0.f;
+    }
+  }
+  __syncthreads();
+  float* dst = y + (n * v.Hv + Y) * static_cast<size_t>(v.Wv) * Cp;
+  const int total = v.Wv * Cp;
+  for (int o = threadIdx.x; o < total; o += 256) {
+    const int X = o / Cp, ch = o - X * Cp, r = ch / v.sh;
+    dst[o] = ch < v.Civ ? rows[r * pitch + X * v.sh + (ch - r * v.sh)] : 0.f;
+  }
+}
+// B operand of the view: out[n][(a,b)][ch] (ch < Kc, zero past Civ and past the real filter)
+//   = w[n*sn + c*sc + (flip ? ff-1-t : t)], t = (a*sv + dy) * fw + b*sh + dx, ch = (c*sv + dy)*sh + dx.
+__global__ void __launch_bounds__(kBlock) s2d_filter_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, const S2D v,
+                                                                 int Kc, long long sn, long long sc, int flip, int round) {
+  const int ffv = v.fhv * v.fwv, ff = v.fh * v.fw;
+  size_t total = static_cast<size_t>(rows) * ffv * Kc;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(t % Kc);
+    size_t rest = t / Kc;
+    const int tap = static_cast<int>(rest % ffv);
+    const size_t n = rest / ffv;
+    const int a = tap / v.fwv, b = tap - a * v.fwv, r = ch / v.sh, c = r / v.sv;
+    const int kh = a * v.sv + (r - c * v.sv), kw = b * v.sh + (ch - r * v.sh);
+    float val = 0.f;
+    if (ch < v.Civ && kh < v.fh && kw < v.fw) {
+      const int tr = kh * v.fw + kw;
+      val = __ldg(w + n * sn + static_cast<size_t>(c) * sc + (flip ? ff - 1 - tr : tr));
+    }
+    out[t] = round ? to_tf32(val) : val;
+  }
+}
+static int launch_s2d(const float* x, float* y, int N, const S2D& v, int Cp, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(v.Ci) * v.sv * (static_cast<size_t>(v.Wv) * v.sh + 1) * sizeof(float);
+  s2d_nhwc_kernel<<<static_cast<unsigned>(N) * v.Hv, 256, smem, s>>>(x, y, v, Cp);
+  return finish_launch();
 }
 
 // top_diff[img][co][pitch] (pitch % 4 == 0, only the first P pixels of a row are real) as a 3-D tensor;
@@ -1448,7 +1542,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -1477,9 +1571,11 @@ static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, c
 // Both copies are TF32-rounded pre-passes into the workspace (one streaming pass each, << the GEMM).
 // *done stays false when the path does not apply (tiny channel counts, no workspace): the caller falls back to
 // the gather kernel.
-static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long long w_sc, int flip, const float* bias, float* out, int N,
+static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long long w_sc, int flip, const float* bias, int relu, float* out, int N,
                           int Ci, int Co, int H, int W, int Ho, int Wo, int ph, int pw, int sv, int sh, int fh, int fw, void* ws,
-                          size_t ws_bytes, cudaStream_t s, bool* done) {
+                          size_t ws_bytes, cudaStream_t s, bool* done, const S2D* s2d = nullptr) {
+  // s2d != null: x and w are the REAL strided convolution's operands (w strides w_sn / w_sc over its real taps) and the
+  // geometry arguments describe its stride-1 space-to-depth view; only the two pre-passes differ.
   *done = false;
   if ((g_opt_no_tma_a.load() & 1) || g_opt_simt.load() || g_opt_no_tma.load() || !ws) return MNV_OK;
   const int cpt = (Ci + BK - 1) / BK, ff = fh * fw;
@@ -1504,23 +1600,24 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   p.M = static_cast<int>(M); p.N = Co; p.K = static_cast<int>(K);
   p.ldb = p.K; p.b_vec = 1;
   p.P = Ho * Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
-  p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt;
+  p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt; p.relu = relu;
   plan_tiles(p, ws2_bytes, true, true);
   // Measured on AlexNet's layers (tools/tma_diag.py, profiles/r01_tma_diag_*.log): the all-TMA kernel is 10-35%
   // faster than the gather kernel, but the channels-last pre-pass costs one pass over the input, so the path pays
   // only when the GEMM does enough work per input element (Co * taps >= ~3000, i.e. ~1500 flop per input byte).
   // Narrow outputs (bn <= 128) are the gather kernel's worst case (128 x 96 tile: 270 TF/s, against 402 TF/s for
   // the 256 x 96 tile here): always taken.  "force_tma_a" overrides for experiments.
-  if (!g_opt_force_tma_a.load() && static_cast<long long>(Co) * ff < 3000 && p.bn > 128) return MNV_OK;
+  if (!s2d && !g_opt_force_tma_a.load() && static_cast<long long>(Co) * ff < 3000 && p.bn > 128) return MNV_OK;
   p.partial = p.splits > 1 ? static_cast<float*>(ws2) : nullptr;
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
   if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
   if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
-  int rc = launch_nhwc(x, xh, N, Ci, Cp, H * W, s);
+  int rc = s2d ? launch_s2d(x, xh, N, *s2d, Cp, s) : launch_nhwc(x, xh, N, Ci, Cp, H * W, s);
   if (rc) return rc;
-  filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
+  if (s2d) s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, *s2d, cpt * BK, w_sn, w_sc, flip, prepass_round());
+  else filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
   rc = finish_launch();
   if (rc) return rc;
   *done = true;
@@ -1552,6 +1649,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "sm_budget") return g_opt_sm_budget.exchange(value);
   if (k == "no_klane") return g_opt_no_klane.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
+  if (k == "no_s2d") return g_opt_no_s2d.exchange(value);
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   return -1;
@@ -1634,16 +1732,39 @@ int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k
   return launch_umma_tma(p, tm_a, tm_b, s);
 }
 
+static int conv_forward_impl(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
+                             int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                             size_t workspace_bytes, mnv_stream_t stream, int relu);
 int mnv_conv_forward(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
                      int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
                      size_t workspace_bytes, mnv_stream_t stream) {
+  return conv_forward_impl(bottom, filter, bias, top, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes, stream, 0);
+}
+int mnv_conv_forward_relu(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
+                          int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                          size_t workspace_bytes, mnv_stream_t stream) {
+  return conv_forward_impl(bottom, filter, bias, top, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes, stream, 1);
+}
+static int conv_forward_impl(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
+                             int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                             size_t workspace_bytes, mnv_stream_t stream, int relu) {
   int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
   if (rc) return rc;
   if (N == 0) return MNV_OK;
   if (!bottom || !filter || !bias || !top) return MNV_EINVAL;
+  {  // strided few-channel convolutions (AlexNet conv1) through their stride-1 space-to-depth view
+    S2D v;
+    const int Ho = (H + 2 * ph - fh) / sv + 1, Wo = (W + 2 * pw - fw) / sh + 1;
+    if (!g_opt_no_s2d.load() && s2d_plan(&v, Ci, H, W, Ho, Wo, ph, pw, sv, sh, fh, fw)) {
+      bool done = false;
+      rc = conv_tma_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, relu, top, N, v.Civ, Co, v.Hv, v.Wv,
+                          Ho, Wo, 0, 0, 1, 1, v.fhv, v.fwv, workspace, workspace_bytes, as_stream(stream), &done, &v);
+      if (rc || done) return rc;
+    }
+  }
   {  // both operands through TMA when the channel count makes 32-channel k-stages worthwhile
     bool done = false;
-    rc = conv_tma_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, top, N, Ci, Co, H, W,
+    rc = conv_tma_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, relu, top, N, Ci, Co, H, W,
                         (H + 2 * ph - fh) / sv + 1, (W + 2 * pw - fw) / sh + 1, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes,
                         as_stream(stream), &done);
     if (rc || done) return rc;
@@ -1654,7 +1775,7 @@ int mnv_conv_forward(const float* bottom, const float* filter, const float* bias
   p.Ho = (H + 2 * ph - fh) / sv + 1; p.Wo = (W + 2 * pw - fw) / sh + 1;
   long long M = static_cast<long long>(N) * p.Ho * p.Wo, K = static_cast<long long>(Ci) * fh * fw;
   if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Ci * H * W)) return MNV_EUNSUPPORTED;
-  p.a = bottom; p.b = filter; p.bias = bias; p.out = top;
+  p.a = bottom; p.b = filter; p.bias = bias; p.out = top; p.relu = relu;
   p.M = static_cast<int>(M); p.N = Co; p.K = static_cast<int>(K);
   p.ldb = p.K; p.b_vec = (p.K % 4 == 0) && aligned16(filter);
   p.P = p.Ho * p.Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
@@ -1680,7 +1801,7 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
     // B[n = ci][k = (tap, co)] = filter[co][ci][tap]: the two 180-degree rotations (true convolution, transposed
     // operator) cancel
     bool done = false;
-    rc = conv_tma_fprop(top_diff, filter, fh * fw, static_cast<long long>(Ci) * fh * fw, 0, nullptr, bottom_diff, N, Co, Ci, Ho, Wo, H, W,
+    rc = conv_tma_fprop(top_diff, filter, fh * fw, static_cast<long long>(Ci) * fh * fw, 0, nullptr, 0, bottom_diff, N, Co, Ci, Ho, Wo, H, W,
                         fh - 1 - ph, fw - 1 - pw, 1, 1, fh, fw, workspace, workspace_bytes, as_stream(stream), &done);
     if (rc || done) return rc;
   }
@@ -1752,6 +1873,32 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
   long long kpad = static_cast<long long>(N) * p.spi * BK;
   if (!fits_int(kpad)) return MNV_EUNSUPPORTED;
   p.K = static_cast<int>(kpad);          // k-stages = N * spi; validity is per-pixel inside the gathers
+  {  // strided few-channel convolutions: the same all-TMA kernel over the stride-1 space-to-depth view
+    S2D v;
+    if (!(g_opt_no_tma_a.load() & 4) && !g_opt_no_s2d.load() && get_im2col_fn() && s2d_plan(&v, Ci, H, W, p.Ho, p.Wo, ph, pw, sv, sh, fh, fw)) {
+      const int cpt = (v.Civ + BK - 1) / BK, Cp = (v.Civ + 3) / 4 * 4;
+      const size_t x_bytes = round256(static_cast<size_t>(N) * v.Hv * v.Wv * Cp * sizeof(float));
+      if (ws_left >= x_bytes && fits_int(static_cast<long long>(N) * v.Hv * v.Wv * Cp)) {
+        GemmParams q = p;
+        float* xh = reinterpret_cast<float*>(ws);
+        q.Ci = v.Civ; q.H = v.Hv; q.W = v.Wv; q.fh = v.fhv; q.fw = v.fwv; q.ph = q.pw = 0; q.sv = q.sh = 1;
+        q.r_ci = Ci; q.r_fh = fh; q.r_fw = fw; q.r_sv = sv; q.r_sh = sh;
+        q.a = xh; q.M = v.fhv * v.fwv * cpt * BK; q.a_mode = TMA_A_IM2COL_MN; q.cpt = cpt; q.out_mode = 2;
+        q.P = q.M; q.col_stride = static_cast<long long>(Ci) * fh * fw;
+        plan_tiles(q, ws_left - x_bytes, true, true);
+        q.partial = q.splits > 1 ? reinterpret_cast<float*>(ws + x_bytes) : nullptr;
+        CUtensorMap tm_a, tm_b;
+        memset(&tm_a, 0, sizeof(tm_a));
+        memset(&tm_b, 0, sizeof(tm_b));
+        if (make_im2col_tmap(&tm_a, xh, Cp, v.Wv, v.Hv, N, 0, 0, v.fwv, v.fhv, 1, 1, BK, true) &&
+            make_dy_tmap(&tm_b, dy_tma, P, pitch, Co, N, q.wide ? q.bn / 2 : q.bn)) {
+          rc = launch_s2d(bottom, xh, N, v, Cp, s);
+          if (rc) return rc;
+          return launch_umma_tma(q, tm_a, tm_b, s);
+        }
+      }
+    }
+  }
   {  // A through TMA as well: channels-last copy of the bottom read by an im2col map, pixels as the k axis
     const int cpt = (Ci + BK - 1) / BK, Cp = (Ci + 3) / 4 * 4;
     const size_t x_bytes = round256(static_cast<size_t>(N) * H * W * Cp * sizeof(float));

@@ -3,6 +3,7 @@ from .narray import NArray, ConvInfo, PoolingInfo, pooling_algo, softmax_algo
 
 soft_op = softmax_algo
 pool_op = pooling_algo
+FUSED_CONV_RELU = True     # Convolver.ff(..., relu=True) exists: owl.net folds single-consumer ReLU units into it
 
 
 def softmax(x, op=soft_op.instance):
@@ -29,8 +30,9 @@ class Convolver:
     def __init__(self, pad_h, pad_w, stride_v, stride_h):
         self.param = ConvInfo(pad_h, pad_w, stride_v, stride_h)
 
-    def ff(self, x, w, b):
-        return NArray.conv_forward(x, w, b, self.param)
+    def ff(self, x, w, b, relu=False):
+        """relu=True (not in the reference signature): rectify in the convolution's epilogue (mnv_conv_forward_relu)."""
+        return NArray.conv_forward(x, w, b, self.param, relu)
 
     def bp(self, y, x, w):
         return NArray.conv_backward_data(y, x, w, self.param)

@@ -364,7 +364,7 @@ class NArray:
 
     # ---- convolution family (narray/convolution.cpp) -----------------------------------------------
     @staticmethod
-    def conv_forward(src, filt, bias, info):
+    def conv_forward(src, filt, bias, info, relu=False):
         W, H, Ci, N = src._shape
         fw, fh, Ci2, Co = filt._shape
         _check(Ci == Ci2, "#input channels mismatch")
@@ -373,7 +373,7 @@ class NArray:
         Ho = (H + 2 * info.pad_height - fh) // info.stride_vertical + 1
         dev = _rt.current_device()
         out = NArray._new([Wo, Ho, Co, N], dev)
-        NArray._call("mnv_conv_forward", dev, src._on(dev).data_ptr(), filt._on(dev).data_ptr(), bias._on(dev).data_ptr(),
+        NArray._call("mnv_conv_forward_relu" if relu else "mnv_conv_forward", dev, src._on(dev).data_ptr(), filt._on(dev).data_ptr(), bias._on(dev).data_ptr(),
                      out._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
                      info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
         return out

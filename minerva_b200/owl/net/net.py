@@ -93,8 +93,10 @@ class ReluUnit(ComputeUnitSimple):
     def __init__(self, name, btm, top):
         super().__init__(name, [btm], [top])
 
+    fused = False     # set by Net._plan_fusion: the producing convolution already rectified x in its epilogue
+
     def ff(self, x, phase):
-        self.ff_y = self.B.ele.relu(x)
+        self.ff_y = x if self.fused else self.B.ele.relu(x)
         return self.ff_y
 
     def bp(self, y, phase):
@@ -238,6 +240,7 @@ class ConvConnection(WeightedComputeUnit):
     def __init__(self, name, btm, top, num_output, kernel_size, stride=1, pad=0, **kw):
         super().__init__(name, btm, top, **kw)
         self.num_output, self.kernel_size, self.stride, self.pad = num_output, kernel_size, stride, pad
+        self.fuse_relu = False
 
     def ff(self, act, phase):
         if not hasattr(self, "convolver"):
@@ -248,6 +251,8 @@ class ConvConnection(WeightedComputeUnit):
             self.fan_in = self.kernel_size * self.kernel_size * ci
             self.wshape, self.bshape = [self.kernel_size, self.kernel_size, ci, self.num_output], [self.num_output]
             self.init_weights_with_filler()
+        if self.fuse_relu:
+            return self.convolver.ff(act, self.weight, self.bias, relu=True)
         return self.convolver.ff(act, self.weight, self.bias)
 
     def bp(self, sen, phase):
@@ -308,6 +313,7 @@ class Net(object):
         self.base_weight_decay = 5e-4
         self.batch_size = 0          # GLOBAL batch: the update divisor (net.py:252-254,1121-1124)
         self.on_weight_grad = None   # hook(unit) fired as soon as a unit's gradients exist
+        self.fuse_conv_relu = True   # False: run conv and ReLU as the reference's two ops
 
     def add_unit(self, unit):
         unit.B = self.B
@@ -324,7 +330,29 @@ class Net(object):
     def get_data_unit(self):
         return [u for u in self.units if isinstance(u, DataUnit)][0]
 
+    def _plan_fusion(self):
+        """SURVEY 8f fusion: a ConvConnection whose output is read by exactly one unit, a ReluUnit, rectifies in its
+        own epilogue (mnv_conv_forward_relu) and the ReluUnit passes the blob through; results are bit-identical to
+        the two-op sequence (owl/owl/net/net.py:281-296 after :621-716).  Only backends that advertise the fused
+        entry point take part (the CPU twin used by the parity tests does not)."""
+        self._fusion_planned = True
+        if not getattr(self.B.co, "FUSED_CONV_RELU", False) or not self.fuse_conv_relu:
+            return
+        for i, u in enumerate(self.units):
+            if not isinstance(u, ConvConnection):
+                continue
+            top, readers = u.top_names[0], []
+            for v in self.units[i + 1:]:
+                if top in v.btm_names:
+                    readers.append(v)
+                if top in v.top_names:      # an in-place unit rewrites the name: later readers see its output
+                    break
+            if len(readers) == 1 and isinstance(readers[0], ReluUnit):
+                u.fuse_relu, readers[0].fused = True, True
+
     def forward(self, phase="TRAIN"):
+        if not getattr(self, "_fusion_planned", False):
+            self._plan_fusion()
         blobs = {}
         for u in self.units:      # builders append units in topological order
             u.forward(blobs, blobs, phase)

@@ -94,6 +94,11 @@ CONV_CASES = [
     (2, 256, 384, 13, 13, 1, 1, 1, 1, 3, 3),  # AlexNet conv3 at full spatial size
     (2, 24, 40, 7, 7, 0, 0, 1, 1, 1, 1),      # GoogLeNet 1x1
     (2, 3, 8, 30, 30, 3, 3, 2, 2, 7, 7),      # GoogLeNet conv1 geometry
+    # strided few-channel convolutions that run through the space-to-depth view (Ci*sv*sh >= 22, like rows 4 and 8 above)
+    (2, 4, 6, 14, 13, 2, 1, 3, 2, 5, 4),      # asymmetric stride, pad and filter; 24 virtual channels
+    (3, 8, 40, 15, 15, 1, 1, 2, 2, 3, 3),     # 32 virtual channels, filter not a multiple of the stride
+    (2, 3, 16, 30, 31, 2, 3, 4, 4, 7, 6),     # pad > 0 with stride 4, (H + 2p - f) % s != 0
+    (2, 6, 200, 21, 21, 0, 0, 4, 4, 8, 8),    # 96 virtual channels = 3 chunks, filter == 2 strides, 200 outputs (bn > 128)
 ]
 
 
@@ -178,6 +183,38 @@ def test_conv_operand_paths(g, case):
         assert g.norm_rel(y, wy) < TOL, name + ": forward"
         assert g.norm_rel(dx, wdx) < TOL, name + ": backward data"
         assert g.norm_rel(dw, wdw) < TOL, name + ": backward filter"
+
+
+@pytest.mark.parametrize("case", [CONV_CASES[1], CONV_CASES[4], CONV_CASES[8], CONV_CASES[10], TMA_CASES[1], TMA_CASES[5], TMA_CASES[6]])
+def test_conv_forward_relu_fused(g, case):
+    """mnv_conv_forward_relu == mnv_relu_forward(mnv_conv_forward), bit for bit, on every operand path (incl. split-K
+    and the SIMT checker)."""
+    N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = case
+    Ho, Wo = orc.conv_out(H, ph, fh, sv), orc.conv_out(W, pw, fw, sh)
+    x = rng.normal(0, 1, N * Ci * H * W).astype(np.float32)
+    w = rng.normal(0, 1, Co * Ci * fh * fw).astype(np.float32)
+    b = rng.normal(0, 1, Co).astype(np.float32)
+    geo = (N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw)
+    ws = g.workspace()
+    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "simt": 0}
+    for name, opts in OPERAND_PATHS[:3] + [("default", {}), ("simt", {"simt": 1})]:
+        if name == "simt" and x.size * Co * fh * fw >= 5e8:
+            continue
+        try:
+            for k, v in {**defaults, **opts}.items():
+                _set(k, v)
+            for wsp, wsb in ((ws, ws.numel()), (0, 0)):
+                y = g.empty(N * Co * Ho * Wo); y.fill_(float("nan"))
+                g.run("mnv_conv_forward", g.dev(x), g.dev(w), g.dev(b), y, *geo, wsp, wsb)
+                yr = g.empty(y.numel()); yr.fill_(float("nan"))
+                g.run("mnv_relu_forward", y, yr, 1, 1, 1, y.numel())
+                yf = g.empty(y.numel()); yf.fill_(float("nan"))
+                g.run("mnv_conv_forward_relu", g.dev(x), g.dev(w), g.dev(b), yf, *geo, wsp, wsb)
+                assert np.array_equal(g.host(yf), g.host(yr)), name
+                assert (g.host(yf) > 0).any() and (g.host(yf) == 0).any()
+        finally:
+            for k, v in defaults.items():
+                _set(k, v)
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 64, 64), (132, 17, 36), (1000, 200, 300), (516, 260, 2100), (2048, 96, 4100)])

@@ -117,6 +117,28 @@ def test_training_step_matches_cpu_oracle(gpu_owl):
     assert not np.array_equal(w0, gpu.units[1].weight.to_numpy())
 
 
+def test_conv_relu_fusion_is_bit_identical(gpu_owl):
+    """Net._plan_fusion: the fused graph (conv epilogue rectifies, ReluUnit passes through) gives the same bits."""
+    from tests.test_net_cpu import _tiny_net, _batch
+    from minerva_b200.owl.net.net import _default_backend, ConvConnection, ReluUnit
+    res = []
+    for fuse in (True, False):
+        gpu_owl.set_seed(5)
+        net = _tiny_net(_default_backend())
+        net.fuse_conv_relu = fuse
+        du = net.get_data_unit()
+        du.data, du.label = _batch(net.B, 8)
+        net.batch_size = 8
+        net.forward("TRAIN")
+        net.backward("TRAIN")
+        n_fused = sum(1 for u in net.units if isinstance(u, ConvConnection) and u.fuse_relu)
+        assert (n_fused > 0) == fuse and n_fused == sum(1 for u in net.units if isinstance(u, ReluUnit) and u.fused)
+        res.append([net.units[uid].weightgrad.to_numpy() for uid in net.get_weighted_unit_ids()]
+                   + [net.get_loss_units()[0].ff_y.to_numpy()])
+    for a, b in zip(*res):
+        np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("builder,shape,batch", [("build_lenet", [28, 28, 1], 16), ("build_mnist_mlp", [784], 16)])
 def test_small_configs_train(gpu_owl, builder, shape, batch):
     """configs[0..1] of BASELINE.json at reduced batch: loss goes down on a fixed synthetic batch."""
