@@ -168,6 +168,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given as (low word, shared high word): the issuing thread only adds to the 14-bit address fields
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -1099,6 +1110,203 @@ __global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// shift-GEMM convolution: stride-1 cross-correlation straight out of a shared-memory copy of the input
+// ------------------------------------------------------------------------------------------------
+// A channels-last activation xv[pos][C] (pos = (n*Hv + Y)*Wv + X, flat over the whole batch) is its own im2col
+// matrix up to a ROW SHIFT: for the output at flat position pos, tap (a, b) reads row pos + a*Wv + b.  So one
+// "plane" of 256 + halo consecutive rows x 32 channels (128 B rows, 128B swizzle, one TMA load) serves every tap of
+// a 256-position tile: the tap only moves the UMMA descriptor's start address by whole 128 B rows.  The 128B swizzle
+// is a function of the absolute shared-memory address on both the TMA and the UMMA side, so a start address that is
+// not 1024 B aligned needs nothing else (measured with tools/shift_diag.py: the base-offset field must stay 0).
+// Nothing is duplicated on the L2 -> SM path, which is what bounds the im2col-fed kernel on narrow outputs
+// (AlexNet conv1 after space-to-depth: 3.0 GB of TMA traffic as im2col, 0.3 GB as planes).
+// Positions whose window would leave the image (X >= Wo or Y >= Ho) are computed and dropped by the epilogue
+// (conv1: 57x57 positions per 55x55 outputs = 7 % more tensor work).
+// Orientation: D[filter][position] -- the filters are the UMMA's M (128 rows, Co <= 128 of them real), the 256
+// positions its N.  One 128 x 256 x 8 instruction costs ~120 cycles whatever N is filled with; with the positions as
+// M, a 96-filter output needs 128 x 96 x 8 instructions of ~95 cycles each (measured: 50 % pipe-active but 2.2x the
+// time).  The epilogue transposes 32 x 32 blocks through shared memory so that a warp stores 32 consecutive pixels of
+// one filter plane (128 B).  k-stage order is chunk-major (all taps of channel chunk 0, then chunk 1, ...) so a plane
+// is released as soon as its taps are issued and the 3-plane ring prefetches across tiles.
+struct ShiftParams {
+  const float* bias;     // per filter, may be null
+  float* out;            // out[n][co][Ho*Wo]
+  int Co, bn, Ho, Wo, Hv, Wv, fwv, taps, cpt, relu;
+  int nk_last;           // 8-channel k-steps of the last channel chunk (1..4): all-zero steps are not issued
+  int b_stages;          // depth of the filter ring (<= kShBStagesMax)
+  int m_tiles;           // ceil(total positions / 256)
+  int plane_boxes;       // 128-row TMA boxes per plane: ceil((256 + halo) / 128) <= 3
+  int total_pos;         // N * Hv * Wv
+  int dbg;               // tuning experiments: bit 0 = no global stores, bit 1 = no epilogue body at all
+  unsigned wait_hint;
+};
+constexpr int kShTileM = 256;
+constexpr int kShPlaneRows = 384, kShPlaneBytes = kShPlaneRows * 128, kShPlanes = 3;
+constexpr int kShBStagesMax = 8;
+constexpr int kShEpiWarps = 8, kShMmaWarp = 8, kShPlaneWarp = 9 /* warp 10: filter producer */, kShThreads = 352;
+constexpr int kShStagingBytes = kShEpiWarps * 32 * 32 * 4;   // one 32 x 32 transpose block per epilogue warp
+constexpr int kShSmemMax = 232448;   // 227 KB opt-in limit
+constexpr int kShSmemFixed = kShPlanes * kShPlaneBytes + kShStagingBytes + 1024 + 256;
+
+// k-steps (8 channels of one tap) run chunk-major, then tap, then 8-channel group, skipping the groups of the last chunk
+// that lie wholly past the real channels (nk_last of 4 remain).  A filter stage (bn x 32 floats) holds one tap of a full
+// chunk, or 4 / nk_last taps of the last one, so its 128 B rows may mix taps (AlexNet conv1 view: 48 channels =
+// 9 stages of 4 steps + 5 stages of 2 x 2 steps, not 18 stages).
+__global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __grid_constant__ ShiftParams p,
+                                                                        const __grid_constant__ CUtensorMap tmap_x,
+                                                                        const __grid_constant__ CUtensorMap tmap_w) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
+  const uint32_t plane0 = smem_u32(smem), bring0 = plane0 + kShPlanes * kShPlaneBytes;
+  float* staging = reinterpret_cast<float*>(smem + kShPlanes * kShPlaneBytes + p.b_stages * b_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kShPlanes * kShPlaneBytes + p.b_stages * b_bytes + kShStagingBytes);
+  const uint32_t pfull0 = smem_u32(bars), pempty0 = smem_u32(bars + 3), bfull0 = smem_u32(bars + 6), bempty0 = smem_u32(bars + 6 + kShBStagesMax);
+  const uint32_t tfull0 = smem_u32(bars + 6 + 2 * kShBStagesMax), tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kShBStagesMax);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tps_last = 4 / p.nk_last;   // taps per filter stage in the last channel chunk
+  const int nstages = (p.cpt - 1) * p.taps + (p.taps + tps_last - 1) / tps_last;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kShPlanes; ++i) { mbar_init(pfull0 + 8 * i, 1); mbar_init(pempty0 + 8 * i, 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, kShEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == kShMmaWarp) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kShEpiWarps) {
+    // ===================== epilogue: TMEM (lane = filter, column = position) -> 32 x 32 transpose in shared memory
+    // -> (+bias, relu) -> out, lane = position =====================
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int P = p.Ho * p.Wo, HWv = p.Hv * p.Wv;
+    const int nco = min(32, p.Co - quarter * 32);        // <= 0: this warp's TMEM lanes hold no real filter
+    float* blk = staging + warp * 1024;
+    // bias and ReLU are applied on the TMEM side, where a thread is one filter: one scalar per thread for the whole kernel
+    const float bias = (p.bias && lane < nco) ? __ldg(p.bias + quarter * 32 + lane) : 0.f;
+    const bool relu = p.relu != 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      mbar_wait(tfull0 + 8 * acc, acc_phase, p.wait_hint);
+      tc_fence_after();
+      if (nco > 0 && !(p.dbg & 2)) {
+        for (int cb = 0; cb < 4; ++cb) {
+          const int col0 = chalf * 128 + cb * 32;
+          uint32_t r0[16], r1[16];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256 + col0);
+          tmem_ld16(taddr, r0);
+          tmem_ld16(taddr + 16, r1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {   // element (filter = lane, position = j) at lane * 32 + (j ^ lane): conflict-free both ways
+            const float v0 = __uint_as_float(r0[j]) + bias, v1 = __uint_as_float(r1[j]) + bias;
+            blk[lane * 32 + (j ^ lane)] = (relu && !(v0 > 0.f)) ? 0.f : v0;
+            blk[lane * 32 + ((j + 16) ^ lane)] = (relu && !(v1 > 0.f)) ? 0.f : v1;
+          }
+          __syncwarp();
+          const int pos = tile * kShTileM + col0 + lane;
+          const int n = pos / HWv, rem = pos - n * HWv, Y = rem / p.Wv, X = rem - Y * p.Wv;
+          const bool ok = pos < p.total_pos && Y < p.Ho && X < p.Wo;
+          if (ok && !(p.dbg & 1)) {
+            float* dst = p.out + (static_cast<size_t>(n) * p.Co + quarter * 32) * P + Y * p.Wo + X;
+#pragma unroll 8
+            for (int l = 0; l < nco; ++l) dst[static_cast<size_t>(l) * P] = blk[l * 32 + (lane ^ l)];
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == kShMmaWarp) {
+    // ===================== MMA issuer: one thread; descriptor high words are constants, low words = address >> 4 ======
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kShTileM);
+      const uint32_t desc_hi = static_cast<uint32_t>(make_sw128_desc(0) >> 32);
+      const uint32_t w_lo0 = (bring0 & 0x3FFFFu) >> 4, w_step = b_bytes >> 4;
+      const uint32_t p_lo0 = (plane0 & 0x3FFFFu) >> 4, row_step = static_cast<uint32_t>(p.Wv) * 8u;
+      const int cpt = p.cpt, taps = p.taps, fwv = p.fwv, nk_last = p.nk_last, nbs = p.b_stages;
+      int ps = 0, bs = 0, acc = 0; uint32_t pph = 0, bph = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, p.wait_hint);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 256;
+        uint32_t accum = 0;
+        for (int chunk = 0; chunk < cpt; ++chunk) {
+          const int nk = chunk + 1 == cpt ? nk_last : 4, tps = 4 / nk;   // taps per filter stage
+          mbar_wait(pfull0 + 8 * ps, pph, p.wait_hint);
+          tc_fence_after();
+          uint32_t row_lo = p_lo0 + ps * (kShPlaneBytes >> 4), x_lo = row_lo;
+          int b = 0;
+          for (int tap = 0; tap < taps;) {
+            mbar_wait(bfull0 + 8 * bs, bph, p.wait_hint);
+            tc_fence_after();
+            uint32_t w_lo = w_lo0 + bs * w_step;
+            for (int g = 0; g < tps && tap < taps; ++g, ++tap) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < nk) {   // A = filters (rows past bn read the next stage's bytes: those accumulator lanes are never drained)
+                  umma_tf32_lohi(d0, w_lo, x_lo + kk * 2, desc_hi, idesc, accum);
+                  accum = 1;
+                  w_lo += 2;
+                }
+              }
+              x_lo += 8u;
+              if (++b == fwv) { b = 0; row_lo += row_step; x_lo = row_lo; }
+            }
+            umma_commit(bempty0 + 8 * bs);
+            if (++bs == nbs) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(pempty0 + 8 * ps);
+          if (++ps == kShPlanes) { ps = 0; pph ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kShPlaneWarp) {
+    // ===================== plane producer: (256 + halo) rows x 32 channels per (tile, chunk) =====================
+    if (lane == 0) {
+      int ps = 0; uint32_t pph = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < p.cpt; ++chunk) {
+          mbar_wait(pempty0 + 8 * ps, pph ^ 1, p.wait_hint);
+          mbar_arrive_expect_tx(pfull0 + 8 * ps, static_cast<uint32_t>(p.plane_boxes) * 128u * 128u);
+          for (int j = 0; j < p.plane_boxes; ++j)   // rows past the tensor arrive as zeros
+            tma_load_2d(plane0 + ps * kShPlaneBytes + j * 128 * 128, &tmap_x, pfull0 + 8 * ps, chunk * BK, tile * kShTileM + j * 128);
+          if (++ps == kShPlanes) { ps = 0; pph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== filter producer: one bn x 32 stage per four k-steps =====================
+    if (lane == 0) {
+      int bs = 0; uint32_t bph = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < nstages; ++ks) {
+          mbar_wait(bempty0 + 8 * bs, bph ^ 1, p.wait_hint);
+          mbar_arrive_expect_tx(bfull0 + 8 * bs, b_bytes);
+          tma_load_2d(bring0 + bs * b_bytes, &tmap_w, bfull0 + 8 * bs, ks * BK, 0);
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kShMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static std::atomic<int> g_opt_wait_hint{100};  // mbarrier.try_wait suspend hint in ns (tuning)
@@ -1118,6 +1326,9 @@ static std::atomic<int> g_opt_no_tall{0};    // 1: never use the 256-row tile (t
 static std::atomic<int> g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
 static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
 static std::atomic<int> g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
+static std::atomic<int> g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
+static std::atomic<int> g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
+static std::atomic<int> g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1276,59 +1487,100 @@ static bool s2d_plan(S2D* v, int Ci, int H, int W, int Ho, int Wo, int ph, int p
   if (Ci >= BK || v->Civ > 1024) return false;                            // enough channels already: the direct map is better
   const int cpt = (v->Civ + BK - 1) / BK;
   if (cpt * BK * 2 > v->Civ * 3) return false;                            // same padding rule as conv_tma_fprop
-  if (static_cast<size_t>(Ci) * sv * (static_cast<size_t>(v->Wv) * sh + 1) * sizeof(float) > 48 * 1024) return false;   // staging rows
+  if (static_cast<size_t>(Ci) * sv * (static_cast<size_t>(v->Wv) * sh + 8) * sizeof(float) > 48 * 1024) return false;   // staging rows
   return true;
 }
-// One CTA per (image, virtual row Y): the Ci*sv source rows are staged in shared memory (coalesced reads along x),
-// then the Wv * Cp output floats of the row are written in order (coalesced), channels Civ..Cp-1 zero.
-__global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const S2D v, int Cp) {
-  extern __shared__ float rows[];
-  const int L = v.Wv * v.sh, pitch = L + 1, R = v.Ci * v.sv;
-  const int Y = blockIdx.x % v.Hv;
-  const size_t n = blockIdx.x / v.Hv;
+// One CTA per (image, group of R virtual rows): the R * Ci*sv source rows are staged in shared memory (coalesced reads
+// along x, all loads of the group in flight before the barrier), then the R * Wv * Cp output floats are written in
+// order (coalesced), channels Civ..Cp-1 zero.  VEC4 (sh == 4, Civ % 4 == 0): one 16-byte store = 4 consecutive x of
+// one staged row.
+__host__ __device__ inline int s2d_pitch(const S2D& v) { return (v.Wv * v.sh + 3) / 4 * 4 + 4; }
+template <bool VEC4>
+__global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const S2D v, int Cp, int R, int groups) {
+  extern __shared__ float4 rows4[];
+  float* rows = reinterpret_cast<float*>(rows4);
+  const int L = v.Wv * v.sh, pitch = s2d_pitch(v), SR = v.Ci * v.sv;
+  const int g = blockIdx.x % groups, Y0 = g * R, Rc = min(R, v.Hv - Y0);
+  const size_t n = blockIdx.x / groups;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int r = wid; r < R; r += 8) {
-    const int c = r / v.sv, yy = Y * v.sv + (r - c * v.sv) - v.ph;
+  for (int rr = wid; rr < Rc * SR; rr += 8) {
+    const int yl = rr / SR, r = rr - yl * SR, c = r / v.sv, yy = (Y0 + yl) * v.sv + (r - c * v.sv) - v.ph;
     const bool row_ok = yy >= 0 && yy < v.H;
     const float* src = x + ((n * v.Ci + c) * v.H + (row_ok ? yy : 0)) * v.W;
+#pragma unroll 4
     for (int i = lane; i < L; i += 32) {
       const int xx = i - v.pw;
-      rows[r * pitch + i] = (row_ok && xx >= 0 && xx < v.W) ? __ldg(src + xx) : 0.f;
+      rows[rr * pitch + i] = (row_ok && xx >= 0 && xx < v.W) ? __ldg(src + xx) : 0.f;
     }
   }
   __syncthreads();
-  float* dst = y + (n * v.Hv + Y) * static_cast<size_t>(v.Wv) * Cp;
-  const int total = v.Wv * Cp;
-  for (int o = threadIdx.x; o < total; o += 256) {
-    const int X = o / Cp, ch = o - X * Cp, r = ch / v.sh;
-    dst[o] = ch < v.Civ ? rows[r * pitch + X * v.sh + (ch - r * v.sh)] : 0.f;
+  float* dst = y + (n * v.Hv + Y0) * static_cast<size_t>(v.Wv) * Cp;
+  if (VEC4) {
+    const int Cq = Cp >> 2, per_row = v.Wv * Cq, total = Rc * per_row;
+    for (int o = threadIdx.x; o < total; o += 256) {
+      const int yl = o / per_row, rem = o - yl * per_row, X = rem / Cq, q = rem - X * Cq;   // q = staged row (sh == 4)
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * q < v.Civ) val = *reinterpret_cast<const float4*>(rows + (yl * SR + q) * pitch + X * 4);
+      reinterpret_cast<float4*>(dst)[o] = val;
+    }
+  } else {
+    const int per_row = v.Wv * Cp, total = Rc * per_row;
+    for (int o = threadIdx.x; o < total; o += 256) {
+      const int yl = o / per_row, rem = o - yl * per_row, X = rem / Cp, ch = rem - X * Cp, r = ch / v.sh;
+      dst[o] = ch < v.Civ ? rows[(yl * SR + r) * pitch + X * v.sh + (ch - r * v.sh)] : 0.f;
+    }
   }
 }
-// B operand of the view: out[n][(a,b)][ch] (ch < Kc, zero past Civ and past the real filter)
-//   = w[n*sn + c*sc + (flip ? ff-1-t : t)], t = (a*sv + dy) * fw + b*sh + dx, ch = (c*sv + dy)*sh + dx.
+// B operand of the view, out[n][k] with row length Kp floats, zero past Civ and past the real filter:
+//   shift == 0 (im2col-fed kernel): k = (tap * cpt + chunk) * 32 + j, channel ch = chunk * 32 + j;
+//   shift != 0 (shift-GEMM kernel): k = stage * 32 + slot * 8 + j in the kernel's stage order -- a stage is one tap of a
+//              full channel chunk (slot = 8-channel group kk), or 4 / nk_last taps of the last chunk (slot = t * nk_last + kk);
+//              ch = chunk * 32 + kk * 8 + j.
+//   value = w[n*sn + c*sc + (flip ? ff-1-t : t)], t = (a*sv + dy) * fw + b*sh + dx, ch = (c*sv + dy)*sh + dx.
 __global__ void __launch_bounds__(kBlock) s2d_filter_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, const S2D v,
-                                                                 int Kc, long long sn, long long sc, int flip, int round) {
+                                                                 int cpt, int shift, int nk_last, int Kp, long long sn, long long sc, int flip,
+                                                                 int round) {
   const int ffv = v.fhv * v.fwv, ff = v.fh * v.fw;
-  size_t total = static_cast<size_t>(rows) * ffv * Kc;
+  size_t total = static_cast<size_t>(rows) * Kp;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(t % Kc);
-    size_t rest = t / Kc;
-    const int tap = static_cast<int>(rest % ffv);
-    const size_t n = rest / ffv;
-    const int a = tap / v.fwv, b = tap - a * v.fwv, r = ch / v.sh, c = r / v.sv;
-    const int kh = a * v.sv + (r - c * v.sv), kw = b * v.sh + (ch - r * v.sh);
+    const int k = static_cast<int>(t % Kp);
+    const size_t n = t / Kp;
+    int tap, ch;
+    bool live = true;
+    if (!shift) {
+      const int ks = k / BK, chunk = ks % cpt;
+      tap = ks / cpt; ch = chunk * BK + k % BK;
+    } else {
+      const int stage = k / BK, slot = (k % BK) >> 3, full = (cpt - 1) * ffv;
+      if (stage < full) {
+        tap = stage % ffv; ch = (stage / ffv) * BK + slot * 8 + (k & 7);
+      } else {
+        const int tps = 4 / nk_last, tin = slot / nk_last;
+        tap = (stage - full) * tps + tin; ch = (cpt - 1) * BK + (slot - tin * nk_last) * 8 + (k & 7);
+        live = tin < tps && tap < ffv;
+      }
+    }
     float val = 0.f;
-    if (ch < v.Civ && kh < v.fh && kw < v.fw) {
-      const int tr = kh * v.fw + kw;
-      val = __ldg(w + n * sn + static_cast<size_t>(c) * sc + (flip ? ff - 1 - tr : tr));
+    if (live) {
+      const int a = tap / v.fwv, b = tap - a * v.fwv, r = ch / v.sh, c = r / v.sv;
+      const int kh = a * v.sv + (r - c * v.sv), kw = b * v.sh + (ch - r * v.sh);
+      if (ch < v.Civ && kh < v.fh && kw < v.fw) {
+        const int tr = kh * v.fw + kw;
+        val = __ldg(w + n * sn + static_cast<size_t>(c) * sc + (flip ? ff - 1 - tr : tr));
+      }
     }
     out[t] = round ? to_tf32(val) : val;
   }
 }
 static int launch_s2d(const float* x, float* y, int N, const S2D& v, int Cp, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(v.Ci) * v.sv * (static_cast<size_t>(v.Wv) * v.sh + 1) * sizeof(float);
-  s2d_nhwc_kernel<<<static_cast<unsigned>(N) * v.Hv, 256, smem, s>>>(x, y, v, Cp);
+  const size_t row_bytes = static_cast<size_t>(v.Ci) * v.sv * s2d_pitch(v) * sizeof(float);
+  int R = static_cast<int>(48 * 1024 / row_bytes);
+  R = R > 4 ? 4 : R < 1 ? 1 : R;
+  const int groups = (v.Hv + R - 1) / R;
+  const unsigned grid = static_cast<unsigned>(N) * groups;
+  if (v.sh == 4 && v.Civ % 4 == 0 && aligned16(y)) s2d_nhwc_kernel<true><<<grid, 256, R * row_bytes, s>>>(x, y, v, Cp, R, groups);
+  else s2d_nhwc_kernel<false><<<grid, 256, R * row_bytes, s>>>(x, y, v, Cp, R, groups);
   return finish_launch();
 }
 
@@ -1616,12 +1868,63 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
   int rc = s2d ? launch_s2d(x, xh, N, *s2d, Cp, s) : launch_nhwc(x, xh, N, Ci, Cp, H * W, s);
   if (rc) return rc;
-  if (s2d) s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, *s2d, cpt * BK, w_sn, w_sc, flip, prepass_round());
+  if (s2d) s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, *s2d, cpt, 0, 4, static_cast<int>(K), w_sn, w_sc, flip, prepass_round());
   else filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
   rc = finish_launch();
   if (rc) return rc;
   *done = true;
   return launch_umma_tma(p, tm_a, tm_b, s);
+}
+
+// Strided few-channel convolution through its space-to-depth view on the shift-GEMM kernel (see conv_shift_fwd_kernel).
+// *done stays false when the geometry does not fit (more than 128 filters, halo above 128 rows, no workspace).
+static int conv_shift_fprop(const float* x, const float* w, long long w_sn, long long w_sc, int flip, const float* bias, int relu, float* out,
+                            int N, int Co, int Ho, int Wo, const S2D& v, void* ws, size_t ws_bytes, cudaStream_t s, bool* done) {
+  *done = false;
+  if (g_opt_no_shift.load() || g_opt_simt.load() || g_opt_no_tma.load() || !ws || !get_encode_fn()) return MNV_OK;
+  const int halo = (v.fhv - 1) * v.Wv + v.fwv - 1, taps = v.fhv * v.fwv;
+  const int cpt = (v.Civ + BK - 1) / BK, Cp = (v.Civ + 3) / 4 * 4, bn = (Co + 15) / 16 * 16;
+  if (bn > 128 || halo > kShPlaneRows - kShTileM) return MNV_OK;
+  const long long total_pos = static_cast<long long>(N) * v.Hv * v.Wv;
+  if (total_pos * Cp >= 0x7fffffffLL) return MNV_OK;
+  const size_t x_bytes = round256(static_cast<size_t>(total_pos) * Cp * sizeof(float));
+  const int nk_last = (v.Civ - (cpt - 1) * BK + 7) / 8, tps_last = 4 / nk_last;
+  const int K = ((cpt - 1) * taps + (taps + tps_last - 1) / tps_last) * BK;   // filter stages x 32
+  const size_t b_bytes = round256(static_cast<size_t>(Co) * K * sizeof(float));
+  if (ws_bytes < x_bytes + b_bytes) return MNV_OK;
+  float* xv = static_cast<float*>(ws);
+  float* wb = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + x_bytes);
+  ShiftParams p;
+  p.bias = bias; p.out = out; p.Co = Co; p.bn = bn; p.Ho = Ho; p.Wo = Wo; p.Hv = v.Hv; p.Wv = v.Wv; p.fwv = v.fwv; p.taps = taps;
+  p.cpt = cpt; p.relu = relu; p.total_pos = static_cast<int>(total_pos); p.nk_last = nk_last;
+  p.b_stages = (kShSmemMax - kShSmemFixed) / (bn * 128);
+  if (p.b_stages > kShBStagesMax) p.b_stages = kShBStagesMax;
+  const int smem_bytes = kShSmemFixed + p.b_stages * bn * 128;
+  p.m_tiles = static_cast<int>((total_pos + kShTileM - 1) / kShTileM);
+  p.plane_boxes = (kShTileM + halo + 127) / 128;
+  p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.dbg = g_opt_shift_dbg.load();
+  CUtensorMap tm_x, tm_w;
+  memset(&tm_x, 0, sizeof(tm_x));
+  memset(&tm_w, 0, sizeof(tm_w));
+  if (!make_b_tmap(&tm_x, xv, p.total_pos, Cp, Cp, 128) || !make_b_tmap(&tm_w, wb, Co, K, K, bn)) return MNV_OK;
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(conv_shift_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kShSmemMax);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  int rc = launch_s2d(x, xv, N, v, Cp, s);
+  if (rc) return rc;
+  s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, v, cpt, 1, nk_last, K, w_sn, w_sc, flip, prepass_round());
+  rc = finish_launch();
+  if (rc) return rc;
+  *done = true;
+  const int sms = sm_budget();
+  conv_shift_fwd_kernel<<<p.m_tiles < sms ? p.m_tiles : sms, kShThreads, smem_bytes, s>>>(p, tm_x, tm_w);
+  return finish_launch();
 }
 
 }  // namespace mnv
@@ -1650,6 +1953,9 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_klane") return g_opt_no_klane.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
   if (k == "no_s2d") return g_opt_no_s2d.exchange(value);
+  if (k == "no_shift") return g_opt_no_shift.exchange(value);
+  if (k == "shift_dbg") return g_opt_shift_dbg.exchange(value);
+  if (k == "s2d_im2col") return g_opt_s2d_im2col.exchange(value);
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   return -1;
@@ -1757,6 +2063,11 @@ static int conv_forward_impl(const float* bottom, const float* filter, const flo
     const int Ho = (H + 2 * ph - fh) / sv + 1, Wo = (W + 2 * pw - fw) / sh + 1;
     if (!g_opt_no_s2d.load() && s2d_plan(&v, Ci, H, W, Ho, Wo, ph, pw, sv, sh, fh, fw)) {
       bool done = false;
+      rc = conv_shift_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, relu, top, N, Co, Ho, Wo, v, workspace,
+                            workspace_bytes, as_stream(stream), &done);
+      if (rc || done) return rc;
+      // the view on the im2col-fed kernel is slower than the gather kernel on AlexNet conv1 (0.48 vs 0.42 ms): experiments only
+      if (g_opt_s2d_im2col.load())
       rc = conv_tma_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, relu, top, N, v.Civ, Co, v.Hv, v.Wv,
                           Ho, Wo, 0, 0, 1, 1, v.fhv, v.fwv, workspace, workspace_bytes, as_stream(stream), &done, &v);
       if (rc || done) return rc;
@@ -1875,7 +2186,7 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
   p.K = static_cast<int>(kpad);          // k-stages = N * spi; validity is per-pixel inside the gathers
   {  // strided few-channel convolutions: the same all-TMA kernel over the stride-1 space-to-depth view
     S2D v;
-    if (!(g_opt_no_tma_a.load() & 4) && !g_opt_no_s2d.load() && get_im2col_fn() && s2d_plan(&v, Ci, H, W, p.Ho, p.Wo, ph, pw, sv, sh, fh, fw)) {
+    if (!(g_opt_no_tma_a.load() & 4) && !g_opt_no_s2d.load() && g_opt_s2d_im2col.load() && get_im2col_fn() && s2d_plan(&v, Ci, H, W, p.Ho, p.Wo, ph, pw, sv, sh, fh, fw)) {
       const int cpt = (v.Civ + BK - 1) / BK, Cp = (v.Civ + 3) / 4 * 4;
       const size_t x_bytes = round256(static_cast<size_t>(N) * v.Hv * v.Wv * Cp * sizeof(float));
       if (ws_left >= x_bytes && fits_int(static_cast<long long>(N) * v.Hv * v.Wv * Cp)) {

@@ -185,6 +185,37 @@ def test_conv_operand_paths(g, case):
         assert g.norm_rel(dw, wdw) < TOL, name + ": backward filter"
 
 
+S2D_CASES = [CONV_CASES[4], CONV_CASES[8]] + CONV_CASES[13:] + [
+    (3, 3, 96, 59, 63, 0, 0, 4, 4, 11, 11),    # several 256-position tiles per image, tiles straddling images
+    (2, 3, 128, 40, 40, 1, 2, 4, 4, 9, 10),    # 128 filters (the kernel's widest tile), pad, filter not a stride multiple
+]
+
+
+@pytest.mark.parametrize("case", S2D_CASES)
+def test_conv_space_to_depth_paths(g, case):
+    """Strided few-channel convolutions: shift-GEMM kernel (default), the view on the im2col-fed kernel, and the gathers."""
+    N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = case
+    Ho, Wo = orc.conv_out(H, ph, fh, sv), orc.conv_out(W, pw, fw, sh)
+    x = rng.normal(0, 1, N * Ci * H * W).astype(np.float32)
+    w = rng.normal(0, 1, Co * Ci * fh * fw).astype(np.float32)
+    b = rng.normal(0, 1, Co).astype(np.float32)
+    dy = rng.normal(0, 1, N * Co * Ho * Wo).astype(np.float32)
+    geo = (N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw)
+    wy = orc.conv_forward(x, w, b, *geo)
+    wdw = orc.conv_backward_filter(x, dy, *geo)
+    defaults = {"no_shift": 0, "s2d_im2col": 0, "no_s2d": 0}
+    for name, opts in (("shift", {}), ("view on im2col kernel", {"no_shift": 1, "s2d_im2col": 1}), ("gather", {"no_s2d": 1})):
+        try:
+            for k, v in {**defaults, **opts}.items():
+                _set(k, v)
+            y, _, dw = _conv_all(g, case, x, w, b, dy)
+        finally:
+            for k, v in defaults.items():
+                _set(k, v)
+        assert g.norm_rel(y, wy) < TOL, name + ": forward"
+        assert g.norm_rel(dw, wdw) < TOL, name + ": backward filter"
+
+
 @pytest.mark.parametrize("case", [CONV_CASES[1], CONV_CASES[4], CONV_CASES[8], CONV_CASES[10], TMA_CASES[1], TMA_CASES[5], TMA_CASES[6]])
 def test_conv_forward_relu_fused(g, case):
     """mnv_conv_forward_relu == mnv_relu_forward(mnv_conv_forward), bit for bit, on every operand path (incl. split-K

@@ -18,9 +18,17 @@ ap.add_argument("--out", default="gpurun_out/opbench.json")
 ap.add_argument("--filter", default="")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--mnv-opt", action="append", default=[], metavar="KEY=INT", help="mnv_debug_set_option before timing (tuning)")
 args = ap.parse_args()
 
 lib = _lib.load()
+if args.mnv_opt:
+    import ctypes
+    lib.mnv_debug_set_option.restype = ctypes.c_int
+    lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    for kv in args.mnv_opt:
+        k, v = kv.split("=")
+        lib.mnv_debug_set_option(k.encode(), int(v))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
 try:
