@@ -1186,7 +1186,7 @@ __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __g
     const int quarter = warp & 3, chalf = warp >> 2;
     const int P = p.Ho * p.Wo, HWv = p.Hv * p.Wv;
     const int nco = min(32, p.Co - quarter * 32);        // <= 0: this warp's TMEM lanes hold no real filter
-    float* blk = staging + warp * 1024;
+    const uint32_t blk = smem_u32(staging) + warp * 4096;   // explicit shared-space accesses: a generic pointer here compiles to LD.E / ST.E
     // bias and ReLU are applied on the TMEM side, where a thread is one filter: one scalar per thread for the whole kernel
     const float bias = (p.bias && lane < nco) ? __ldg(p.bias + quarter * 32 + lane) : 0.f;
     const bool relu = p.relu != 0;
@@ -1204,8 +1204,8 @@ __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 16; ++j) {   // element (filter = lane, position = j) at lane * 32 + (j ^ lane): conflict-free both ways
             const float v0 = __uint_as_float(r0[j]) + bias, v1 = __uint_as_float(r1[j]) + bias;
-            blk[lane * 32 + (j ^ lane)] = (relu && !(v0 > 0.f)) ? 0.f : v0;
-            blk[lane * 32 + ((j + 16) ^ lane)] = (relu && !(v1 > 0.f)) ? 0.f : v1;
+            st_shared_f32(blk + 4 * (lane * 32 + (j ^ lane)), (relu && !(v0 > 0.f)) ? 0.f : v0);
+            st_shared_f32(blk + 4 * (lane * 32 + ((j + 16) ^ lane)), (relu && !(v1 > 0.f)) ? 0.f : v1);
           }
           __syncwarp();
           const int pos = tile * kShTileM + col0 + lane;
@@ -1214,7 +1214,7 @@ __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __g
           if (ok && !(p.dbg & 1)) {
             float* dst = p.out + (static_cast<size_t>(n) * p.Co + quarter * 32) * P + Y * p.Wo + X;
 #pragma unroll 8
-            for (int l = 0; l < nco; ++l) dst[static_cast<size_t>(l) * P] = blk[l * 32 + (lane ^ l)];
+            for (int l = 0; l < nco; ++l) dst[static_cast<size_t>(l) * P] = __uint_as_float(ld_shared_u32(blk + 4 * (l * 32 + (lane ^ l))));
           }
           __syncwarp();
         }
@@ -1507,21 +1507,29 @@ __global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__
     const int yl = rr / SR, r = rr - yl * SR, c = r / v.sv, yy = (Y0 + yl) * v.sv + (r - c * v.sv) - v.ph;
     const bool row_ok = yy >= 0 && yy < v.H;
     const float* src = x + ((n * v.Ci + c) * v.H + (row_ok ? yy : 0)) * v.W;
-#pragma unroll 4
+    // 4-byte cp.async with zero fill: nothing waits on a register, so every load of the group is in flight at once
+    // (an LDG loop whose trip count is not a compile-time constant runs its tail one load at a time)
+    const uint32_t dst_row = smem_u32(rows + rr * pitch);
     for (int i = lane; i < L; i += 32) {
       const int xx = i - v.pw;
-      rows[rr * pitch + i] = (row_ok && xx >= 0 && xx < v.W) ? __ldg(src + xx) : 0.f;
+      const bool ok = row_ok && xx >= 0 && xx < v.W;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_row + 4 * i), "l"(src + (ok ? xx : 0)), "r"(ok ? 4 : 0) : "memory");
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   float* dst = y + (n * v.Hv + Y0) * static_cast<size_t>(v.Wv) * Cp;
-  if (VEC4) {
-    const int Cq = Cp >> 2, per_row = v.Wv * Cq, total = Rc * per_row;
-    for (int o = threadIdx.x; o < total; o += 256) {
-      const int yl = o / per_row, rem = o - yl * per_row, X = rem / Cq, q = rem - X * Cq;   // q = staged row (sh == 4)
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (4 * q < v.Civ) val = *reinterpret_cast<const float4*>(rows + (yl * SR + q) * pitch + X * 4);
-      reinterpret_cast<float4*>(dst)[o] = val;
+  if (VEC4) {   // Cq consecutive threads write one pixel's Cp floats; no division inside the loops
+    const int Cq = Cp >> 2, ppi = 256 / Cq, q = threadIdx.x % Cq, p0 = threadIdx.x / Cq;
+    if (p0 < ppi) {
+      const bool live = 4 * q < v.Civ;
+      float4* dst4 = reinterpret_cast<float4*>(dst);
+      for (int yl = 0; yl < Rc; ++yl) {
+        const float* src = rows + (yl * SR + q) * pitch;   // q = staged row (sh == 4)
+#pragma unroll 4
+        for (int X = p0; X < v.Wv; X += ppi)
+          dst4[(yl * v.Wv + X) * Cq + q] = live ? *reinterpret_cast<const float4*>(src + X * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   } else {
     const int per_row = v.Wv * Cp, total = Rc * per_row;

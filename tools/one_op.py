@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Launch one op a few times (for `ncu -k regex:... -s N -c M`).  Usage: one_op.py <name> [iters]
+"""Launch one op a few times (for `ncu -k regex:... -s N -c M`).  Usage: one_op.py <name> [iters [KEY=INT ...]]
 names: conv{1..5}_{fwd,bwd,wgrad}, fc6_fwd, gemm8k, pool1_fwd, pool1_bwd, lrn1_fwd, lrn1_bwd, bias1"""
 import os
 import sys
@@ -12,6 +12,11 @@ from minerva_b200 import _lib
 lib = _lib.load()
 name = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+for kv in sys.argv[3:]:      # KEY=INT tuning / debug options (mnv_debug_set_option)
+    import ctypes
+    lib.mnv_debug_set_option.restype = ctypes.c_int
+    lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.mnv_debug_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1]))
 B = 256
 st = torch.cuda.current_stream().cuda_stream
 ws = torch.empty(lib.mnv_workspace_bytes_hint(), dtype=torch.uint8, device="cuda")
