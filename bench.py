@@ -138,10 +138,10 @@ class ClockSampler(threading.Thread):
 # algorithmic work of one C-ABI call for the roofline of the dominant kernel
 # ------------------------------------------------------------------------------------------------
 def gemm_flops(name, a):
-    if name == "mnv_matmult":
+    if name in ("mnv_matmult", "mnv_matmult_ex"):
         return 2.0 * a[3] * a[4] * a[5]
-    if name in ("mnv_conv_forward", "mnv_conv_backward_data", "mnv_conv_backward_filter"):
-        off = 4 if name == "mnv_conv_forward" else 3
+    if name in ("mnv_conv_forward", "mnv_conv_forward_relu", "mnv_conv_backward_data", "mnv_conv_backward_filter"):
+        off = 4 if name.startswith("mnv_conv_forward") else 3
         N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = a[off:off + 11]
         Ho, Wo = (H + 2 * ph - fh) // sv + 1, (W + 2 * pw - fw) // sh + 1
         return 2.0 * N * Ho * Wo * Co * Ci * fh * fw
@@ -372,7 +372,7 @@ def main():
         achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": achieved / tf32_peak, "traffic": ncu_traffic(args.workload),
-                    "kernel": "mnv::umma_gemm_kernel (tcgen05 TF32: MatMult + conv fwd/bwd-data/bwd-filter)",
+                    "kernel": "mnv::umma_gemm_kernel + mnv::conv_shift_fwd_kernel (tcgen05 TF32: MatMult + conv fwd/bwd-data/bwd-filter, pre-passes included)",
                     "launches_timed": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
                     "share_of_step": g_ms / total_ms if total_ms else None,
                     "peak_source": "%s bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate)" % pk["source"]}

@@ -244,6 +244,19 @@ int mnv_lrn_backward(const float* bottom_data, const float* top_data, const floa
                      const float* top_diff, float* bottom_diff, int local_size, float alpha,
                      float beta, int num_img, int channel, int width, int height,
                      mnv_stream_t stream);
+/* Extensions (fusion): the same backward passes followed by ReLU backward, for a bottom that is a ReLU
+ * output (mask = bottom > 0; both kernels read the bottom anyway) -- bit-identical to the unfused pair
+ * mnv_relu_backward(bottom, bottom, mnv_xxx_backward(...)).  owl.net uses them when a ReluUnit's only consumer is an
+ * LRNUnit / max PoolingUnit (owl/owl/net/net.py:281-296 runs the mask as its own 12 B/element pass). */
+int mnv_lrn_backward_relu(const float* bottom_data, const float* top_data, const float* scale,
+                          const float* top_diff, float* bottom_diff, int local_size, float alpha,
+                          float beta, int num_img, int channel, int width, int height,
+                          mnv_stream_t stream);
+int mnv_max_pooling_backward_relu(const float* bottom, const float* top, const float* top_diff,
+                                  float* bottom_diff, int num_images, int num_channels,
+                                  int bottom_height, int bottom_width, int stride_vertical,
+                                  int stride_horizontal, int window_height, int window_width,
+                                  int pad_height, int pad_width, mnv_stream_t stream);
 
 /* ---- fused momentum-SGD update (owl/net/net.py:252-256) ----------------
  * delta = mom*delta - (lr/batch)*grad - (lr*wd)*w ; w += delta    (20 B/param instead of the

@@ -226,6 +226,28 @@ __device__ __forceinline__ void stage_in(float* __restrict__ dst, const float* _
   if (static_cast<int>(threadIdx.x) < n - done) dst[done + threadIdx.x] = __ldg(src + done + threadIdx.x);
 }
 
+// The same copy with cp.async: nothing waits on a register, so every load of the group is in flight at once and the
+// copy of the NEXT plane group can overlap the arithmetic on the current one (callers double-buffer and close each
+// group with stage_commit(); stage_wait_prev() = all but the newest group have landed).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async_f32(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void stage_in_async(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  int head = (4 - misalign4(src)) & 3;
+  if (head > n) head = n;
+  if (static_cast<int>(threadIdx.x) < head) cp_async_f32(dst + threadIdx.x, src + threadIdx.x);
+  const int n4 = (n - head) >> 2;
+  const uint32_t d4 = smem_addr(dst + head);
+  const float* s4 = src + head;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d4 + 16u * i), "l"(s4 + 4 * i) : "memory");
+  const int done = head + (n4 << 2);
+  if (static_cast<int>(threadIdx.x) < n - done) cp_async_f32(dst + done + threadIdx.x, src + done + threadIdx.x);
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void stage_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <bool IS_MAX>
 __global__ void __launch_bounds__(kBlock) pool_fwd_smem_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, PoolGeom g,
                                                                 int G, FastDiv d_howo, FastDiv d_wo) {
@@ -368,12 +390,24 @@ __global__ void __launch_bounds__(kBlock) maxpool332_fwd_kernel(const float* __r
                                                                  int G, FastDiv d_howo, FastDiv d_wo) {
   extern __shared__ float sm[];
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo, W = g.W;
-  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
-    const int cnt = min(G, planes - p0);
+  const int buf = (G * HW + 4 + 3) & ~3, stride = gridDim.x * G;   // two staging buffers: group k+1 streams in under group k's maxima
+  int p0 = blockIdx.x * G, it = 0;
+  if (p0 < planes) {
     const float* xsrc = x + static_cast<size_t>(p0) * HW;
-    float* sx = sm + misalign4(xsrc);
-    stage_in(sx, xsrc, cnt * HW);
+    stage_in_async(sm + misalign4(xsrc), xsrc, min(G, planes - p0) * HW);
+  }
+  stage_commit();
+  for (; p0 < planes; p0 += stride, it ^= 1) {
+    const int cnt = min(G, planes - p0), nxt = p0 + stride;
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    if (nxt < planes) {
+      const float* nsrc = x + static_cast<size_t>(nxt) * HW;
+      stage_in_async(sm + (it ^ 1) * buf + misalign4(nsrc), nsrc, min(G, planes - nxt) * HW);
+    }
+    stage_commit();
+    stage_wait_prev();
     __syncthreads();
+    const float* sx = sm + it * buf + misalign4(xsrc);
     float* yp = y + static_cast<size_t>(p0) * HoWo;
     for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {
       int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * g.Wo;
@@ -390,7 +424,7 @@ __global__ void __launch_bounds__(kBlock) maxpool332_fwd_kernel(const float* __r
         }
       yp[o] = best;
     }
-    __syncthreads();
+    __syncthreads();   // this buffer is refilled by the next iteration's prefetch
   }
 }
 
@@ -400,22 +434,38 @@ __global__ void __launch_bounds__(kBlock) maxpool332_fwd_kernel(const float* __r
 template <bool CHECK>
 __global__ void __launch_bounds__(kBlock) maxpool332_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  float* __restrict__ dx, int planes, PoolGeom g, int G,
-                                                                 FastDiv d_howo, FastDiv d_wo, FastDiv d_blk, FastDiv d_bw) {
+                                                                 FastDiv d_howo, FastDiv d_wo, FastDiv d_blk, FastDiv d_bw, int relu) {
   extern __shared__ float sm[];
   const int H = g.H, W = g.W, HW = H * W, Ho = g.Ho, Wo = g.Wo, HoWo = Ho * Wo;
   const int BH = (H + 1) >> 1, BW = (W + 1) >> 1, BLK = BH * BW;   // 2x2 blocks per plane
-  float* sx_base = sm;
-  float* sdy_base = sm + ((G * HW + 4 + 3) & ~3);
-  int* sarg = reinterpret_cast<int*>(sdy_base + ((G * HoWo + 4 + 3) & ~3));
-  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
-    const int cnt = min(G, planes - p0);
+  // two (x, dy) staging buffers + one arg-max plane: group k+1 streams in under group k's two phases
+  const int xbuf = (G * HW + 4 + 3) & ~3, dbuf = (G * HoWo + 4 + 3) & ~3, buf = xbuf + dbuf, stride = gridDim.x * G;
+  int* sarg = reinterpret_cast<int*>(sm + 2 * buf);
+  int p0 = blockIdx.x * G, it = 0;
+  if (p0 < planes) {
     const float* xsrc = x + static_cast<size_t>(p0) * HW;
     const float* dysrc = dy + static_cast<size_t>(p0) * HoWo;
-    float* sx = sx_base + misalign4(xsrc);
-    float* sdy = sdy_base + misalign4(dysrc);
-    stage_in(sx, xsrc, cnt * HW);
-    stage_in(sdy, dysrc, cnt * HoWo);
+    const int cnt = min(G, planes - p0);
+    stage_in_async(sm + misalign4(xsrc), xsrc, cnt * HW);
+    stage_in_async(sm + xbuf + misalign4(dysrc), dysrc, cnt * HoWo);
+  }
+  stage_commit();
+  for (; p0 < planes; p0 += stride, it ^= 1) {
+    const int cnt = min(G, planes - p0), nxt = p0 + stride;
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    const float* dysrc = dy + static_cast<size_t>(p0) * HoWo;
+    if (nxt < planes) {
+      const float* nx = x + static_cast<size_t>(nxt) * HW;
+      const float* nd = dy + static_cast<size_t>(nxt) * HoWo;
+      const int ncnt = min(G, planes - nxt);
+      stage_in_async(sm + (it ^ 1) * buf + misalign4(nx), nx, ncnt * HW);
+      stage_in_async(sm + (it ^ 1) * buf + xbuf + misalign4(nd), nd, ncnt * HoWo);
+    }
+    stage_commit();
+    stage_wait_prev();
     __syncthreads();
+    const float* sx = sm + it * buf + misalign4(xsrc);
+    const float* sdy = sm + it * buf + xbuf + misalign4(dysrc);
     for (int o = threadIdx.x; o < cnt * HoWo; o += blockDim.x) {   // phase A: arg-max of every window
       int gq = fdiv(o, d_howo), r = o - gq * HoWo, i = fdiv(r, d_wo), j = r - i * Wo;
       const int base = (2 * i) * W + 2 * j;
@@ -449,25 +499,29 @@ __global__ void __launch_bounds__(kBlock) maxpool332_bwd_kernel(const float* __r
       if (id && jr) { a11 = ap[bi * Wo + bj]; d11 = dyp[bi * Wo + bj]; }
       const int h = 2 * bi, w = 2 * bj, r00 = h * W + w;
       float* out = dxp + gq * HW + r00;
+      const float* xin = sx + gq * HW + r00;   // relu: the pooled tensor is a ReLU output, x > 0 is the ReLU-backward mask
       // (h, w): in all four windows
       float acc = 0.f;
       if (a00 == r00) acc = __fadd_rn(acc, d00);
       if (a01 == r00) acc = __fadd_rn(acc, d01);
       if (a10 == r00) acc = __fadd_rn(acc, d10);
       if (a11 == r00) acc = __fadd_rn(acc, d11);
-      out[0] = acc;
+      out[0] = (relu && !(xin[0] > 0.f)) ? 0.f : acc;
       if (w + 1 < W) {   // (h, w+1): windows (bi-1, bj), (bi, bj)
         acc = 0.f;
         if (a01 == r00 + 1) acc = __fadd_rn(acc, d01);
         if (a11 == r00 + 1) acc = __fadd_rn(acc, d11);
-        out[1] = acc;
+        out[1] = (relu && !(xin[1] > 0.f)) ? 0.f : acc;
       }
       if (h + 1 < H) {   // (h+1, w): windows (bi, bj-1), (bi, bj)
         acc = 0.f;
         if (a10 == r00 + W) acc = __fadd_rn(acc, d10);
         if (a11 == r00 + W) acc = __fadd_rn(acc, d11);
-        out[W] = acc;
-        if (w + 1 < W) out[W + 1] = (a11 == r00 + W + 1) ? __fadd_rn(0.f, d11) : 0.f;   // (h+1, w+1): window (bi, bj)
+        out[W] = (relu && !(xin[W] > 0.f)) ? 0.f : acc;
+        if (w + 1 < W) {   // (h+1, w+1): window (bi, bj)
+          acc = (a11 == r00 + W + 1) ? __fadd_rn(0.f, d11) : 0.f;
+          out[W + 1] = (relu && !(xin[W + 1] > 0.f)) ? 0.f : acc;
+        }
       }
     }
     __syncthreads();
@@ -642,7 +696,7 @@ template <int SIZE, bool BETA075>
 __global__ void __launch_bounds__(kBlock) lrn_bwd_kernel(const float* __restrict__ bottom, const float* __restrict__ top,
                                                          const float* __restrict__ scale, const float* __restrict__ top_diff,
                                                          float* __restrict__ bottom_diff, int num, int C, size_t step, int size_rt,
-                                                         float neg_beta, float cache_ratio) {
+                                                         float neg_beta, float cache_ratio, int relu) {
   size_t total = static_cast<size_t>(num) * step;
   const int size = SIZE > 0 ? SIZE : size_rt;
   const int pre_pad = size - (size + 1) / 2, post_pad = size - pre_pad - 1;
@@ -689,8 +743,9 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd_kernel(const float* __restrict
             tdo = __ldg(td + o); sco = __ldg(s + o);
           }
           float lhs = __fmul_rn(tdo, pow_neg_beta<BETA075>(sco, neg_beta));
-          float rhs = __fmul_rn(__fmul_rn(cache_ratio, __ldg(b + o)), acc);
-          bd[o] = __fsub_rn(lhs, rhs);
+          const float bv = __ldg(b + o);
+          float rhs = __fmul_rn(__fmul_rn(cache_ratio, bv), acc);
+          bd[o] = (relu && !(bv > 0.f)) ? 0.f : __fsub_rn(lhs, rhs);   // relu: bottom is a ReLU output, mask = ReLU backward
         }
       }
     }
@@ -860,7 +915,7 @@ template <bool BETA075>
 __global__ void __launch_bounds__(kBlock) lrn_bwd5_kernel(const float* __restrict__ bottom, const float* __restrict__ top,
                                                           const float* __restrict__ scale, const float* __restrict__ top_diff,
                                                           float* __restrict__ bottom_diff, int num, int C, unsigned step,
-                                                          float neg_beta, float cache_ratio) {
+                                                          float neg_beta, float cache_ratio, int relu) {
   // 32-bit element offsets as in lrn_fwd5_kernel: `ld` runs 8 channels ahead of the head for top_diff / top / scale,
   // the bottom value of output channel head-2 is fetched at ld - 2*step, `st` is the output channel.
   const unsigned total = static_cast<unsigned>(num) * step;
@@ -907,7 +962,7 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd5_kernel(const float* __restric
         if (o >= 0 && o < C) {
           const float lhs = __fmul_rn(td2, pow_neg_beta_sfu<BETA075>(sc2, neg_beta));
           const float rhs = __fmul_rn(__fmul_rn(cache_ratio, cb[u]), acc);
-          bottom_diff[st] = __fsub_rn(lhs, rhs);
+          bottom_diff[st] = (relu && !(cb[u] > 0.f)) ? 0.f : __fsub_rn(lhs, rhs);   // relu: bottom is a ReLU output, mask = ReLU backward
           st += step;
         }
         td2 = td1; td1 = tdh; sc2 = sc1; sc1 = sch;
@@ -926,18 +981,19 @@ static int launch_pool_fwd(const float* x, float* y, size_t planes, const PoolGe
     size_t bytes = (per * G + 4) * sizeof(float);
     int rc = pool_smem_attr(pool_fwd_smem_kernel<IS_MAX>, bytes);
     if (rc) return rc;
-    if (IS_MAX && g.wh == 3 && g.ww == 3 && g.sv == 2 && g.sh == 2 && g.ph == 0 && g.pw == 0) {
+    const size_t bytes2 = 2 * ((per * G + 4 + 3) & ~static_cast<size_t>(3)) * sizeof(float);   // double-buffered staging
+    if (IS_MAX && g.wh == 3 && g.ww == 3 && g.sv == 2 && g.sh == 2 && g.ph == 0 && g.pw == 0 && bytes2 <= static_cast<size_t>(kPoolSmemMax)) {
       const bool fit = (g.Ho - 1) * 2 + 3 <= g.H && (g.Wo - 1) * 2 + 3 <= g.W;
       if (fit) {
-        rc = pool_smem_attr(maxpool332_fwd_kernel<false>, bytes);
+        rc = pool_smem_attr(maxpool332_fwd_kernel<false>, bytes2);
         if (rc) return rc;
-        maxpool332_fwd_kernel<false><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
-                                                                                  make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
+        maxpool332_fwd_kernel<false><<<pool_grid(planes, G), kBlock, bytes2, s>>>(x, y, static_cast<int>(planes), g, G,
+                                                                                   make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
       } else {
-        rc = pool_smem_attr(maxpool332_fwd_kernel<true>, bytes);
+        rc = pool_smem_attr(maxpool332_fwd_kernel<true>, bytes2);
         if (rc) return rc;
-        maxpool332_fwd_kernel<true><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
-                                                                                 make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
+        maxpool332_fwd_kernel<true><<<pool_grid(planes, G), kBlock, bytes2, s>>>(x, y, static_cast<int>(planes), g, G,
+                                                                                  make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
       }
       return finish_launch();
     }
@@ -1010,8 +1066,11 @@ int mnv_average_pooling_forward(const float* x, float* y, int N, int C, int H, i
   if (!x || !y) return MNV_EINVAL;
   return launch_pool_fwd<false>(x, y, planes, g, as_stream(s));
 }
-int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
-                             int W, int sv, int sh, int wh, int ww, int ph, int pw, mnv_stream_t s) {
+static int max_pooling_backward_impl(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
+                                     int W, int sv, int sh, int wh, int ww, int ph, int pw, mnv_stream_t s, bool* relu) {
+  // *relu in: apply the ReLU-backward mask (x > 0) to dx; out: whether the kernel that ran did (else the caller does)
+  const int want_relu = *relu ? 1 : 0;
+  *relu = false;
   PoolGeom g;
   int rc = make_geom(&g, N, C, H, W, sv, sh, wh, ww, ph, pw);
   if (rc) return rc;
@@ -1034,18 +1093,22 @@ int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, fl
     if (rc) return rc;                                                                                            \
     maxpool_bwd_smem_kernel<WH_, WW_, SV_, SH_><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f1, f2, f3, f4, f5, f6); \
   } while (0)
-      if (wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0) {
+      // double-buffered (x, dy) staging + one arg-max plane
+      const size_t HW_ = static_cast<size_t>(H) * W, HoWo_ = static_cast<size_t>(g.Ho) * g.Wo;
+      const size_t bytes2 = (2 * (((G * HW_ + 4 + 3) & ~static_cast<size_t>(3)) + ((G * HoWo_ + 4 + 3) & ~static_cast<size_t>(3))) + G * HoWo_) * sizeof(float);
+      if (wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0 && bytes2 <= static_cast<size_t>(kPoolSmemMax)) {
         const bool fit = (g.Ho - 1) * 2 + 3 <= H && (g.Wo - 1) * 2 + 3 <= W;
         const FastDiv fb = make_fastdiv(((H + 1) / 2) * ((W + 1) / 2)), fbw = make_fastdiv((W + 1) / 2);
         if (fit) {
-          rc = pool_smem_attr(maxpool332_bwd_kernel<false>, bytes);
+          rc = pool_smem_attr(maxpool332_bwd_kernel<false>, bytes2);
           if (rc) return rc;
-          maxpool332_bwd_kernel<false><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f3, f4, fb, fbw);
+          maxpool332_bwd_kernel<false><<<grid, kBlock, bytes2, st>>>(x, dy, dx, P, g, G, f3, f4, fb, fbw, want_relu);
         } else {
-          rc = pool_smem_attr(maxpool332_bwd_kernel<true>, bytes);
+          rc = pool_smem_attr(maxpool332_bwd_kernel<true>, bytes2);
           if (rc) return rc;
-          maxpool332_bwd_kernel<true><<<grid, kBlock, bytes, st>>>(x, dy, dx, P, g, G, f3, f4, fb, fbw);
+          maxpool332_bwd_kernel<true><<<grid, kBlock, bytes2, st>>>(x, dy, dx, P, g, G, f3, f4, fb, fbw, want_relu);
         }
+        *relu = want_relu != 0;
       }
       else if (wh == 3 && ww == 3 && sv == 2 && sh == 2) MNV_POOL_BWD(3, 3, 2, 2);
       else if (wh == 2 && ww == 2 && sv == 2 && sh == 2) MNV_POOL_BWD(2, 2, 2, 2);
@@ -1058,6 +1121,19 @@ int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, fl
   }
   maxpool_bwd_kernel<<<stream_grid(planes * H * W), kBlock, 0, as_stream(s)>>>(x, y, dy, dx, planes, g);
   return finish_launch();
+}
+int mnv_max_pooling_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
+                             int W, int sv, int sh, int wh, int ww, int ph, int pw, mnv_stream_t s) {
+  bool relu = false;
+  return max_pooling_backward_impl(x, y, dy, dx, N, C, H, W, sv, sh, wh, ww, ph, pw, s, &relu);
+}
+int mnv_max_pooling_backward_relu(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
+                                  int W, int sv, int sh, int wh, int ww, int ph, int pw, mnv_stream_t s) {
+  bool relu = true;
+  int rc = max_pooling_backward_impl(x, y, dy, dx, N, C, H, W, sv, sh, wh, ww, ph, pw, s, &relu);
+  if (rc || relu) return rc;
+  // geometries without a fused kernel: the mask as a second, in-place elementwise pass (thread i reads and writes element i only)
+  return mnv_relu_backward(x, x, dx, dx, N, C, H, W, s);
 }
 int mnv_average_pooling_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C,
                                  int H, int W, int sv, int sh, int wh, int ww, int ph, int pw, mnv_stream_t s) {
@@ -1142,9 +1218,9 @@ int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_siz
   }
   return finish_launch();
 }
-int mnv_lrn_backward(const float* bottom_data, const float* top_data, const float* scale, const float* top_diff,
-                     float* bottom_diff, int local_size, float alpha, float beta, int num_img, int channel,
-                     int width, int height, mnv_stream_t s) {
+static int lrn_backward_impl(const float* bottom_data, const float* top_data, const float* scale, const float* top_diff,
+                             float* bottom_diff, int local_size, float alpha, float beta, int num_img, int channel,
+                             int width, int height, mnv_stream_t s, int relu) {
   if (num_img < 0 || channel < 0 || width < 0 || height < 0 || local_size <= 0) return MNV_EINVAL;
   size_t step = static_cast<size_t>(width) * height, work = step * num_img;
   if (work == 0 || channel == 0) return MNV_OK;
@@ -1154,13 +1230,24 @@ int mnv_lrn_backward(const float* bottom_data, const float* top_data, const floa
   const int grid = stream_grid(work);
   if (local_size == 5 && channel >= 5 && (static_cast<unsigned long long>(channel) + 16) * work < (1ull << 31)) {
     const unsigned step32 = static_cast<unsigned>(step);
-    if (b075) lrn_bwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step32, -beta, cache_ratio);
-    else lrn_bwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step32, -beta, cache_ratio);
+    if (b075) lrn_bwd5_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step32, -beta, cache_ratio, relu);
+    else lrn_bwd5_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step32, -beta, cache_ratio, relu);
   } else {
-    if (b075) lrn_bwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
-    else lrn_bwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio);
+    if (b075) lrn_bwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio, relu);
+    else lrn_bwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_data, scale, top_diff, bottom_diff, num_img, channel, step, local_size, -beta, cache_ratio, relu);
   }
   return finish_launch();
+}
+
+int mnv_lrn_backward(const float* bottom_data, const float* top_data, const float* scale, const float* top_diff,
+                     float* bottom_diff, int local_size, float alpha, float beta, int num_img, int channel,
+                     int width, int height, mnv_stream_t s) {
+  return lrn_backward_impl(bottom_data, top_data, scale, top_diff, bottom_diff, local_size, alpha, beta, num_img, channel, width, height, s, 0);
+}
+int mnv_lrn_backward_relu(const float* bottom_data, const float* top_data, const float* scale, const float* top_diff,
+                          float* bottom_diff, int local_size, float alpha, float beta, int num_img, int channel,
+                          int width, int height, mnv_stream_t s) {
+  return lrn_backward_impl(bottom_data, top_data, scale, top_diff, bottom_diff, local_size, alpha, beta, num_img, channel, width, height, s, 1);
 }
 
 }  // extern "C"

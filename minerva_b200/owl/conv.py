@@ -4,6 +4,7 @@ from .narray import NArray, ConvInfo, PoolingInfo, pooling_algo, softmax_algo
 soft_op = softmax_algo
 pool_op = pooling_algo
 FUSED_CONV_RELU = True     # Convolver.ff(..., relu=True) exists: owl.net folds single-consumer ReLU units into it
+FUSED_RELU_BACKWARD = True  # Lrner.bp / max Pooler.bp(..., relu=True) exist: owl.net folds the preceding ReLU unit's backward into them
 
 
 def softmax(x, op=soft_op.instance):
@@ -22,8 +23,8 @@ class Lrner:
     def ff(self, x, scale):
         return NArray.lrn_forward(x, scale, self.local_size, self.alpha, self.beta)
 
-    def bp(self, bottom_data, top_data, scale, top_diff):
-        return NArray.lrn_backward(bottom_data, top_data, scale, top_diff, self.local_size, self.alpha, self.beta)
+    def bp(self, bottom_data, top_data, scale, top_diff, relu=False):
+        return NArray.lrn_backward(bottom_data, top_data, scale, top_diff, self.local_size, self.alpha, self.beta, relu)
 
 
 class Convolver:
@@ -51,5 +52,5 @@ class Pooler:
     def ff(self, x):
         return NArray.pooling_forward(x, self.param)
 
-    def bp(self, y, ff_y, ff_x):
-        return NArray.pooling_backward(y, ff_y, ff_x, self.param)
+    def bp(self, y, ff_y, ff_x, relu=False):
+        return NArray.pooling_backward(y, ff_y, ff_x, self.param, relu)

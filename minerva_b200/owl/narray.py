@@ -446,12 +446,15 @@ class NArray:
         return out
 
     @staticmethod
-    def pooling_backward(diff, top, bottom, info):
+    def pooling_backward(diff, top, bottom, info, relu=False):
+        """relu=True (max pooling only; not in the reference signature): `bottom` is a ReLU output and the result is
+        also masked by bottom > 0, i.e. ReLU backward is folded into the same kernel (mnv_max_pooling_backward_relu)."""
         _check(diff._shape == top._shape, "inputs sizes mismatch")
+        _check(not relu or info.algorithm.value == 0, "the fused ReLU mask exists for max pooling only")
         W, H, C, N = bottom._shape
         dev = _rt.current_device()
         out = NArray._new(bottom._shape, dev)
-        name = "mnv_%s_pooling_backward" % ("max" if info.algorithm.value == 0 else "average")
+        name = "mnv_%s_pooling_backward" % ("max" if info.algorithm.value == 0 else "average") + ("_relu" if relu else "")
         NArray._call(name, dev, bottom._on(dev).data_ptr(), top._on(dev).data_ptr(), diff._on(dev).data_ptr(),
                      out._t.data_ptr(), N, C, H, W, *NArray._pool_args(info))
         return out
@@ -468,11 +471,12 @@ class NArray:
         return out
 
     @staticmethod
-    def lrn_backward(bottom_data, top_data, scale, top_diff, local_size, alpha, beta):
+    def lrn_backward(bottom_data, top_data, scale, top_diff, local_size, alpha, beta, relu=False):
+        """relu=True (not in the reference signature): `bottom_data` is a ReLU output, ReLU backward is folded in."""
         W, H, C, N = bottom_data._shape
         dev = _rt.current_device()
         out = NArray._new(bottom_data._shape, dev)
-        NArray._call("mnv_lrn_backward", dev, bottom_data._on(dev).data_ptr(), top_data._on(dev).data_ptr(),
+        NArray._call("mnv_lrn_backward_relu" if relu else "mnv_lrn_backward", dev, bottom_data._on(dev).data_ptr(), top_data._on(dev).data_ptr(),
                      scale._on(dev).data_ptr(), top_diff._on(dev).data_ptr(), out._t.data_ptr(), int(local_size),
                      float(alpha), float(beta), N, C, W, H)
         return out

@@ -94,13 +94,14 @@ class ReluUnit(ComputeUnitSimple):
         super().__init__(name, [btm], [top])
 
     fused = False     # set by Net._plan_fusion: the producing convolution already rectified x in its epilogue
+    bp_fused = False  # set by Net._plan_fusion: the consuming LRN / max-pooling unit's backward kernel applies the mask
 
     def ff(self, x, phase):
         self.ff_y = x if self.fused else self.B.ele.relu(x)
         return self.ff_y
 
     def bp(self, y, phase):
-        return self.B.ele.relu_back(y, self.ff_y)
+        return y if self.bp_fused else self.B.ele.relu_back(y, self.ff_y)
 
 
 class SigmoidUnit(ComputeUnitSimple):
@@ -141,7 +142,11 @@ class PoolingUnit(ComputeUnitSimple):
         self.ff_y = self.pooler.ff(x)
         return self.ff_y
 
+    relu_bp = False   # set by Net._plan_fusion: ff_x is a ReLU output whose backward mask this unit applies
+
     def bp(self, y, phase):
+        if self.relu_bp:
+            return self.pooler.bp(y, self.ff_y, self.ff_x, relu=True)
         return self.pooler.bp(y, self.ff_y, self.ff_x)
 
 
@@ -182,7 +187,11 @@ class LRNUnit(ComputeUnitSimple):
         self.ff_y = self.lrner.ff(x, self.scale)
         return self.ff_y
 
+    relu_bp = False   # set by Net._plan_fusion: ff_x is a ReLU output whose backward mask this unit applies
+
     def bp(self, y, phase):
+        if self.relu_bp:
+            return self.lrner.bp(self.ff_x, self.ff_y, self.scale, y, relu=True)
         return self.lrner.bp(self.ff_x, self.ff_y, self.scale, y)
 
 
@@ -314,6 +323,7 @@ class Net(object):
         self.batch_size = 0          # GLOBAL batch: the update divisor (net.py:252-254,1121-1124)
         self.on_weight_grad = None   # hook(unit) fired as soon as a unit's gradients exist
         self.fuse_conv_relu = True   # False: run conv and ReLU as the reference's two ops
+        self.fuse_relu_backward = True   # False: ReLU backward stays its own pass in front of LRN / max-pooling backward
 
     def add_unit(self, unit):
         unit.B = self.B
@@ -336,19 +346,30 @@ class Net(object):
         the two-op sequence (owl/owl/net/net.py:281-296 after :621-716).  Only backends that advertise the fused
         entry point take part (the CPU twin used by the parity tests does not)."""
         self._fusion_planned = True
-        if not getattr(self.B.co, "FUSED_CONV_RELU", False) or not self.fuse_conv_relu:
-            return
-        for i, u in enumerate(self.units):
-            if not isinstance(u, ConvConnection):
-                continue
-            top, readers = u.top_names[0], []
+
+        def readers_of(i, top):
+            out = []
             for v in self.units[i + 1:]:
                 if top in v.btm_names:
-                    readers.append(v)
+                    out.append(v)
                 if top in v.top_names:      # an in-place unit rewrites the name: later readers see its output
                     break
-            if len(readers) == 1 and isinstance(readers[0], ReluUnit):
-                u.fuse_relu, readers[0].fused = True, True
+            return out
+        if getattr(self.B.co, "FUSED_CONV_RELU", False) and self.fuse_conv_relu:
+            for i, u in enumerate(self.units):
+                if isinstance(u, ConvConnection):
+                    readers = readers_of(i, u.top_names[0])
+                    if len(readers) == 1 and isinstance(readers[0], ReluUnit):
+                        u.fuse_relu, readers[0].fused = True, True
+        # backward: a ReluUnit read only by an LRN or max-pooling unit hands its mask to that unit's backward kernel
+        # (mnv_lrn_backward_relu / mnv_max_pooling_backward_relu; both read the ReLU output anyway)
+        if getattr(self.B.co, "FUSED_RELU_BACKWARD", False) and self.fuse_relu_backward:
+            for i, u in enumerate(self.units):
+                if isinstance(u, ReluUnit):
+                    readers = readers_of(i, u.top_names[0])
+                    if len(readers) == 1 and (isinstance(readers[0], LRNUnit) or
+                                              (isinstance(readers[0], PoolingUnit) and readers[0].pool == "max")):
+                        u.bp_fused, readers[0].relu_bp = True, True
 
     def forward(self, phase="TRAIN"):
         if not getattr(self, "_fusion_planned", False):

@@ -228,6 +228,10 @@ def test_pooling_bit_exact(g, case, relu_input):
         g.run("mnv_%s_pooling_backward" % fname, dx, g.dev(want), dyd, dres, N, C, H, W, sv, sh, wh, ww, ph, pw)
         wb = getattr(orc, kind + "_pooling_backward")(x, want, dy_, N, C, H, W, sv, sh, wh, ww, ph, pw)
         g.assert_bits_equal(g.host(dres), wb, kind + " bwd")
+        if kind == "max" and relu_input:   # fused ReLU backward: mask by bottom > 0 in the same kernel (or a second pass)
+            dfus = g.empty(x.size)
+            g.run("mnv_max_pooling_backward_relu", dx, g.dev(want), dyd, dfus, N, C, H, W, sv, sh, wh, ww, ph, pw)
+            g.assert_bits_equal(g.host(dfus), np.where(x > 0, wb, np.float32(0)).astype(np.float32), "max bwd + relu bwd")
 
 
 @pytest.mark.parametrize("N,C,H,W,size", [(2, 7, 3, 4, 5), (4, 96, 27, 27, 5), (2, 256, 13, 13, 5), (2, 5, 2, 3, 3),
@@ -245,6 +249,10 @@ def test_lrn(g, N, C, H, W, size):
     g.run("mnv_lrn_backward", g.dev(x), g.dev(y), g.dev(scale), g.dev(dy_), dres, size, alpha, beta, N, C, W, H)
     wb = orc.lrn_backward(x, y, scale, dy_, size, alpha, beta, N, C, W, H)
     assert np.abs(g.host(dres) - wb).max() <= 1e-5 * np.abs(wb).max()
+    # fused ReLU backward == the unfused pair, bit for bit (x here has both signs: the mask is bottom > 0)
+    dfus = g.empty(x.size)
+    g.run("mnv_lrn_backward_relu", g.dev(x), g.dev(y), g.dev(scale), g.dev(dy_), dfus, size, alpha, beta, N, C, W, H)
+    g.assert_bits_equal(g.host(dfus), np.where(x > 0, g.host(dres), np.float32(0)).astype(np.float32), "lrn bwd + relu bwd")
 
 
 @pytest.mark.parametrize("N,C,H,W", [(2, 5, 4, 4), (16, 96, 55, 55), (8, 256, 13, 13), (256, 10, 1, 1), (3, 1000, 1, 1)])

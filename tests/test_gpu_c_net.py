@@ -125,7 +125,7 @@ def test_conv_relu_fusion_is_bit_identical(gpu_owl):
     for fuse in (True, False):
         gpu_owl.set_seed(5)
         net = _tiny_net(_default_backend())
-        net.fuse_conv_relu = fuse
+        net.fuse_conv_relu = net.fuse_relu_backward = fuse
         du = net.get_data_unit()
         du.data, du.label = _batch(net.B, 8)
         net.batch_size = 8
@@ -133,6 +133,8 @@ def test_conv_relu_fusion_is_bit_identical(gpu_owl):
         net.backward("TRAIN")
         n_fused = sum(1 for u in net.units if isinstance(u, ConvConnection) and u.fuse_relu)
         assert (n_fused > 0) == fuse and n_fused == sum(1 for u in net.units if isinstance(u, ReluUnit) and u.fused)
+        # relu1 -> LRN and relu2 -> max pool hand their backward masks over; relu6 -> dropout keeps its own pass
+        assert sum(1 for u in net.units if isinstance(u, ReluUnit) and u.bp_fused) == (2 if fuse else 0)
         res.append([net.units[uid].weightgrad.to_numpy() for uid in net.get_weighted_unit_ids()]
                    + [net.get_loss_units()[0].ff_y.to_numpy()])
     for a, b in zip(*res):
