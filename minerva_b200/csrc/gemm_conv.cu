@@ -72,6 +72,11 @@ struct GemmParams {
   long long img_stride, col_stride;
   // tiling
   int bn, m_tiles, n_tiles, splits, stages_per_split, k_stages;
+  // Tail split (splits == 1 only): a tile grid that ends in a thin last wave gives that wave's tiles to tail_splits CTAs
+  // each (partials + tail reduce), so the machine stays full -- 338 tiles on 148 SMs cost 2 + 1/3 waves instead of 3.
+  int tail_first;       // first tile id (raster order) that is K-split; == m_tiles * n_tiles when there is no tail
+  int tail_splits, tail_stages;
+  int total_units;      // work items of the persistent loop: tail_first + (tiles - tail_first) * tail_splits, or tiles * splits
   int use_ktab;         // A_IM2COL_FWD: k -> (offset, kh, kw) table in shared memory
   int spi;              // backward-filter with TMA-fed top_diff: k-stages per image (K padded per image), else 0
   unsigned wait_hint;   // mbarrier.try_wait suspend-time hint (ns)
@@ -603,7 +608,7 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const CUte
 // the kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kRasterM = 16;
-struct TileCoord { int mt, nt, split, ks_begin, ks_end; };
+struct TileCoord { int mt, nt, split, ks_begin, ks_end, partial; };
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
   TileCoord t;
   // Grouped rasterisation: inside one K split the tile index walks kRasterM m-tiles down, then one n-tile
@@ -611,8 +616,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   // a wave touches drop from (4.6*128 + N) to (16*128 + 9*bn), which is what keeps an 8192^3 GEMM's B
   // (268 MB > L2) from being re-fetched from HBM every wave.
   const int per_split = p.m_tiles * p.n_tiles;
-  t.split = tile / per_split;
-  int id = tile - t.split * per_split;
+  int id, stages;
+  if (tile >= p.tail_first) {          // tail split (implies splits == 1): the last tiles, tail_splits CTAs each
+    const int u = tile - p.tail_first, ntail = per_split - p.tail_first;
+    t.split = u / ntail;
+    id = p.tail_first + (u - t.split * ntail);
+    stages = p.tail_stages;
+    t.partial = 1;
+  } else {
+    t.split = tile / per_split;
+    id = tile - t.split * per_split;
+    stages = p.stages_per_split;
+    t.partial = p.splits > 1;
+  }
   const int band = kRasterM * p.n_tiles;
   const int g = id / band;
   id -= g * band;
@@ -620,8 +636,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   const int gm = min(kRasterM, p.m_tiles - first_m);
   t.nt = id / gm;
   t.mt = first_m + (id - t.nt * gm);
-  t.ks_begin = t.split * p.stages_per_split;
-  t.ks_end = min(p.k_stages, t.ks_begin + p.stages_per_split);
+  t.ks_begin = t.split * stages;
+  t.ks_end = min(p.k_stages, t.ks_begin + stages);
   return t;
 }
 
@@ -659,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int total_tiles = p.total_units;
 
   if (threadIdx.x == 0) {
     // full: TMA-fed B: the 4 warps of the slot's producer group + the TMA thread's arrive.expect_tx;
@@ -696,15 +712,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       mbar_wait(tfull0 + 8 * acc_stage, acc_phase, p.wait_hint);
       tc_fence_after();
       const int n0 = t.nt * p.bn;
-      const bool add_bias = p.bias != nullptr && p.splits == 1;
-      const bool relu = p.relu != 0 && p.splits == 1;
+      const bool add_bias = p.bias != nullptr && !t.partial;
+      const bool relu = p.relu != 0 && !t.partial;
 #pragma unroll
       for (int half = 0; half < (TALL ? 2 : 1); ++half) {
         const int m = t.mt * kTileM + half * BM + quarter * 32 + lane;
         const bool row_ok = out_row_ok(p, m);
         float* dst;
         long long cstride;
-        if (p.splits > 1) {  // partial[split][n][m]
+        if (t.partial) {  // partial[split][n][m]
           dst = p.partial + static_cast<size_t>(t.split) * p.M * p.N + (row_ok ? m : 0);
           cstride = p.M;
         } else {
@@ -1087,6 +1103,25 @@ __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams 
     if (!out_row_ok(p, m)) continue;
     float acc = __ldg(p.partial + t);
     for (int s = 1; s < p.splits; ++s) acc += __ldg(p.partial + static_cast<size_t>(s) * mn + t);
+    if (p.bias) acc += __ldg(p.bias + n);
+    if (p.relu) acc = acc > 0.f ? acc : 0.f;
+    p.out[out_index(p, m, n)] = acc;
+  }
+}
+
+// tail split: the same fold for the K-split tiles of the last wave only (tile ids >= tail_first in raster order)
+__global__ void __launch_bounds__(kBlock) splitk_tail_reduce_kernel(const GemmParams p) {
+  const int tile_m = p.tall ? 2 * BM : BM, per_tile = tile_m * p.bn;
+  const int ntail = p.m_tiles * p.n_tiles - p.tail_first;
+  const size_t mn = static_cast<size_t>(p.M) * p.N, total = static_cast<size_t>(ntail) * per_tile;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int tt = static_cast<int>(i / per_tile), e = static_cast<int>(i - static_cast<size_t>(tt) * per_tile);
+    const TileCoord t = decode_tile(p, p.tail_first + tt);   // split 0 of that tile: same (mt, nt)
+    const int m = t.mt * tile_m + e % tile_m, n = t.nt * p.bn + e / tile_m;
+    if (n >= p.N || !out_row_ok(p, m)) continue;
+    const size_t at = static_cast<size_t>(n) * p.M + m;
+    float acc = __ldg(p.partial + at);
+    for (int sp = 1; sp < p.tail_splits; ++sp) acc += __ldg(p.partial + static_cast<size_t>(sp) * mn + at);
     if (p.bias) acc += __ldg(p.bias + n);
     if (p.relu) acc = acc > 0.f ? acc : 0.f;
     p.out[out_index(p, m, n)] = acc;
@@ -1698,6 +1733,26 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
   }
 }
 
+// Tail split (see GemmParams): when the tile grid ends in a last wave that fills at most half the machine, the tiles of
+// that wave are K-split over the idle CTAs.  Partials use the split-K layout partial[split][n][m] (only the tail tiles'
+// entries are touched); splitk_tail_reduce_kernel folds them.
+static std::atomic<int> g_opt_no_tail{0};    // 1: no tail split (tuning)
+static void plan_tail(GemmParams& p, void* ws, size_t ws_bytes) {
+  p.tail_splits = 0;
+  if (g_opt_no_tail.load() || p.splits != 1 || !ws) return;
+  const int sms = sm_budget(), tiles = p.m_tiles * p.n_tiles;
+  const int rem = tiles % sms;
+  if (tiles < sms || rem == 0 || rem * 2 > sms) return;
+  int S = sms / rem;
+  if (S > 8) S = 8;
+  if (S > p.k_stages / 8) S = p.k_stages / 8;     // at least 8 k-stages per tail split
+  if (S < 2) return;
+  if (ws_bytes < static_cast<size_t>(S) * p.M * p.N * sizeof(float)) return;
+  p.tail_stages = (p.k_stages + S - 1) / S;
+  p.tail_splits = (p.k_stages + p.tail_stages - 1) / p.tail_stages;
+  p.tail_first = tiles - rem;
+  p.partial = static_cast<float*>(ws);
+}
 static const CUtensorMap& null_tmap() { static CUtensorMap z = {}; return z; }
 template <int AM, int BMD, bool BTMA, int RING>
 static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_t s, const CUtensorMap& tm_a = null_tmap()) {
@@ -1710,10 +1765,17 @@ static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
-  long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+  GemmParams q = p;
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (q.tail_splits > 1 && q.splits == 1 && q.partial) {
+    q.total_units = q.tail_first + (tiles - q.tail_first) * q.tail_splits;
+  } else {
+    q.tail_splits = 0; q.tail_first = 0x7fffffff; q.total_units = tiles * p.splits;
+  }
+  const long long total = q.total_units;
   const int sms = sm_budget();
   int grid = static_cast<int>(total < sms ? total : sms);
-  umma_gemm_kernel<AM, BMD, BTMA, RING><<<grid, kThreads, kSmemBytes, s>>>(p, tm, tm_a);
+  umma_gemm_kernel<AM, BMD, BTMA, RING><<<grid, kThreads, kSmemBytes, s>>>(q, tm, tm_a);
   return finish_launch();
 }
 template <int AM, int BMD, bool BTMA>
@@ -1728,7 +1790,13 @@ static int launch_umma_tma(const GemmParams& p, const CUtensorMap& tm_a, const C
            : p.wide    ? launch_umma_w<A_TMA, B_KMAJOR, true, 1>(p, tm_b, s, tm_a)
            : (p.bn <= 128 && !g_opt_no_deep.load()) ? launch_umma_w<A_TMA, B_KMAJOR, true, 2>(p, tm_b, s, tm_a)
                           : launch_umma_w<A_TMA, B_KMAJOR, true, 0>(p, tm_b, s, tm_a);
-  if (rc || p.splits == 1) return rc;
+  if (rc) return rc;
+  if (p.splits == 1 && p.tail_splits > 1 && p.partial) {
+    const size_t items = static_cast<size_t>(p.m_tiles * p.n_tiles - p.tail_first) * (p.tall ? 2 * BM : BM) * p.bn;
+    splitk_tail_reduce_kernel<<<stream_grid(items), kBlock, 0, s>>>(p);
+    return finish_launch();
+  }
+  if (p.splits == 1) return rc;
   splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
   return finish_launch();
 }
@@ -1802,7 +1870,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -1869,6 +1937,7 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   // the 256 x 96 tile here): always taken.  "force_tma_a" overrides for experiments.
   if (!s2d && !g_opt_force_tma_a.load() && static_cast<long long>(Co) * ff < 3000 && p.bn > 128) return MNV_OK;
   p.partial = p.splits > 1 ? static_cast<float*>(ws2) : nullptr;
+  plan_tail(p, ws2, ws2_bytes);
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
@@ -1961,6 +2030,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_klane") return g_opt_no_klane.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
   if (k == "no_s2d") return g_opt_no_s2d.exchange(value);
+  if (k == "no_tail") return g_opt_no_tail.exchange(value);
   if (k == "no_shift") return g_opt_no_shift.exchange(value);
   if (k == "shift_dbg") return g_opt_shift_dbg.exchange(value);
   if (k == "s2d_im2col") return g_opt_s2d_im2col.exchange(value);

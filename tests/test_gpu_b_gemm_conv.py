@@ -185,6 +185,40 @@ def test_conv_operand_paths(g, case):
         assert g.norm_rel(dw, wdw) < TOL, name + ": backward filter"
 
 
+@pytest.mark.parametrize("case", [(120, 64, 48, 13, 13, 1, 1, 1, 1, 3, 3),     # 159 tiles: 11 tail tiles x 2 splits
+                                  (128, 96, 72, 13, 13, 1, 1, 1, 1, 3, 3),     # 169 tiles: 21 tail tiles x 3 splits
+                                  (100, 32, 300, 14, 14, 0, 0, 1, 1, 1, 1)])   # two n-tiles per m-tile, tail in the last raster band
+def test_conv_tail_split(g, case):
+    """Tile grids that end in a thin last wave K-split that wave's tiles (partials + tail reduce): forward (bias + fused
+    ReLU in the reduce) and stride-1 backward-data, with and without the tail split."""
+    N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = case
+    Ho, Wo = orc.conv_out(H, ph, fh, sv), orc.conv_out(W, pw, fw, sh)
+    x = rng.normal(0, 1, N * Ci * H * W).astype(np.float32)
+    w = rng.normal(0, 1, Co * Ci * fh * fw).astype(np.float32)
+    b = rng.normal(0, 1, Co).astype(np.float32)
+    dy = rng.normal(0, 1, N * Co * Ho * Wo).astype(np.float32)
+    geo = (N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw)
+    wy = orc.conv_forward(x, w, b, *geo)
+    wdx = orc.conv_backward_data(dy, w, *geo)
+    ws = g.workspace()
+    for no_tail in (0, 1):
+        try:
+            _set("no_tail", no_tail)
+            _set("force_tma_a", 1)
+            y = g.empty(wy.size); y.fill_(float("nan"))
+            g.run("mnv_conv_forward", g.dev(x), g.dev(w), g.dev(b), y, *geo, ws, ws.numel())
+            yr = g.empty(wy.size); yr.fill_(float("nan"))
+            g.run("mnv_conv_forward_relu", g.dev(x), g.dev(w), g.dev(b), yr, *geo, ws, ws.numel())
+            dx = g.empty(x.size); dx.fill_(float("nan"))
+            g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, ws, ws.numel())
+        finally:
+            _set("no_tail", 0)
+            _set("force_tma_a", 0)
+        assert g.norm_rel(g.host(y), wy) < TOL, "forward, no_tail=%d" % no_tail
+        assert np.array_equal(g.host(yr), np.maximum(g.host(y), 0)), "fused relu, no_tail=%d" % no_tail
+        assert g.norm_rel(g.host(dx), wdx) < TOL, "backward data, no_tail=%d" % no_tail
+
+
 S2D_CASES = [CONV_CASES[4], CONV_CASES[8]] + CONV_CASES[13:] + [
     (3, 3, 96, 59, 63, 0, 0, 4, 4, 11, 11),    # several 256-position tiles per image, tiles straddling images
     (2, 3, 128, 40, 40, 1, 2, 4, 4, 9, 10),    # 128 filters (the kernel's widest tile), pad, filter not a stride multiple
