@@ -252,6 +252,17 @@ int mnv_lrn_backward_relu(const float* bottom_data, const float* top_data, const
                           const float* top_diff, float* bottom_diff, int local_size, float alpha,
                           float beta, int num_img, int channel, int width, int height,
                           mnv_stream_t stream);
+/* Extension (recompute instead of re-read): LRN without the `scale` array.  The forward pass writes only
+ * `res` (8 B per element instead of 12); the backward pass reads only bottom and top_diff (12 B instead of 20) and
+ * recomputes scale and top in registers with the forward pass's exact operation sequence, so bottom_diff is
+ * bit-identical to mnv_lrn_backward fed with the stored arrays.  relu != 0 additionally applies the ReLU-backward mask
+ * (bottom > 0).  Window 5 only (AlexNet, GoogLeNet); other windows return MNV_EUNSUPPORTED and the caller keeps the
+ * three-array form.  owl.net's LRNUnit uses the pair when both passes run on this backend. */
+int mnv_lrn_forward_lite(const float* bottom, float* res, int local_size, float alpha, float beta,
+                         int num_img, int channel, int width, int height, mnv_stream_t stream);
+int mnv_lrn_backward_lite(const float* bottom_data, const float* top_diff, float* bottom_diff,
+                          int local_size, float alpha, float beta, int num_img, int channel,
+                          int width, int height, int relu, mnv_stream_t stream);
 int mnv_max_pooling_backward_relu(const float* bottom, const float* top, const float* top_diff,
                                   float* bottom_diff, int num_images, int num_channels,
                                   int bottom_height, int bottom_width, int stride_vertical,

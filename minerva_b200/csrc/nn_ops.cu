@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(kBlock) lrn_fwd5_kernel(const float* __restric
           if (o >= 0 && o < C) {
             const float sc = __fadd_rn(1.0f, __fmul_rn(acc[j], alpha_over_size));
             const float ov = __fmul_rn(x2[j], pow_neg_beta_sfu<BETA075>(sc, neg_beta));
-            if (live[j]) { scale[st[j]] = sc; out[st[j]] = ov; }
+            if (live[j]) { if (scale) scale[st[j]] = sc; out[st[j]] = ov; }
             st[j] += step;
           }
           x2[j] = x1[j]; x1[j] = xin;
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(256) lrn_fwd5_aligned_kernel(const float* __re
         const int o = c0 + u - 2;
         if (o >= 0 && o < C) {
           const float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
-          buf[pp][0][u][tid] = sc;
+          if (scale) buf[pp][0][u][tid] = sc;
           buf[pp][1][u][tid] = __fmul_rn(x2, pow_neg_beta_sfu<BETA075>(sc, neg_beta));
         }
         x2 = x1; x1 = xin;
@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(256) lrn_fwd5_aligned_kernel(const float* __re
           const unsigned g0 = base + static_cast<unsigned>(o) * step;
           const unsigned e = (tid - (g0 & 31u)) & 255u;   // whole 128-byte lines per warp
           if (e < cnt) {
-            scale[g0 + e] = buf[pp][0][u][e];
+            if (scale) scale[g0 + e] = buf[pp][0][u][e];
             out[g0 + e] = buf[pp][1][u][e];
           }
         }
@@ -969,6 +969,80 @@ __global__ void __launch_bounds__(kBlock) lrn_bwd5_kernel(const float* __restric
       }
 #pragma unroll
       for (int u = 0; u < kLrnChunk; ++u) { ctd[u] = ntd[u]; ctp[u] = ntp[u]; csc[u] = nsc[u]; cb[u] = nb[u]; }
+    }
+  }
+}
+
+// LRN backward from (bottom, top_diff) alone: `scale` and `top` are recomputed in registers with exactly the forward
+// pass's operations (same add / subtract order, same SFU power), so the result is bit-identical to lrn_bwd5_kernel fed
+// with the forward pass's stored arrays -- 12 B per element instead of 20, and the forward pass need not store `scale`
+// (8 B instead of 12).  The recurrences are chained: head h loads channel h; scale / top / ratio exist for channel
+// j = h - 2; the output channel is o = h - 4.
+template <bool BETA075>
+__global__ void __launch_bounds__(kBlock) lrn_bwd5_lite_kernel(const float* __restrict__ bottom, const float* __restrict__ top_diff,
+                                                               float* __restrict__ bottom_diff, int num, int C, unsigned step,
+                                                               float alpha_over_size, float neg_beta, float cache_ratio, int relu) {
+  const unsigned total = static_cast<unsigned>(num) * step;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const unsigned n = t / step, p = t - n * step;
+    unsigned ld = n * static_cast<unsigned>(C) * step + p;
+    unsigned st = ld;
+    float cx[kLrnChunk], ctd[kLrnChunk], nx[kLrnChunk], ntd[kLrnChunk];
+#pragma unroll
+    for (int u = 0; u < kLrnChunk; ++u) {
+      const bool ok = u < C;
+      cx[u] = ok ? __ldg(bottom + ld) : 0.f;
+      ctd[u] = ok ? __ldg(top_diff + ld) : 0.f;
+      ld += step;
+    }
+    float sq0 = 0.f, sq1 = 0.f, sq2 = 0.f, sq3 = 0.f, sq4 = 0.f, acc = 0.f;      // squares of x[h-1 .. h-5]
+    float xa = 0.f, xb = 0.f, xc = 0.f, xd = 0.f;                                // x[h-1 .. h-4]
+    float tda = 0.f, tdb = 0.f, tdc = 0.f, tdd = 0.f;                            // top_diff[h-1 .. h-4]
+    float pa = 0.f, pb = 0.f;                                                    // scale^-beta of channels h-3, h-4
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, acc2 = 0.f;          // top_diff*top/scale of j-1 .. j-5
+    for (int c0 = 0; c0 < C + 4; c0 += kLrnChunk) {
+      const int left = C - (c0 + kLrnChunk);   // channels still to load
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) {
+        const bool ok = u < left;
+        nx[u] = ok ? __ldg(bottom + ld) : 0.f;
+        ntd[u] = ok ? __ldg(top_diff + ld) : 0.f;
+        ld += step;
+      }
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) {
+        const int h = c0 + u;
+        const float xin = cx[u], tdin = ctd[u];      // 0 past C
+        // forward recurrence (lrn_fwd5_kernel): scale of channel j = h - 2
+        const float add = __fmul_rn(xin, xin);
+        acc = __fadd_rn(acc, add);
+        acc = __fsub_rn(acc, sq4);
+        sq4 = sq3; sq3 = sq2; sq2 = sq1; sq1 = sq0; sq0 = add;
+        const int j = h - 2;
+        float pj = 0.f, r = 0.f;                     // past C: 0 * 0 / 1 = +0, as lrn_bwd5_kernel gets from its masked loads
+        if (j >= 0 && j < C) {
+          const float sc = __fadd_rn(1.0f, __fmul_rn(acc, alpha_over_size));
+          pj = pow_neg_beta_sfu<BETA075>(sc, neg_beta);
+          const float top = __fmul_rn(xb, pj);       // what the forward pass stored
+          r = __fdividef(__fmul_rn(tdb, top), sc);
+        }
+        // backward recurrence (lrn_bwd5_kernel) with j as its head: output channel o = j - 2
+        acc2 = __fadd_rn(acc2, r);
+        acc2 = __fsub_rn(acc2, r4);
+        r4 = r3; r3 = r2; r2 = r1; r1 = r0; r0 = r;
+        const int o = h - 4;
+        if (o >= 0 && o < C) {
+          const float lhs = __fmul_rn(tdd, pb);
+          const float rhs = __fmul_rn(__fmul_rn(cache_ratio, xd), acc2);
+          bottom_diff[st] = (relu && !(xd > 0.f)) ? 0.f : __fsub_rn(lhs, rhs);
+          st += step;
+        }
+        xd = xc; xc = xb; xb = xa; xa = xin;
+        tdd = tdc; tdc = tdb; tdb = tda; tda = tdin;
+        pb = pa; pa = pj;
+      }
+#pragma unroll
+      for (int u = 0; u < kLrnChunk; ++u) { cx[u] = nx[u]; ctd[u] = ntd[u]; }
     }
   }
 }
@@ -1185,12 +1259,17 @@ int mnv_conv_backward_bias(const float* dy, float* db, int N, int C, int H, int 
   return finish_launch();
 }
 
-int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_size, float alpha, float beta,
-                    int num_img, int channel, int width, int height, mnv_stream_t s) {
+static bool lrn_fast5(int local_size, int channel, size_t work, int lookahead) {
+  // the size-5 kernels keep 32-bit element offsets (their loads run up to `lookahead` channels past the tensor's end, unissued)
+  return local_size == 5 && channel >= 5 && (static_cast<unsigned long long>(channel) + lookahead) * work < (1ull << 31);
+}
+static int lrn_forward_impl(const float* bottom, float* scale, float* res, int local_size, float alpha, float beta,
+                            int num_img, int channel, int width, int height, mnv_stream_t s) {
   if (num_img < 0 || channel < 0 || width < 0 || height < 0 || local_size <= 0) return MNV_EINVAL;
   size_t step = static_cast<size_t>(width) * height, work = step * num_img;
   if (work == 0 || channel == 0) return MNV_OK;
-  if (!bottom || !scale || !res) return MNV_EINVAL;
+  if (!bottom || !res) return MNV_EINVAL;
+  if (!scale && !lrn_fast5(local_size, channel, work, 32)) return MNV_EUNSUPPORTED;   // scale-less form: window 5 only
   const float aos = alpha / local_size;
   const bool b075 = beta == 0.75f;
   const int grid = stream_grid(work);
@@ -1216,6 +1295,30 @@ int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_siz
     if (b075) lrn_fwd_kernel<0, true><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
     else lrn_fwd_kernel<0, false><<<grid, kBlock, 0, as_stream(s)>>>(bottom, scale, res, num_img, channel, step, local_size, aos, -beta);
   }
+  return finish_launch();
+}
+int mnv_lrn_forward(const float* bottom, float* scale, float* res, int local_size, float alpha, float beta,
+                    int num_img, int channel, int width, int height, mnv_stream_t s) {
+  if (!scale && static_cast<size_t>(width) * height * num_img != 0 && channel != 0) return MNV_EINVAL;
+  return lrn_forward_impl(bottom, scale, res, local_size, alpha, beta, num_img, channel, width, height, s);
+}
+int mnv_lrn_forward_lite(const float* bottom, float* res, int local_size, float alpha, float beta,
+                         int num_img, int channel, int width, int height, mnv_stream_t s) {
+  return lrn_forward_impl(bottom, nullptr, res, local_size, alpha, beta, num_img, channel, width, height, s);
+}
+int mnv_lrn_backward_lite(const float* bottom_data, const float* top_diff, float* bottom_diff, int local_size, float alpha,
+                          float beta, int num_img, int channel, int width, int height, int relu, mnv_stream_t s) {
+  if (num_img < 0 || channel < 0 || width < 0 || height < 0 || local_size <= 0) return MNV_EINVAL;
+  size_t step = static_cast<size_t>(width) * height, work = step * num_img;
+  if (work == 0 || channel == 0) return MNV_OK;
+  if (!bottom_data || !top_diff || !bottom_diff) return MNV_EINVAL;
+  if (!lrn_fast5(local_size, channel, work, 32)) return MNV_EUNSUPPORTED;
+  const float cache_ratio = static_cast<float>(2. * alpha * beta / local_size);  // cuda_perform.cu:665
+  const float aos = alpha / local_size;
+  const unsigned step32 = static_cast<unsigned>(step);
+  const int grid = stream_grid(work);
+  if (beta == 0.75f) lrn_bwd5_lite_kernel<true><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_diff, bottom_diff, num_img, channel, step32, aos, -beta, cache_ratio, relu);
+  else lrn_bwd5_lite_kernel<false><<<grid, kBlock, 0, as_stream(s)>>>(bottom_data, top_diff, bottom_diff, num_img, channel, step32, aos, -beta, cache_ratio, relu);
   return finish_launch();
 }
 static int lrn_backward_impl(const float* bottom_data, const float* top_data, const float* scale, const float* top_diff,

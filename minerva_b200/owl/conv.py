@@ -26,6 +26,16 @@ class Lrner:
     def bp(self, bottom_data, top_data, scale, top_diff, relu=False):
         return NArray.lrn_backward(bottom_data, top_data, scale, top_diff, self.local_size, self.alpha, self.beta, relu)
 
+    # scale-less pair (not in the reference API): forward stores only its output, backward recomputes scale / top
+    def lite_ok(self, shape):
+        return NArray.lrn_lite_ok(shape, self.local_size)
+
+    def ff_lite(self, x):
+        return NArray.lrn_forward_lite(x, self.local_size, self.alpha, self.beta)
+
+    def bp_lite(self, bottom_data, top_diff, relu=False):
+        return NArray.lrn_backward_lite(bottom_data, top_diff, self.local_size, self.alpha, self.beta, relu)
+
 
 class Convolver:
     def __init__(self, pad_h, pad_w, stride_v, stride_h):

@@ -481,6 +481,32 @@ class NArray:
                      float(alpha), float(beta), N, C, W, H)
         return out
 
+    @staticmethod
+    def lrn_lite_ok(shape, local_size):
+        """Window 5, >= 5 channels, 32-bit offsets: the shapes mnv_lrn_*_lite handle (include/mnv.h)."""
+        W, H, C, N = shape
+        return int(local_size) == 5 and C >= 5 and (C + 32) * W * H * N < (1 << 31)
+
+    @staticmethod
+    def lrn_forward_lite(src, local_size, alpha, beta):
+        """LRN forward without the `scale` array (not in the reference API): see mnv_lrn_forward_lite."""
+        W, H, C, N = src._shape
+        dev = _rt.current_device()
+        out = NArray._new(src._shape, dev)
+        NArray._call("mnv_lrn_forward_lite", dev, src._on(dev).data_ptr(), out._t.data_ptr(),
+                     int(local_size), float(alpha), float(beta), N, C, W, H)
+        return out
+
+    @staticmethod
+    def lrn_backward_lite(bottom_data, top_diff, local_size, alpha, beta, relu=False):
+        """LRN backward from (bottom, top_diff) alone, scale and top recomputed in registers: see mnv_lrn_backward_lite."""
+        W, H, C, N = bottom_data._shape
+        dev = _rt.current_device()
+        out = NArray._new(bottom_data._shape, dev)
+        NArray._call("mnv_lrn_backward_lite", dev, bottom_data._on(dev).data_ptr(), top_diff._on(dev).data_ptr(),
+                     out._t.data_ptr(), int(local_size), float(alpha), float(beta), N, C, W, H, 1 if relu else 0)
+        return out
+
     # ---- constructors / host transfer ---------------------------------------------------------------
     @staticmethod
     def _filled(shape, val):

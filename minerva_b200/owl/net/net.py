@@ -177,10 +177,17 @@ class LRNUnit(ComputeUnitSimple):
         super().__init__(name, [btm], [top])
         self.args = (local_size, alpha, beta)
 
+    lite = True       # Net.fuse_lrn_recompute: drop the `scale` array, recompute it in the backward kernel
+
     def ff(self, x, phase):
         if not hasattr(self, "lrner"):
             self.lrner = self.B.co.Lrner(*self.args)
         self.ff_x = x
+        if self.lite and hasattr(self.lrner, "ff_lite") and self.lrner.lite_ok(x.shape):
+            # 8 + 12 B per element for the two passes instead of 12 + 20 (mnv_lrn_forward_lite / _backward_lite)
+            self.scale = None
+            self.ff_y = self.lrner.ff_lite(x)
+            return self.ff_y
         # the reference allocates `scale` with owl.zeros (net.py:498); LRNForward overwrites every element, so the
         # device backend skips that fill (182 + 119 MB of writes per AlexNet step)
         self.scale = getattr(self.B.owl, "_uninit", self.B.owl.zeros)(x.shape)
@@ -190,6 +197,8 @@ class LRNUnit(ComputeUnitSimple):
     relu_bp = False   # set by Net._plan_fusion: ff_x is a ReLU output whose backward mask this unit applies
 
     def bp(self, y, phase):
+        if self.scale is None:
+            return self.lrner.bp_lite(self.ff_x, y, relu=self.relu_bp)
         if self.relu_bp:
             return self.lrner.bp(self.ff_x, self.ff_y, self.scale, y, relu=True)
         return self.lrner.bp(self.ff_x, self.ff_y, self.scale, y)
@@ -324,6 +333,7 @@ class Net(object):
         self.on_weight_grad = None   # hook(unit) fired as soon as a unit's gradients exist
         self.fuse_conv_relu = True   # False: run conv and ReLU as the reference's two ops
         self.fuse_relu_backward = True   # False: ReLU backward stays its own pass in front of LRN / max-pooling backward
+        self.fuse_lrn_recompute = True   # False: LRN keeps the reference's (bottom, top, scale) three-array form
 
     def add_unit(self, unit):
         unit.B = self.B
@@ -346,6 +356,9 @@ class Net(object):
         the two-op sequence (owl/owl/net/net.py:281-296 after :621-716).  Only backends that advertise the fused
         entry point take part (the CPU twin used by the parity tests does not)."""
         self._fusion_planned = True
+        for u in self.units:
+            if isinstance(u, LRNUnit):
+                u.lite = bool(self.fuse_lrn_recompute)
 
         def readers_of(i, top):
             out = []

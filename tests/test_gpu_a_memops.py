@@ -235,7 +235,7 @@ def test_pooling_bit_exact(g, case, relu_input):
 
 
 @pytest.mark.parametrize("N,C,H,W,size", [(2, 7, 3, 4, 5), (4, 96, 27, 27, 5), (2, 256, 13, 13, 5), (2, 5, 2, 3, 3),
-                                          (1, 6, 2, 2, 4), (2, 3, 4, 4, 5)])
+                                          (1, 6, 2, 2, 4), (2, 3, 4, 4, 5), (3, 96, 55, 55, 5), (2, 5, 16, 16, 5), (2, 19, 8, 7, 5)])
 def test_lrn(g, N, C, H, W, size):
     alpha, beta = 1e-4, 0.75
     x = rng.normal(0, 20, N * C * H * W).astype(np.float32)
@@ -253,6 +253,22 @@ def test_lrn(g, N, C, H, W, size):
     dfus = g.empty(x.size)
     g.run("mnv_lrn_backward_relu", g.dev(x), g.dev(y), g.dev(scale), g.dev(dy_), dfus, size, alpha, beta, N, C, W, H)
     g.assert_bits_equal(g.host(dfus), np.where(x > 0, g.host(dres), np.float32(0)).astype(np.float32), "lrn bwd + relu bwd")
+    # scale-less pair: forward output and backward result bit-identical to the three-array form fed with the GPU's own arrays
+    if size == 5 and C >= 5:
+        dout2 = g.empty(x.size)
+        g.run("mnv_lrn_forward_lite", g.dev(x), dout2, size, alpha, beta, N, C, W, H)
+        g.assert_bits_equal(g.host(dout2), g.host(dout), "lrn forward without scale")
+        dref = g.empty(x.size)
+        g.run("mnv_lrn_backward", g.dev(x), dout, dscale, g.dev(dy_), dref, size, alpha, beta, N, C, W, H)
+        for relu in (0, 1):
+            dlite = g.empty(x.size); dlite.fill_(float("nan"))
+            g.run("mnv_lrn_backward_lite", g.dev(x), g.dev(dy_), dlite, size, alpha, beta, N, C, W, H, relu)
+            want = np.where(x > 0, g.host(dref), np.float32(0)).astype(np.float32) if relu else g.host(dref)
+            g.assert_bits_equal(g.host(dlite), want, "lrn backward from (bottom, top_diff), relu=%d" % relu)
+    else:
+        from minerva_b200._lib import MnvError
+        with pytest.raises(MnvError):
+            g.run("mnv_lrn_forward_lite", g.dev(x), g.empty(x.size), size, alpha, beta, N, C, W, H)
 
 
 @pytest.mark.parametrize("N,C,H,W", [(2, 5, 4, 4), (16, 96, 55, 55), (8, 256, 13, 13), (256, 10, 1, 1), (3, 1000, 1, 1)])
