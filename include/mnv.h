@@ -269,6 +269,26 @@ int mnv_max_pooling_backward_relu(const float* bottom, const float* top, const f
                                   int stride_horizontal, int window_height, int window_width,
                                   int pad_height, int pad_width, mnv_stream_t stream);
 
+/* Extension (remember instead of recompute): 3x3 / stride 2 / pad 0 max pooling (AlexNet, GoogLeNet) whose
+ * forward pass also writes one byte per pooled element -- the window position kh*3+kw of the first maximum in scan
+ * order, 255 for a window of NaNs -- so that the backward pass reads (top_diff, idx) = 5 B per pooled element instead of
+ * re-reading the whole bottom (4 B per INPUT element) and recomputing the arg-max.  bottom_diff is bit-identical to
+ * mnv_max_pooling_backward.  relu_top != NULL folds ReLU backward in for a bottom that is a ReLU output: pass the
+ * pooled top (the arg-max element passes iff its value, the window maximum, is > 0).  Other geometries return
+ * MNV_EUNSUPPORTED and the caller keeps the recomputing pair. */
+int mnv_max_pooling_idx_supported(int num_images, int num_channels, int bottom_height, int bottom_width,
+                                  int stride_vertical, int stride_horizontal, int window_height,
+                                  int window_width, int pad_height, int pad_width);   /* 1 / 0, no launch */
+int mnv_max_pooling_forward_idx(const float* bottom, float* top, unsigned char* idx, int num_images,
+                                int num_channels, int bottom_height, int bottom_width,
+                                int stride_vertical, int stride_horizontal, int window_height,
+                                int window_width, int pad_height, int pad_width, mnv_stream_t stream);
+int mnv_max_pooling_backward_idx(const float* top_diff, const unsigned char* idx, const float* relu_top,
+                                 float* bottom_diff, int num_images, int num_channels,
+                                 int bottom_height, int bottom_width, int stride_vertical,
+                                 int stride_horizontal, int window_height, int window_width,
+                                 int pad_height, int pad_width, mnv_stream_t stream);
+
 /* ---- fused momentum-SGD update (owl/net/net.py:252-256) ----------------
  * delta = mom*delta - (lr/batch)*grad - (lr*wd)*w ; w += delta    (20 B/param instead of the
  * reference's ten-op chain).  In place on w and delta. */

@@ -76,6 +76,7 @@ struct GemmParams {
   // each (partials + tail reduce), so the machine stays full -- 338 tiles on 148 SMs cost 2 + 1/3 waves instead of 3.
   int tail_first;       // first tile id (raster order) that is K-split; == m_tiles * n_tiles when there is no tail
   int tail_splits, tail_stages;
+  int pf_dist;          // L2 prefetch distance in k-stages for the TMA-fed operands (0 = none)
   int total_units;      // work items of the persistent loop: tail_first + (tiles - tail_first) * tail_splits, or tiles * splits
   int use_ktab;         // A_IM2COL_FWD: k -> (offset, kh, kw) table in shared memory
   int spi;              // backward-filter with TMA-fed top_diff: k-stages per image (K padded per image), else 0
@@ -592,6 +593,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// L2 prefetch of a box a few k-stages ahead: the smem ring covers ~1.5 us of TMA latency, less than an HBM round trip
+// under load, so operands that stream from HBM (FC weights, channels-last activation copies) are pulled into L2 early.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* tmap, int c, int w, int h, int n, int kw, int kh) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(static_cast<uint16_t>(kw)), "h"(static_cast<uint16_t>(kh))
+               : "memory");
+}
+
 // im2col-mode load: the box starts at pixel (w, h, n) of the (C, W, H, N) tensor -- a position of the filter
 // window's origin inside the bounding box the map was encoded with -- shifted by the tap offsets (kw, kh), and
 // walks `pixelsPerColumn` window positions along W, then H, then N; out-of-tensor elements arrive as zeros.
@@ -824,6 +839,30 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           }
         }
         for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
+          if (p.pf_dist > 0 && ks + p.pf_dist < t.ks_end) {   // pull the boxes of k-stage ks + pf_dist into L2
+            const int kp = ks + p.pf_dist;
+            if (AM == A_TMA) {
+              if (p.a_mode == TMA_A_IM2COL_K) {
+                const int tap = kp / p.cpt, cc = kp - tap * p.cpt, kh = tap / p.fw;
+#pragma unroll
+                for (int h = 0; h < kHalves; ++h) tma_prefetch_im2col_4d(&tmap_a, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
+              } else if (p.a_mode == TMA_A_TILED_MN) {
+#pragma unroll
+                for (int j = 0; j < kChunks; ++j) tma_prefetch_2d(&tmap_a, t.mt * kTileM + 32 * j, kp * BK);
+              } else if (p.a_mode == TMA_A_TILED_K) {
+#pragma unroll
+                for (int h = 0; h < kHalves; ++h) tma_prefetch_2d(&tmap_a, kp * BK, t.mt * kTileM + h * BM);
+              }
+            }
+            if (!(AM == A_TMA && p.b_mn)) {
+              const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;
+              for (int h = 0; h < halves; ++h) {
+                const int n0 = t.nt * p.bn + h * rows;
+                if (p.spi > 0) { const int img = kp / p.spi; tma_prefetch_3d(&tmap_b, (kp - img * p.spi) * BK, n0, img); }
+                else tma_prefetch_2d(&tmap_b, kp * BK, n0);
+              }
+            }
+          }
           mbar_wait(empty0 + 8 * stage, phase ^ 1, p.wait_hint);
           mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
           if (AM == A_TMA) {
@@ -1344,6 +1383,7 @@ __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __g
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static std::atomic<int> g_opt_pf_dist{0};      // TMA L2-prefetch distance in k-stages (0 = off)
 static std::atomic<int> g_opt_wait_hint{100};  // mbarrier.try_wait suspend hint in ns (tuning)
 static std::atomic<int> g_opt_no_wide{0};     // 1: never use the wide (bn > 256) tile (tuning)
 static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
@@ -1870,7 +1910,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -2030,6 +2070,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_klane") return g_opt_no_klane.exchange(value);
   if (k == "no_tall") return g_opt_no_tall.exchange(value);
   if (k == "no_s2d") return g_opt_no_s2d.exchange(value);
+  if (k == "pf_dist") return g_opt_pf_dist.exchange(value);
   if (k == "no_tail") return g_opt_no_tail.exchange(value);
   if (k == "no_shift") return g_opt_no_shift.exchange(value);
   if (k == "shift_dbg") return g_opt_shift_dbg.exchange(value);

@@ -64,3 +64,13 @@ class Pooler:
 
     def bp(self, y, ff_y, ff_x, relu=False):
         return NArray.pooling_backward(y, ff_y, ff_x, self.param, relu)
+
+    # arg-max remembering pair for 3x3/2 max pooling (not in the reference API): see mnv_max_pooling_*_idx
+    def idx_ok(self, shape):
+        return NArray.pooling_idx_ok(self.param, shape)
+
+    def ff_idx(self, x):
+        return NArray.pooling_forward_idx(x, self.param)
+
+    def bp_idx(self, y, idx, ff_y, bottom_shape, relu=False):
+        return NArray.pooling_backward_idx(y, idx, bottom_shape, self.param, ff_y if relu else None)

@@ -460,6 +460,38 @@ class NArray:
         return out
 
     @staticmethod
+    def pooling_idx_ok(info, shape):
+        """3x3 / stride 2 / pad 0 max pooling of planes that fit the staged kernel: what mnv_max_pooling_*_idx handle."""
+        W, H, C, N = shape
+        return (info.algorithm.value == 0 and
+                bool(_lib.load().mnv_max_pooling_idx_supported(N, C, H, W, *NArray._pool_args(info))))
+
+    @staticmethod
+    def pooling_forward_idx(src, info):
+        """Max pooling that also returns the arg-max bytes (a raw uint8 device buffer; not in the reference API)."""
+        W, H, C, N = src._shape
+        lib = _lib.load()
+        Ho = lib.mnv_pooled_size(H, info.pad_height, info.height, info.stride_vertical)
+        Wo = lib.mnv_pooled_size(W, info.pad_width, info.width, info.stride_horizontal)
+        dev = _rt.current_device()
+        out = NArray._new([Wo, Ho, C, N], dev)
+        idx = torch.empty(max(out.size, 1), dtype=torch.uint8, device=dev.device)
+        NArray._call("mnv_max_pooling_forward_idx", dev, src._on(dev).data_ptr(), out._t.data_ptr(), idx.data_ptr(), N, C, H, W,
+                     *NArray._pool_args(info))
+        return out, idx
+
+    @staticmethod
+    def pooling_backward_idx(diff, idx, bottom_shape, info, relu_top=None):
+        """Backward from (top_diff, arg-max bytes); relu_top (the pooled top) folds ReLU backward in."""
+        W, H, C, N = bottom_shape
+        dev = _rt.current_device()
+        out = NArray._new(bottom_shape, dev)
+        NArray._call("mnv_max_pooling_backward_idx", dev, diff._on(dev).data_ptr(), idx.data_ptr(),
+                     relu_top._on(dev).data_ptr() if relu_top is not None else None, out._t.data_ptr(), N, C, H, W,
+                     *NArray._pool_args(info))
+        return out
+
+    @staticmethod
     def lrn_forward(src, scale, local_size, alpha, beta):
         """`scale` is written in place, as in the reference (cuda.cpp:45-59; owl/net/net.py:496-500)."""
         W, H, C, N = src._shape

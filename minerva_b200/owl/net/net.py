@@ -134,17 +134,26 @@ class PoolingUnit(ComputeUnitSimple):
         self.geom = (kernel, kernel, stride, stride, pad, pad)
         self.pool = pool
 
+    use_idx = True    # Net.fuse_pool_index: 3x3/2 max pooling remembers its arg-max bytes for the backward pass
+
     def ff(self, x, phase):
         if not hasattr(self, "pooler"):
             co = self.B.co
             self.pooler = co.Pooler(*self.geom, op=co.pool_op.max if self.pool == "max" else co.pool_op.avg)
         self.ff_x = x
+        self.ff_idx = None
+        if self.use_idx and self.pool == "max" and hasattr(self.pooler, "ff_idx") and self.pooler.idx_ok(x.shape):
+            # backward reads 5 B per pooled element instead of re-reading the bottom (mnv_max_pooling_*_idx)
+            self.ff_y, self.ff_idx = self.pooler.ff_idx(x)
+            return self.ff_y
         self.ff_y = self.pooler.ff(x)
         return self.ff_y
 
     relu_bp = False   # set by Net._plan_fusion: ff_x is a ReLU output whose backward mask this unit applies
 
     def bp(self, y, phase):
+        if self.ff_idx is not None:
+            return self.pooler.bp_idx(y, self.ff_idx, self.ff_y, self.ff_x.shape, relu=self.relu_bp)
         if self.relu_bp:
             return self.pooler.bp(y, self.ff_y, self.ff_x, relu=True)
         return self.pooler.bp(y, self.ff_y, self.ff_x)
@@ -334,6 +343,7 @@ class Net(object):
         self.fuse_conv_relu = True   # False: run conv and ReLU as the reference's two ops
         self.fuse_relu_backward = True   # False: ReLU backward stays its own pass in front of LRN / max-pooling backward
         self.fuse_lrn_recompute = True   # False: LRN keeps the reference's (bottom, top, scale) three-array form
+        self.fuse_pool_index = True      # False: max pooling backward recomputes the arg-max from the bottom
 
     def add_unit(self, unit):
         unit.B = self.B
@@ -359,6 +369,8 @@ class Net(object):
         for u in self.units:
             if isinstance(u, LRNUnit):
                 u.lite = bool(self.fuse_lrn_recompute)
+            if isinstance(u, PoolingUnit):
+                u.use_idx = bool(self.fuse_pool_index)
 
         def readers_of(i, top):
             out = []

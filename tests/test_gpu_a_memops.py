@@ -197,6 +197,7 @@ POOL_CASES = [
     (4, 8, 55, 55, 2, 2, 3, 3, 0, 0), (4, 8, 27, 27, 2, 2, 3, 3, 0, 0), (4, 8, 13, 13, 2, 2, 3, 3, 0, 0),
     (4, 16, 24, 24, 2, 2, 2, 2, 0, 0), (4, 32, 12, 12, 3, 3, 3, 3, 0, 0), (2, 3, 14, 14, 2, 2, 3, 3, 0, 0),
     (2, 3, 7, 9, 1, 1, 3, 3, 1, 1), (2, 4, 14, 14, 3, 3, 5, 5, 0, 0), (2, 4, 7, 7, 1, 1, 7, 7, 0, 0),
+    (3, 5, 8, 11, 2, 2, 3, 3, 0, 0), (2, 3, 3, 3, 2, 2, 3, 3, 0, 0), (300, 7, 6, 6, 2, 2, 3, 3, 0, 0),   # 3x3/2: overhanging windows, one window, many planes
 ]
 
 
@@ -232,6 +233,27 @@ def test_pooling_bit_exact(g, case, relu_input):
             dfus = g.empty(x.size)
             g.run("mnv_max_pooling_backward_relu", dx, g.dev(want), dyd, dfus, N, C, H, W, sv, sh, wh, ww, ph, pw)
             g.assert_bits_equal(g.host(dfus), np.where(x > 0, wb, np.float32(0)).astype(np.float32), "max bwd + relu bwd")
+        if kind == "max" and (sv, sh, wh, ww, ph, pw) == (2, 2, 3, 3, 0, 0):
+            # arg-max remembering pair: same top, same bottom_diff, with and without the folded ReLU mask
+            import torch
+            out2 = g.empty(N * C * Ho * Wo)
+            idx = torch.full((N * C * Ho * Wo,), 77, dtype=torch.uint8, device="cuda")
+            g.run("mnv_max_pooling_forward_idx", dx, out2, idx, N, C, H, W, sv, sh, wh, ww, ph, pw)
+            g.assert_bits_equal(g.host(out2), want, "max fwd (idx variant)")
+            assert int(idx.max()) <= 8
+            didx = g.empty(x.size); didx.fill_(float("nan"))
+            g.run("mnv_max_pooling_backward_idx", dyd, idx, 0, didx, N, C, H, W, sv, sh, wh, ww, ph, pw)
+            g.assert_bits_equal(g.host(didx), wb, "max bwd from arg-max bytes")
+            if relu_input:
+                didx.fill_(float("nan"))
+                g.run("mnv_max_pooling_backward_idx", dyd, idx, out2, didx, N, C, H, W, sv, sh, wh, ww, ph, pw)
+                g.assert_bits_equal(g.host(didx), np.where(x > 0, wb, np.float32(0)).astype(np.float32), "max bwd from arg-max bytes + relu bwd")
+        elif kind == "max":
+            from minerva_b200._lib import MnvError
+            import torch
+            with pytest.raises(MnvError):
+                g.run("mnv_max_pooling_forward_idx", dx, g.empty(N * C * Ho * Wo), torch.empty(N * C * Ho * Wo, dtype=torch.uint8, device="cuda"),
+                      N, C, H, W, sv, sh, wh, ww, ph, pw)
 
 
 @pytest.mark.parametrize("N,C,H,W,size", [(2, 7, 3, 4, 5), (4, 96, 27, 27, 5), (2, 256, 13, 13, 5), (2, 5, 2, 3, 3),

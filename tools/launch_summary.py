@@ -39,7 +39,8 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append({"kernel": k, "launches": a[0], "time_us": a[1], "share": a[1] / tot, "dram_bytes_per_launch": a[2] / a[0],
                 "tensor_pipe_active_pct_time_weighted": tc})
 if len(sys.argv) > 2:
-    umma = [o for o in out if o["kernel"].startswith("umma_gemm_kernel")]
+    # the tcgen05 kernels: the persistent GEMM / implicit-GEMM kernel and the shift-GEMM convolution kernel
+    umma = [o for o in out if o["kernel"].startswith(("umma_gemm_kernel", "conv_shift_fwd_kernel"))]
     n = sum(o["launches"] for o in umma)
     json.dump({"source": sys.argv[1], "launches": len(launch), "total_us": tot, "kernels": out,
                "umma_gemm_kernel": {"launches": n, "share": sum(o["share"] for o in umma),

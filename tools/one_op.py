@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch one op a few times (for `ncu -k regex:... -s N -c M`).  Usage: one_op.py <name> [iters [KEY=INT ...]]
-names: conv{1..5}_{fwd,bwd,wgrad}, fc6_fwd, gemm8k, pool1_fwd, pool1_bwd, lrn1_fwd, lrn1_bwd, bias1"""
+names: conv{1..5}_{fwd,bwd,wgrad}, fc6_fwd, gemm8k, pool1_fwd, pool1_bwd, lrn1_fwd, lrn1_bwd, lrn1_fwd_lite, lrn1_bwd_lite, bias1"""
 import os
 import sys
 
@@ -63,7 +63,11 @@ elif name.startswith("lrn1"):
     C, H = 96, 55
     n = B * C * H * H
     x, sc, y, dy, dx = rnd(n), rnd(n).abs() + 1, rnd(n), rnd(n), rnd(n)
-    if name.endswith("fwd"):
+    if name.endswith("fwd_lite"):
+        fn = lambda: call("mnv_lrn_forward_lite", x, y, 5, 1e-4, 0.75, B, C, H, H)
+    elif name.endswith("bwd_lite"):
+        fn = lambda: call("mnv_lrn_backward_lite", x, dy, dx, 5, 1e-4, 0.75, B, C, H, H, 1)
+    elif name.endswith("fwd"):
         fn = lambda: call("mnv_lrn_forward", x, sc, y, 5, 1e-4, 0.75, B, C, H, H)
     else:
         fn = lambda: call("mnv_lrn_backward", x, y, sc, dy, dx, 5, 1e-4, 0.75, B, C, H, H)

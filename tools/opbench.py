@@ -119,6 +119,9 @@ if want("lrn"):
         x, sc, y, dy, dx = rnd(n), rnd(n), rnd(n), rnd(n), rnd(n)
         report("lrn_fwd C%d %dx%d" % (C, H, H), timeit(lambda: call("mnv_lrn_forward", x, sc, y, 5, 1e-4, 0.75, B, C, H, H)), bytes_=12 * n)
         report("lrn_bwd C%d %dx%d" % (C, H, H), timeit(lambda: call("mnv_lrn_backward", x, y, sc, dy, dx, 5, 1e-4, 0.75, B, C, H, H)), bytes_=20 * n)
+        # the scale-less pair owl.net uses: algorithmic bytes 8 and 12 per element
+        report("lrn_fwd_lite C%d %dx%d" % (C, H, H), timeit(lambda: call("mnv_lrn_forward_lite", x, y, 5, 1e-4, 0.75, B, C, H, H)), bytes_=8 * n)
+        report("lrn_bwd_lite+relu C%d %dx%d" % (C, H, H), timeit(lambda: call("mnv_lrn_backward_lite", x, dy, dx, 5, 1e-4, 0.75, B, C, H, H, 1)), bytes_=12 * n)
         del x, sc, y, dy, dx
 if want("bias"):
     for (C, H) in ((96, 55), (256, 27), (384, 13)):
