@@ -140,8 +140,9 @@ class ClockSampler(threading.Thread):
 def gemm_flops(name, a):
     if name in ("mnv_matmult", "mnv_matmult_ex"):
         return 2.0 * a[3] * a[4] * a[5]
-    if name in ("mnv_conv_forward", "mnv_conv_forward_relu", "mnv_conv_backward_data", "mnv_conv_backward_filter"):
-        off = 4 if name.startswith("mnv_conv_forward") else 3
+    if name in ("mnv_conv_forward", "mnv_conv_forward_relu", "mnv_conv_backward_data", "mnv_conv_backward_filter",
+                "mnv_conv_backward_filter_bias"):
+        off = 4 if name.startswith("mnv_conv_forward") or name.endswith("_bias") else 3
         N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = a[off:off + 11]
         Ho, Wo = (H + 2 * ph - fh) // sv + 1, (W + 2 * pw - fw) // sh + 1
         return 2.0 * N * Ho * Wo * Co * Ci * fh * fw

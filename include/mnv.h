@@ -252,6 +252,18 @@ int mnv_lrn_backward_relu(const float* bottom_data, const float* top_data, const
                           const float* top_diff, float* bottom_diff, int local_size, float alpha,
                           float beta, int num_img, int channel, int width, int height,
                           mnv_stream_t stream);
+/* Extension (fusion): ConvBackwardFilter + ConvBackwardBias in one call.  filter_diff is what
+ * mnv_conv_backward_filter writes (same kernels, bit-identical); bias_diff[c] = sum of top_diff over images and pixels
+ * is accumulated by the pre-pass that re-pitches top_diff for the tensor maps (odd plane sizes: every AlexNet /
+ * GoogLeNet layer), so the separate 4 B-per-element reduction disappears; with 16-byte-pitched planes or without a
+ * workspace it falls back to mnv_conv_backward_bias.  owl.net's ConvConnection.bp asks for both gradients at once
+ * (owl/owl/net/net.py:700-716 issues two ops). */
+int mnv_conv_backward_filter_bias(const float* bottom, const float* top_diff, float* filter_diff,
+                                  float* bias_diff, int num_images, int bottom_num_channels,
+                                  int top_num_channels, int bottom_height, int bottom_width,
+                                  int pad_height, int pad_width, int stride_vertical,
+                                  int stride_horizontal, int filter_height, int filter_width,
+                                  void* workspace, size_t workspace_bytes, mnv_stream_t stream);
 /* Extension (recompute instead of re-read): LRN without the `scale` array.  The forward pass writes only
  * `res` (8 B per element instead of 12); the backward pass reads only bottom and top_diff (12 B instead of 20) and
  * recomputes scale and top in registers with the forward pass's exact operation sequence, so bottom_diff is

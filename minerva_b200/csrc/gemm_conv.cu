@@ -1682,8 +1682,12 @@ static bool make_dy_tmap(CUtensorMap* tm, const float* dy, int P, int pitch, int
   return r == CUDA_SUCCESS;
 }
 
-// row-pitch repack for TMA: dst[r][0..inner) = src[r][0..inner), dst rows `pitch` floats apart
-__global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int inner, int pitch, size_t rows, int round) {
+// row-pitch repack for TMA: dst[r][0..inner) = src[r][0..inner), dst rows `pitch` floats apart.  rowsum != null: the
+// pass also leaves each row's sum (of the unrounded values) in rowsum[r] -- for top_diff rows (image, channel) that is
+// the per-image bias gradient, folded over the images by rowsum_fold_kernel (ConvBackwardBias for free: the 4 B per
+// element its own kernel would re-read are already in registers here).
+__global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int inner, int pitch, size_t rows, int round,
+                                                         float* __restrict__ rowsum) {
   // one warp per row keeps both sides coalesced without integer division
   size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
@@ -1691,9 +1695,23 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
   for (size_t r = warp; r < rows; r += nwarps) {
     const float* s = src + r * inner;
     float* d = dst + r * pitch;
-    if (round) for (int i = lane; i < inner; i += 32) d[i] = to_tf32(__ldg(s + i));
-    else for (int i = lane; i < inner; i += 32) d[i] = __ldg(s + i);
+    float acc = 0.f;
+    if (round) for (int i = lane; i < inner; i += 32) { const float v = __ldg(s + i); d[i] = to_tf32(v); acc += v; }
+    else for (int i = lane; i < inner; i += 32) { const float v = __ldg(s + i); d[i] = v; acc += v; }
+    if (rowsum) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) rowsum[r] = acc;
+    }
   }
+}
+// db[c] = sum over images, in image order, of rowsum[n * C + c]
+__global__ void __launch_bounds__(128) rowsum_fold_kernel(const float* __restrict__ rowsum, float* __restrict__ db, int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc += __ldg(rowsum + static_cast<size_t>(n) * C + c);
+  db[c] = acc;
 }
 
 // SMs the persistent tensor-core kernel may occupy.  It runs one CTA per SM for the whole launch, so when another
@@ -1856,7 +1874,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
     size_t need = (static_cast<size_t>(p.N) * pitch * sizeof(float) + 255) / 256 * 256;
     if (ws_bytes >= need) {
       float* packed = static_cast<float*>(ws);
-      repitch_kernel<<<stream_grid(static_cast<size_t>(p.N) * 32), kBlock, 0, s>>>(p.b, packed, p.K, pitch, static_cast<size_t>(p.N), prepass_round());
+      repitch_kernel<<<stream_grid(static_cast<size_t>(p.N) * 32), kBlock, 0, s>>>(p.b, packed, p.K, pitch, static_cast<size_t>(p.N), prepass_round(), nullptr);
       int rc0 = finish_launch();
       if (rc0) return rc0;
       p.b = packed; p.ldb = pitch; p.b_vec = 1;
@@ -2260,9 +2278,38 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
   return launch_gemm<A_IM2COL_BWD, B_KMAJOR>(p, ws2, ws2_bytes, as_stream(stream));
 }
 
+static int conv_backward_filter_impl(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
+                                     int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                                     size_t workspace_bytes, mnv_stream_t stream, float* bias_diff, bool* bias_done);
 int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
                              int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
                              size_t workspace_bytes, mnv_stream_t stream) {
+  bool unused = false;
+  return conv_backward_filter_impl(bottom, top_diff, filter_diff, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes,
+                                   stream, nullptr, &unused);
+}
+int mnv_conv_backward_filter_bias(const float* bottom, const float* top_diff, float* filter_diff, float* bias_diff, int N,
+                                  int Ci, int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw,
+                                  void* workspace, size_t workspace_bytes, mnv_stream_t stream) {
+  if (!bias_diff) return MNV_EINVAL;
+  int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
+  if (rc) return rc;
+  if (N == 0) {
+    rc = mnv_fill(bias_diff, static_cast<size_t>(Co), 0.f, stream);
+    if (rc) return rc;
+  }
+  bool bias_done = false;
+  rc = conv_backward_filter_impl(bottom, top_diff, filter_diff, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes,
+                                 stream, bias_diff, &bias_done);
+  if (rc || bias_done || N == 0) return rc;
+  // top_diff needed no re-pitch (16-byte rows) or there was no workspace: the stand-alone reduction
+  return mnv_conv_backward_bias(top_diff, bias_diff, N, Co, (H + 2 * ph - fh) / sv + 1, (W + 2 * pw - fw) / sh + 1, workspace,
+                                workspace_bytes, stream);
+}
+static int conv_backward_filter_impl(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
+                                     int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                                     size_t workspace_bytes, mnv_stream_t stream, float* bias_diff, bool* bias_done) {
+  *bias_done = false;
   int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
   if (rc) return rc;
   if (!bottom || !top_diff || !filter_diff) return MNV_EINVAL;
@@ -2293,11 +2340,21 @@ int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* 
     if (ws_left < need) return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, s);
     float* packed = reinterpret_cast<float*>(ws);
     size_t rows = static_cast<size_t>(N) * Co;
-    repitch_kernel<<<stream_grid(rows * 32), kBlock, 0, s>>>(top_diff, packed, P, pitch, rows, prepass_round());
+    ws += need; ws_left -= need;
+    // the bias gradient rides on this pass: per-(image, channel) sums, folded over the images afterwards
+    float* rowsum = nullptr;
+    const size_t rs_bytes = round256(rows * sizeof(float));
+    if (bias_diff && ws_left >= rs_bytes) { rowsum = reinterpret_cast<float*>(ws); ws += rs_bytes; ws_left -= rs_bytes; }
+    repitch_kernel<<<stream_grid(rows * 32), kBlock, 0, s>>>(top_diff, packed, P, pitch, rows, prepass_round(), rowsum);
     rc = finish_launch();
     if (rc) return rc;
+    if (rowsum) {
+      rowsum_fold_kernel<<<(Co + 127) / 128, 128, 0, s>>>(rowsum, bias_diff, N, Co);
+      rc = finish_launch();
+      if (rc) return rc;
+      *bias_done = true;
+    }
     dy_tma = packed;
-    ws += need; ws_left -= need;
   }
   p.spi = (P + BK - 1) / BK;
   long long kpad = static_cast<long long>(N) * p.spi * BK;

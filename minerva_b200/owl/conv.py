@@ -51,6 +51,10 @@ class Convolver:
     def weight_grad(self, y, x, w):
         return NArray.conv_backward_filter(y, x, w, self.param)
 
+    def weight_bias_grad(self, y, x, w):
+        """(weight_grad, bias_grad) from one call (not in the reference API): the bias sums ride on a pre-pass of weight_grad."""
+        return NArray.conv_backward_filter_bias(y, x, w, self.param)
+
     def bias_grad(self, y):
         return NArray.conv_backward_bias(y)
 

@@ -403,6 +403,19 @@ class NArray:
         return out
 
     @staticmethod
+    def conv_backward_filter_bias(diff, bottom, filt, info):
+        """Both parameter gradients of a convolution in one call (not in the reference API): mnv_conv_backward_filter_bias."""
+        W, H, Ci, N = bottom._shape
+        fw, fh, _, Co = filt._shape
+        _check(diff._shape[3] == N, "#images mismatch")
+        dev = _rt.current_device()
+        dw, db = NArray._new(filt._shape, dev), NArray._new([Co], dev)
+        NArray._call("mnv_conv_backward_filter_bias", dev, bottom._on(dev).data_ptr(), diff._on(dev).data_ptr(),
+                     dw._t.data_ptr(), db._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
+                     info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
+        return dw, db
+
+    @staticmethod
     def conv_backward_bias(diff):
         W, H, C, N = diff._shape
         dev = _rt.current_device()

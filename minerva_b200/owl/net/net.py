@@ -282,9 +282,14 @@ class ConvConnection(WeightedComputeUnit):
             return self.convolver.ff(act, self.weight, self.bias, relu=True)
         return self.convolver.ff(act, self.weight, self.bias)
 
+    fuse_grads = True    # Net.fuse_conv_grads: weight and bias gradient from one call (mnv_conv_backward_filter_bias)
+
     def bp(self, sen, phase):
-        self.weightgrad = self.convolver.weight_grad(sen, self.ff_act, self.weight)
-        self.biasgrad = self.convolver.bias_grad(sen)
+        if self.fuse_grads and hasattr(self.convolver, "weight_bias_grad"):
+            self.weightgrad, self.biasgrad = self.convolver.weight_bias_grad(sen, self.ff_act, self.weight)
+        else:
+            self.weightgrad = self.convolver.weight_grad(sen, self.ff_act, self.weight)
+            self.biasgrad = self.convolver.bias_grad(sen)
         if not self.need_bp:
             return None
         return self.convolver.bp(sen, self.ff_act, self.weight)
@@ -344,6 +349,7 @@ class Net(object):
         self.fuse_relu_backward = True   # False: ReLU backward stays its own pass in front of LRN / max-pooling backward
         self.fuse_lrn_recompute = True   # False: LRN keeps the reference's (bottom, top, scale) three-array form
         self.fuse_pool_index = True      # False: max pooling backward recomputes the arg-max from the bottom
+        self.fuse_conv_grads = True      # False: ConvBackwardFilter and ConvBackwardBias stay two ops
 
     def add_unit(self, unit):
         unit.B = self.B
@@ -371,6 +377,8 @@ class Net(object):
                 u.lite = bool(self.fuse_lrn_recompute)
             if isinstance(u, PoolingUnit):
                 u.use_idx = bool(self.fuse_pool_index)
+            if isinstance(u, ConvConnection):
+                u.fuse_grads = bool(self.fuse_conv_grads)
 
         def readers_of(i, top):
             out = []

@@ -219,6 +219,30 @@ def test_conv_tail_split(g, case):
         assert g.norm_rel(g.host(dx), wdx) < TOL, "backward data, no_tail=%d" % no_tail
 
 
+@pytest.mark.parametrize("case", [CONV_CASES[1], CONV_CASES[4], CONV_CASES[10], TMA_CASES[5], (3, 8, 12, 10, 10, 1, 1, 1, 1, 3, 3),
+                                  (2, 16, 20, 8, 8, 0, 0, 1, 1, 1, 1)])
+def test_conv_backward_filter_bias_fused(g, case):
+    """mnv_conv_backward_filter_bias: filter_diff bit-identical to mnv_conv_backward_filter, bias_diff within the
+    reduction tolerance of the oracle -- on the re-pitch path (odd planes), the 16-byte-pitched fallback (10x10, 8x8
+    planes) and without a workspace."""
+    N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = case
+    Ho, Wo = orc.conv_out(H, ph, fh, sv), orc.conv_out(W, pw, fw, sh)
+    x = rng.normal(0, 1, N * Ci * H * W).astype(np.float32)
+    dy = rng.normal(0.1, 1, N * Co * Ho * Wo).astype(np.float32)
+    geo = (N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw)
+    want_db = orc.conv_backward_bias(dy, N, Co, Ho, Wo)
+    l1 = np.abs(dy.astype(np.float64)).reshape(N, Co, Ho * Wo).sum((0, 2))
+    ws = g.workspace()
+    for wsp, wsb in ((ws, ws.numel()), (0, 0)):
+        dw = g.empty(Co * Ci * fh * fw); dw.fill_(float("nan"))
+        g.run("mnv_conv_backward_filter", g.dev(x), g.dev(dy), dw, *geo, wsp, wsb)
+        dw2 = g.empty(dw.numel()); dw2.fill_(float("nan"))
+        db = g.empty(Co); db.fill_(float("nan"))
+        g.run("mnv_conv_backward_filter_bias", g.dev(x), g.dev(dy), dw2, db, *geo, wsp, wsb)
+        assert np.array_equal(g.host(dw), g.host(dw2))
+        assert np.all(np.abs(g.host(db).astype(np.float64) - want_db) <= 1e-5 * l1)
+
+
 S2D_CASES = [CONV_CASES[4], CONV_CASES[8]] + CONV_CASES[13:] + [
     (3, 3, 96, 59, 63, 0, 0, 4, 4, 11, 11),    # several 256-position tiles per image, tiles straddling images
     (2, 3, 128, 40, 40, 1, 2, 4, 4, 9, 10),    # 128 filters (the kernel's widest tile), pad, filter not a stride multiple
