@@ -1705,13 +1705,31 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
     }
   }
 }
-// db[c] = sum over images, in image order, of rowsum[n * C + c]
-__global__ void __launch_bounds__(128) rowsum_fold_kernel(const float* __restrict__ rowsum, float* __restrict__ db, int N, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc += __ldg(rowsum + static_cast<size_t>(n) * C + c);
-  db[c] = acc;
+// db[c] = sum over the images of rowsum[n * C + c].  A CTA folds 32 channels: 8 threads per channel take every 8th
+// image (independent loads, 128 B per warp), then the 8 partial sums are added in lane order -- a fixed order, so the
+// result is deterministic (a single thread walking all N images was latency-bound: 26 us per call).
+__global__ void __launch_bounds__(256) rowsum_fold_kernel(const float* __restrict__ rowsum, float* __restrict__ db, int N, int C) {
+  __shared__ float part[8][33];
+  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C) {
+    int n = nl;
+    for (; n + 24 < N; n += 32) {
+      a0 += __ldg(rowsum + static_cast<size_t>(n) * C + c);
+      a1 += __ldg(rowsum + static_cast<size_t>(n + 8) * C + c);
+      a2 += __ldg(rowsum + static_cast<size_t>(n + 16) * C + c);
+      a3 += __ldg(rowsum + static_cast<size_t>(n + 24) * C + c);
+    }
+    for (; n < N; n += 8) a0 += __ldg(rowsum + static_cast<size_t>(n) * C + c);
+  }
+  part[nl][cl] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (nl == 0 && c < C) {
+    float acc = part[0][cl];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) acc += part[i][cl];
+    db[c] = acc;
+  }
 }
 
 // SMs the persistent tensor-core kernel may occupy.  It runs one CTA per SM for the whole launch, so when another
@@ -2349,7 +2367,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
     rc = finish_launch();
     if (rc) return rc;
     if (rowsum) {
-      rowsum_fold_kernel<<<(Co + 127) / 128, 128, 0, s>>>(rowsum, bias_diff, N, Co);
+      rowsum_fold_kernel<<<(Co + 31) / 32, 256, 0, s>>>(rowsum, bias_diff, N, Co);
       rc = finish_launch();
       if (rc) return rc;
       *bias_done = true;
