@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--unfused-update", action="store_true", help="use the reference's ten-op SGD chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--merge", default="auto", choices=["auto", "peer", "nccl", "off"], help="N>1 gradient merge (owl/net/merge.py)")
     ap.add_argument("--nccl-ctas", type=int, default=0,
                     help="N>1: SMs left to NCCL (NCCL_MAX_CTAS) and kept out of the persistent tensor-core kernel's grid; 0 = do not manage")
     ap.add_argument("--mnv-opt", action="append", default=[], metavar="KEY=INT",
@@ -267,7 +268,7 @@ def main():
     x, onehot = host_batch(wl, net.input_shape, batch, 100 + rank)
     du = net.get_data_unit()
     du.data, du.label = owl.from_numpy(x), owl.from_numpy(onehot)
-    trainer = onet.NetTrainer(net, dist if world > 1 else None, fused_update=not args.unfused_update)
+    trainer = onet.NetTrainer(net, dist if world > 1 else None, fused_update=not args.unfused_update, merge=args.merge)
     gdev = rt.current_device()
 
     def sync_all():
@@ -412,7 +413,7 @@ def main():
             "config": {"workload": wl["name"], "global_batch": batch * world, "per_gpu_batch": batch,
                        "parallelism": "dp%d" % world, "update": "chain" if args.unfused_update else "fused momentum-SGD kernel",
                        "l2": "working set per step (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                       "gradient_merge": "NCCL all-reduce per weighted unit, overlapped with backward" if world > 1 else "none (1 GPU)",
+                       "gradient_merge": trainer.merge_kind, **({"gradient_merge_note": trainer.merge_note} if hasattr(trainer, "merge_note") else {}),
                        **({"tuning": args.mnv_opt} if args.mnv_opt else {})},
             "clocks": sampler.summary(), "gpu_launches": int(launches), "loss": float(loss),
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,

@@ -113,7 +113,23 @@ class NArray:
     @staticmethod
     def _new(shape, dev=None):
         dev = dev or _rt.current_device()
+        if NArray._placed:       # place_next(): this result goes into a caller-owned buffer
+            t = NArray._placed.pop(0)
+            if t.numel() != max(_prod(shape), 0):
+                NArray._placed = []
+                raise _lib.MnvError("place_next: the next result has %d elements, the buffer %d" % (_prod(shape), t.numel()))
+            return NArray(t, shape, dev)
         return NArray(torch.empty(max(_prod(shape), 0), dtype=torch.float32, device=dev.device), shape, dev)
+
+    _placed = []
+
+    @staticmethod
+    def place_next(*tensors):
+        """The next len(tensors) results allocated by NArray ops are written straight into these flat fp32 device
+        buffers (in order) instead of fresh memory.  Used by the data-parallel trainer so that gradients are produced
+        inside the peer-mapped merge buffer (owl/net/merge.py) -- the role of the reference's explicit output DataShards
+        (op/compute_fn.h:9-12), which owl's value-semantics API otherwise hides."""
+        NArray._placed = list(tensors)
 
     def _on(self, dev):
         """Pull a remote input onto `dev` (the reference's DoCopyRemoteData, device.cpp:75-91,209-212)."""

@@ -59,6 +59,13 @@ class WeightedComputeUnit(ComputeUnitSimple):
         self.fan_in = self.fan_out = 1
         self.need_bp = True     # first layer: the data gradient is not needed (owl.net computes it anyway)
 
+    grad_out = None      # (flat fp32 buffer for weightgrad, for biasgrad): set by the data-parallel trainer's peer merge
+
+    def _place_grads(self):
+        """The two results computed next (weight gradient, then bias gradient) are written into `grad_out`."""
+        if self.grad_out is not None:
+            self.B.owl.NArray.place_next(*self.grad_out)
+
     def init_weights_with_filler(self):
         """net.py:196-238.  Gaussian fillers are drawn on the device; xavier (uniform) on the host with
         numpy, as the reference does, then uploaded."""
@@ -253,6 +260,7 @@ class FullyConnection(WeightedComputeUnit):
 
     def bp(self, sen, phase):
         shp = self.ff_act.shape
+        self._place_grads()
         self.weightgrad = sen * self.ff_a2d.trans()
         self.biasgrad = sen.sum(1)
         if not self.need_bp:
@@ -285,6 +293,7 @@ class ConvConnection(WeightedComputeUnit):
     fuse_grads = True    # Net.fuse_conv_grads: weight and bias gradient from one call (mnv_conv_backward_filter_bias)
 
     def bp(self, sen, phase):
+        self._place_grads()
         if self.fuse_grads and hasattr(self.convolver, "weight_bias_grad"):
             self.weightgrad, self.biasgrad = self.convolver.weight_bias_grad(sen, self.ff_act, self.weight)
         else:

@@ -12,23 +12,66 @@ import time
 
 
 class NetTrainer(object):
-    def __init__(self, net, dist=None, fused_update=True):
+    def __init__(self, net, dist=None, fused_update=True, merge="auto"):
         """dist: an initialised torch.distributed module (or None for 1 GPU).
-        fused_update: one mnv_sgd_momentum_update per tensor instead of the reference's op chain."""
+        fused_update: one mnv_sgd_momentum_update per tensor instead of the reference's op chain.
+        merge: "peer" = reduce-scatter / all-gather over NVLink peer memory on the copy engines (merge.py),
+               "nccl" = one NCCL all-reduce per gradient, "auto" = peer when the process group is NCCL on CUDA and the
+               symmetric-memory rendezvous works, else nccl (gloo in the CPU tests)."""
         self.net = net
         self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
         self.world = self.dist.get_world_size() if self.dist else 1
         self.fused_update = fused_update
         self._pending = []
+        self.peer = None
+        self.merge_kind = "none (1 GPU)"
+        if self.dist:
+            self.merge_kind = "NCCL all-reduce per weighted unit, overlapped with backward"
+            if merge in ("auto", "peer") and self.dist.get_backend() == "nccl":
+                try:
+                    from .merge import PeerGradMerge
+                    import minerva_b200.owl._runtime as rt
+                    self.peer = PeerGradMerge(net, self.dist, rt.current_device())
+                    self.merge_kind = ("reduce-scatter + all-gather over NVLink peer (symmetric) memory on the copy engines, "
+                                       "per bucket, overlapped with backward; local shard sum = the only kernel")
+                except Exception as ex:     # no symmetric-memory support in this build / topology
+                    if merge == "peer":
+                        raise
+                    self.peer = None
+                    self.merge_note = "peer merge unavailable: %r" % (ex,)
         net.on_weight_grad = self._on_weight_grad if self.dist else None
+        if merge == "off" and self.dist:      # diagnostics only: replicas drift apart; measures the step without any exchange
+            net.on_weight_grad, self.peer = None, None
+            self.merge_kind = "OFF (diagnostic run, not data-parallel training)"
 
     # -- gradient merge -------------------------------------------------------------------------
     def _on_weight_grad(self, unit):
+        if self.peer is not None:
+            try:
+                self.peer.on_weight_grad(unit)
+                return
+            except Exception as ex:
+                if self.peer.flat is not None:
+                    raise           # half-way through a step: nothing sane to fall back to
+                self._peer_failed(ex)
         d = self.dist
         for g in (unit.weightgrad, unit.biasgrad):
             self._pending.append(d.all_reduce(g.as_torch(), op=d.ReduceOp.SUM, async_op=True))
 
+    def _peer_failed(self, ex):
+        self.peer = None
+        self.merge_kind = "NCCL all-reduce per weighted unit, overlapped with backward"
+        self.merge_note = "peer merge unavailable: %r" % (ex,)
+
     def _wait_merge(self):
+        if self.peer is not None:
+            try:
+                self.peer.finish_step()
+            except Exception as ex:
+                if self.peer.flat is not None:
+                    raise
+                # the rendezvous failed while building the layout: this step's gradients were already all-reduced
+                self._peer_failed(ex)
         for w in self._pending:
             w.wait()
         self._pending = []
@@ -36,6 +79,8 @@ class NetTrainer(object):
     # -- one iteration ------------------------------------------------------------------------------
     def step(self):
         net = self.net
+        if self.peer is not None:
+            self.peer.begin_step()
         net.forward("TRAIN")
         net.backward("TRAIN")
         self._wait_merge()

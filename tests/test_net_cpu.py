@@ -135,3 +135,31 @@ def test_data_parallel_matches_single_process(tmp_path):
     a, b = np.load(f1), np.load(f2)
     assert np.abs(a[0] - b[0]).max() <= 1e-5 * np.abs(a[0]).max()
     assert np.abs(a[1] - b[1]).max() <= 1e-5 * np.abs(a[1]).max()
+
+
+def test_peer_merge_layout():
+    """owl/net/merge.py plan_layout: slices are disjoint, 16-byte aligned, in backward order; every bucket splits into
+    `world` shards of whole vectors; the FC gradients close the first bucket and the last unit has a bucket of its own."""
+    from minerva_b200.owl.net.merge import plan_layout
+    sizes = [("fc8", 4096000, 1000), ("fc7", 16777216, 4096), ("fc6", 37748736, 4096), ("conv5", 884736, 256),
+             ("conv4", 1327104, 384), ("conv3", 884736, 384), ("conv2", 614400, 256), ("conv1", 34848, 96)]
+    for world in (2, 3, 8):
+        slices, buckets, total = plan_layout(sizes, world, last_fc=2)
+        assert [b[2] for b in buckets] == ["fc6", "conv2", "conv1"]
+        spans = sorted((o, o + n) for o, n in slices.values())
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and all(o % 4 == 0 for o, _ in spans)
+        pos = 0
+        for off, n, last in buckets:
+            assert off == pos and n % (4 * world) == 0
+            pos += n
+        assert pos == total
+        for (name, tag), (o, n) in slices.items():       # a slice lies inside the bucket its unit closes or precedes
+            b = [i for i, (bo, bn, _) in enumerate(buckets) if bo <= o and o + n <= bo + bn]
+            assert len(b) == 1
+        fc_bytes = sum(n for (name, tag), (o, n) in slices.items() if name.startswith("fc"))
+        assert buckets[0][1] >= fc_bytes
+    # no fully-connected unit, two units: the first unit and the last one
+    slices, buckets, total = plan_layout([("c2", 10, 2), ("c1", 7, 1)], 2, last_fc=-1)
+    assert [b[2] for b in buckets] == ["c2", "c1"]
+    slices, buckets, total = plan_layout([("only", 5, 1)], 4, last_fc=0)
+    assert len(buckets) == 1 and buckets[0][1] % 16 == 0
