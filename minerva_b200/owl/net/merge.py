@@ -84,12 +84,12 @@ class PeerGradMerge(object):
         for u, _, _ in order:     # from now on the units compute their gradients straight into `flat`
             u.grad_out = tuple(self.flat[o:o + n] for o, n in (self.slices[(u.name, "w")], self.slices[(u.name, "b")]))
         torch.cuda.synchronize(self.dev.device)
-        self.dist.barrier()
 
     # -- per step -------------------------------------------------------------------------------------------------
     def begin_step(self):
         self._arrived = 0
         self._first = []
+        self.net.B.owl.NArray.place_next()      # no stale placement survives an aborted step
 
     def on_weight_grad(self, unit):
         """Called by Net.backward as soon as `unit`'s gradients exist (compute stream)."""
@@ -158,7 +158,22 @@ class PeerGradMerge(object):
             for u, gw, gb in self._first:
                 d.all_reduce(gw.as_torch(), op=d.ReduceOp.SUM)
                 d.all_reduce(gb.as_torch(), op=d.ReduceOp.SUM)
-            self._build(self._first)
+            # the switch to the peer exchange is collective: if the symmetric allocation / rendezvous fails on ANY
+            # rank, every rank stays on the NCCL merge (a split decision would deadlock the first barrier)
+            err = None
+            try:
+                self._build(self._first)
+            except Exception as ex:
+                err = ex
+                self.flat = None
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.dev.device)
+            d.all_reduce(ok, op=d.ReduceOp.MIN)
             self._first = []
+            if int(ok.item()) == 0:
+                self.flat = None
+                for u in self.net.units:
+                    if getattr(u, "grad_out", None) is not None:
+                        u.grad_out = None
+                raise RuntimeError("peer merge not available on every rank: %r" % (err,))
             return
         self.dev.stream.wait_event(self.done)
