@@ -198,6 +198,7 @@ POOL_CASES = [
     (4, 16, 24, 24, 2, 2, 2, 2, 0, 0), (4, 32, 12, 12, 3, 3, 3, 3, 0, 0), (2, 3, 14, 14, 2, 2, 3, 3, 0, 0),
     (2, 3, 7, 9, 1, 1, 3, 3, 1, 1), (2, 4, 14, 14, 3, 3, 5, 5, 0, 0), (2, 4, 7, 7, 1, 1, 7, 7, 0, 0),
     (3, 5, 8, 11, 2, 2, 3, 3, 0, 0), (2, 3, 3, 3, 2, 2, 3, 3, 0, 0), (300, 7, 6, 6, 2, 2, 3, 3, 0, 0),   # 3x3/2: overhanging windows, one window, many planes
+    (1, 2, 70, 131, 2, 2, 3, 3, 0, 0), (2, 3, 9, 64, 2, 2, 3, 3, 0, 0), (2, 2, 5, 4, 2, 2, 3, 3, 0, 0),    # wider than 64 columns (thread-per-block kernel), exactly 64, tiny
 ]
 
 

@@ -112,7 +112,11 @@ if want("pool"):
         ein, eout = x.numel(), y.numel()
         report("max_pool_fwd 3x3/2 C%d %d->%d" % (C, H, Ho), timeit(lambda: call("mnv_max_pooling_forward", x, y, B, C, H, H, 2, 2, 3, 3, 0, 0)), bytes_=4 * (ein + eout))
         report("max_pool_bwd 3x3/2 C%d %d->%d" % (C, H, Ho), timeit(lambda: call("mnv_max_pooling_backward", x, y, dy, dx, B, C, H, H, 2, 2, 3, 3, 0, 0)), bytes_=4 * (2 * ein + 2 * eout))
-        del x, y, dy, dx
+        # the arg-max remembering pair owl.net uses (5 B per pooled element on both sides instead of re-reading the bottom)
+        idx = torch.empty(eout, dtype=torch.uint8, device="cuda")
+        report("max_pool_fwd_idx 3x3/2 C%d %d->%d" % (C, H, Ho), timeit(lambda: call("mnv_max_pooling_forward_idx", x, y, idx, B, C, H, H, 2, 2, 3, 3, 0, 0)), bytes_=4 * ein + 5 * eout)
+        report("max_pool_bwd_idx+relu 3x3/2 C%d %d->%d" % (C, H, Ho), timeit(lambda: call("mnv_max_pooling_backward_idx", dy, idx, y, dx, B, C, H, H, 2, 2, 3, 3, 0, 0)), bytes_=9 * eout + 4 * ein)
+        del x, y, dy, dx, idx
 if want("lrn"):
     for (C, H) in ((96, 55), (256, 27)):
         n = B * C * H * H
