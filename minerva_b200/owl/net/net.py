@@ -327,6 +327,14 @@ class SoftmaxUnit(ComputeUnit):
         res = lossmat.sum(0).sum(1).to_numpy()
         return -float(res.reshape(-1)[0]) / lossmat.shape[1]
 
+    def getloss_device(self):
+        """The same reduction left on the device: -> (1-element NArray holding sum(ln(y) o label), batch size).  The
+        caller reads it back when it chooses to (a training loop that logs the loss one step late never drains the
+        launch queue; the reference's trainer prints losses from asynchronously evaluated NArrays the same way,
+        owl/owl/net/trainer.py:139-146)."""
+        lossmat = self.B.ele.mult(self.B.ele.ln(self.ff_y), self.y)
+        return lossmat.sum(0).sum(1), lossmat.shape[1]
+
 
 class DataUnit(ComputeUnit):
     """Synthetic data layer: the caller sets `.data` / `.label` (owl NArrays) before forward."""

@@ -56,6 +56,8 @@ def test_numeric_gradient_of_the_graph():
     net.forward("TEST")          # TEST: no dropout, deterministic
     net.backward("TEST")
     loss_unit = net.get_loss_units()[0]
+    dsum, n = loss_unit.getloss_device()      # the reduction left on the device == the blocking getloss()
+    assert abs(-float(dsum.to_numpy().reshape(-1)[0]) / n - loss_unit.getloss()) <= 1e-6 * abs(loss_unit.getloss())
     for uname, idxs in (("fc8", [0, 7, 33]), ("conv2", [1, 50, 200]), ("conv1", [0, 11, 100])):
         u = net.units[net.name_to_uid[uname]]
         g = u.weightgrad.a.copy()
