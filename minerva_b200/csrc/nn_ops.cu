@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(kBlock) maxpool332_bwd_idx_kernel(const float*
 }
 
 constexpr int kPoolSmemMax = 96 * 1024;      // opt-in dynamic shared memory ceiling for the staged kernels
+constexpr int kPoolSmemBig = 200 * 1024;     // ceiling for the double-buffered 3x3/2 kernels (GoogLeNet pool1: two 50 KB planes per CTA)
 constexpr int kPoolSmemTarget = 24 * 1024;   // aim: ~6K floats per CTA pass, several CTAs per SM
 
 // planes per CTA pass for `per_plane` floats of staging; 0 => does not fit, use the global-memory kernel
@@ -606,7 +607,7 @@ static int pool_group(size_t per_plane_floats, size_t planes, size_t max_index) 
 template <class K>
 static int pool_smem_attr(K kernel, size_t bytes) {
   if (bytes <= 48 * 1024) return MNV_OK;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemMax);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBig);
   return e == cudaSuccess ? MNV_OK : static_cast<int>(e);
 }
 static int pool_grid(size_t planes, int G) {
@@ -1117,7 +1118,7 @@ static int launch_pool_fwd(const float* x, float* y, size_t planes, const PoolGe
     int rc = pool_smem_attr(pool_fwd_smem_kernel<IS_MAX>, bytes);
     if (rc) return rc;
     const size_t bytes2 = 2 * ((per * G + 4 + 3) & ~static_cast<size_t>(3)) * sizeof(float);   // double-buffered staging
-    if (IS_MAX && g.wh == 3 && g.ww == 3 && g.sv == 2 && g.sh == 2 && g.ph == 0 && g.pw == 0 && bytes2 <= static_cast<size_t>(kPoolSmemMax)) {
+    if (IS_MAX && g.wh == 3 && g.ww == 3 && g.sv == 2 && g.sh == 2 && g.ph == 0 && g.pw == 0 && bytes2 <= static_cast<size_t>(kPoolSmemBig)) {
       const bool fit = (g.Ho - 1) * 2 + 3 <= g.H && (g.Wo - 1) * 2 + 3 <= g.W;
       if (fit) {
         rc = pool_smem_attr(maxpool332_fwd_kernel<false>, bytes2);
@@ -1233,7 +1234,7 @@ static int max_pooling_backward_impl(const float* x, const float* y, const float
       // double-buffered (x, dy) staging + one arg-max plane
       const size_t HW_ = static_cast<size_t>(H) * W, HoWo_ = static_cast<size_t>(g.Ho) * g.Wo;
       const size_t bytes2 = (2 * (((G * HW_ + 4 + 3) & ~static_cast<size_t>(3)) + ((G * HoWo_ + 4 + 3) & ~static_cast<size_t>(3))) + G * HoWo_) * sizeof(float);
-      if (wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0 && bytes2 <= static_cast<size_t>(kPoolSmemMax)) {
+      if (wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0 && bytes2 <= static_cast<size_t>(kPoolSmemBig)) {
         const bool fit = (g.Ho - 1) * 2 + 3 <= H && (g.Wo - 1) * 2 + 3 <= W;
         const FastDiv fb = make_fastdiv(((H + 1) / 2) * ((W + 1) / 2)), fbw = make_fastdiv((W + 1) / 2);
         if (fit) {
@@ -1279,7 +1280,7 @@ int mnv_max_pooling_idx_supported(int N, int C, int H, int W, int sv, int sh, in
   const size_t planes = static_cast<size_t>(N) * C, per = static_cast<size_t>(H) * W;
   if (planes == 0 || planes >= 0x7fffffff) return 0;
   const int G = pool_group(per, planes, per);
-  if (G <= 0 || 2 * ((per * G + 4 + 3) & ~static_cast<size_t>(3)) * sizeof(float) > static_cast<size_t>(kPoolSmemMax)) return 0;   // forward staging
+  if (G <= 0 || 2 * ((per * G + 4 + 3) & ~static_cast<size_t>(3)) * sizeof(float) > static_cast<size_t>(kPoolSmemBig)) return 0;   // forward staging
   const size_t blk = static_cast<size_t>((H + 1) / 2) * ((W + 1) / 2);
   return blk * blk < (1ull << 32) ? 1 : 0;
 }
