@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch one op a few times (for `ncu -k regex:... -s N -c M`).  Usage: one_op.py <name> [iters [KEY=INT ...]]
-names: conv{1..5}_{fwd,bwd,wgrad}, fc6_fwd, gemm8k, pool1_fwd, pool1_bwd, lrn1_fwd, lrn1_bwd, lrn1_fwd_lite, lrn1_bwd_lite, bias1"""
+names: conv{1..5}_{fwd,bwd,wgrad}, fc6_fwd, gemm8k, pool1_fwd, pool1_bwd, pool1_bwd_idx, lrn1_fwd, lrn1_bwd, lrn1_fwd_lite, lrn1_bwd_lite, bias1"""
 import os
 import sys
 
@@ -54,7 +54,11 @@ elif name.startswith("pool1"):
     Ho = lib.mnv_pooled_size(H, 0, 3, 2)
     x, y = torch.relu(rnd(B * C * H * H)), rnd(B * C * Ho * Ho)
     dy, dx = rnd(B * C * Ho * Ho), rnd(B * C * H * H)
-    if name.endswith("fwd"):
+    if name.endswith("bwd_idx"):      # the arg-max remembering pair owl.net uses
+        idx = torch.empty(y.numel(), dtype=torch.uint8, device="cuda")
+        call("mnv_max_pooling_forward_idx", x, y, idx, B, C, H, H, 2, 2, 3, 3, 0, 0)
+        fn = lambda: call("mnv_max_pooling_backward_idx", dy, idx, y, dx, B, C, H, H, 2, 2, 3, 3, 0, 0)
+    elif name.endswith("fwd"):
         fn = lambda: call("mnv_max_pooling_forward", x, y, B, C, H, H, 2, 2, 3, 3, 0, 0)
     else:
         call("mnv_max_pooling_forward", x, y, B, C, H, H, 2, 2, 3, 3, 0, 0)
