@@ -165,3 +165,58 @@ def test_peer_merge_layout():
     assert [b[2] for b in buckets] == ["c2", "c1"]
     slices, buckets, total = plan_layout([("only", 5, 1)], 4, last_fc=0)
     assert len(buckets) == 1 and buckets[0][1] % 16 == 0
+
+
+def test_fusion_plan_flags():
+    """Net._plan_fusion on a backend that advertises the fused entry points (no compute): a ReLU is folded into its
+    producing convolution / its consuming LRN or max pooling only when it is the single reader / has a single reader."""
+    from minerva_b200.owl.net.net import (Net, DataUnit, ConvConnection, ReluUnit, LRNUnit, PoolingUnit, FullyConnection,
+                                          SoftmaxUnit, ConcatUnit)
+
+    class _Co:
+        FUSED_CONV_RELU = True
+        FUSED_RELU_BACKWARD = True
+
+    class _B:
+        co, ele, owl = _Co, None, None
+
+    def build():
+        net = Net(_B())
+        net.add_unit(DataUnit("data", ["data", "label"]))
+        net.add_unit(ConvConnection("c1", "data", "c1", 8, 3))
+        net.add_unit(ReluUnit("r1", "c1", "c1r"))              # single reader of c1; read by an LRN only
+        net.add_unit(LRNUnit("n1", "c1r", "n1"))
+        net.add_unit(ConvConnection("c2", "n1", "c2", 8, 3))
+        net.add_unit(ReluUnit("r2", "c2", "c2r"))              # read by a max pool AND a conv: backward mask stays
+        net.add_unit(PoolingUnit("p2", "c2r", "p2", 3, 2))
+        net.add_unit(ConvConnection("c3", "c2r", "c3", 8, 1))
+        net.add_unit(ReluUnit("r3", "c3", "c3r"))
+        net.add_unit(PoolingUnit("p3", "c3r", "p3", 3, 2, pool="avg"))   # average pooling has no fused mask
+        net.add_unit(ConvConnection("c4", "p2", "c4", 8, 1))
+        net.add_unit(ReluUnit("r4a", "c4", "c4a"))             # c4 has two readers: no epilogue fusion
+        net.add_unit(ReluUnit("r4b", "c4", "c4b"))
+        net.add_unit(ConcatUnit("cat", ["c4a", "c4b", "p3"], "cat"))
+        net.add_unit(FullyConnection("fc", "cat", "fc", 4))
+        net.add_unit(SoftmaxUnit("loss", "fc", "label", "prob"))
+        return net
+
+    net = build()
+    net._plan_fusion()
+    u = {x.name: x for x in net.units}
+    assert u["c1"].fuse_relu and u["r1"].fused and u["c2"].fuse_relu and u["c3"].fuse_relu and not u["c4"].fuse_relu
+    assert not u["r4a"].fused and not u["r4b"].fused
+    assert u["r1"].bp_fused and u["n1"].relu_bp                 # ReLU -> LRN
+    assert not u["r2"].bp_fused and not u["p2"].relu_bp         # two readers
+    assert not u["r3"].bp_fused and not u["p3"].relu_bp         # average pooling
+    net = build()
+    net.fuse_conv_relu = net.fuse_relu_backward = net.fuse_lrn_recompute = net.fuse_pool_index = net.fuse_conv_grads = False
+    net._plan_fusion()
+    for x in net.units:
+        assert not getattr(x, "fuse_relu", False) and not getattr(x, "fused", False) and not getattr(x, "bp_fused", False)
+        assert not getattr(x, "relu_bp", False)
+        if isinstance(x, LRNUnit):
+            assert not x.lite
+        if isinstance(x, PoolingUnit):
+            assert not x.use_idx
+        if isinstance(x, ConvConnection):
+            assert not x.fuse_grads
