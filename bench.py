@@ -251,12 +251,11 @@ def main():
     import minerva_b200.owl.net as onet
     from minerva_b200.owl import _runtime as rt
     from minerva_b200 import _lib
-    lib = _lib.load()
+    # --mnv-opt (experiments only) switches the whole process to the tuning build of the library; the default run
+    # uses the product library, in which every option is a compile-time constant
+    lib = _lib.use_tuning() if args.mnv_opt else _lib.load()
     for kv in args.mnv_opt:
-        import ctypes
         k, v = kv.split("=")
-        lib.mnv_debug_set_option.restype = ctypes.c_int
-        lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
         lib.mnv_debug_set_option(k.encode(), int(v))
 
     dev_id = owl.create_gpu_device(local)

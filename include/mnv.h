@@ -25,7 +25,9 @@
  * Workspace: kernels that need scratch memory (split-K partials, bias-grad partials) take an
  * explicit (workspace, workspace_bytes) pair owned by the device layer, one per stream, as the
  * reference's PooledDataStore would hand out.  Passing NULL/0 is legal and selects the
- * scratch-free schedule.  mnv_workspace_bytes_hint() returns a size that lets every schedule
+ * scratch-free schedule (every convolution / MatMult entry has one; the only exception is
+ * mnv_matmult_ex, which returns MNV_EWORKSPACE when an operand's alignment forces it to
+ * materialise a transpose and no workspace was given).  mnv_workspace_bytes_hint() returns a size that lets every schedule
  * run for the AlexNet / GoogLeNet shapes.
  */
 #ifndef MNV_H_
@@ -300,6 +302,13 @@ int mnv_max_pooling_backward_idx(const float* top_diff, const unsigned char* idx
                                  int bottom_height, int bottom_width, int stride_vertical,
                                  int stride_horizontal, int window_height, int window_width,
                                  int pad_height, int pad_width, mnv_stream_t stream);
+
+/* ---- explicit in-place forms ------------------------------------------------------------------
+ * The entries above never alias an output with an input.  Two callers need to: the data-parallel gradient merge
+ * (owl/net/merge.py: shard += peer's shard; the reference's `wgrad[upd_gpu] += wgrad[gid]`, owl/owl/net/trainer.py:131-135)
+ * and the max-pooling-backward ReLU fallback.  These read the aliased buffer with ordinary (coherent) loads. */
+int mnv_accumulate(float* acc, const float* x, size_t n, mnv_stream_t stream);          /* acc[i] += x[i] */
+int mnv_relu_mask_inplace(float* dx, const float* x, size_t n, mnv_stream_t stream);    /* dx[i] = x[i] > 0 ? dx[i] : 0 */
 
 /* ---- fused momentum-SGD update (owl/net/net.py:252-256) ----------------
  * delta = mom*delta - (lr/batch)*grad - (lr*wd)*w ; w += delta    (20 B/param instead of the

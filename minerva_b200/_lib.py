@@ -53,7 +53,9 @@ class MnvError(RuntimeError):
 
 
 _lib = None
+_tuning = None
 PROTOS = parse_header()
+TUNING_LIB_PATH = os.path.join(HERE, "lib", "libmnv_b200_tuning.so")
 
 
 def load():
@@ -80,6 +82,36 @@ def load():
     return lib
 
 
+def load_tuning():
+    """The TUNING build (include/mnv_debug.h): same ABI plus mnv_debug_set_option.  A separate handle for tools/ and
+    the alternate-operand-path tests; nothing in the product (minerva_b200.owl, bench.py's timed path) loads it."""
+    global _tuning
+    if _tuning is not None:
+        return _tuning
+    if not os.path.exists(TUNING_LIB_PATH):
+        raise MnvError("tuning build not found: %s (python -m minerva_b200.build)" % TUNING_LIB_PATH)
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
+    lib = C.CDLL(TUNING_LIB_PATH)
+    for name, (res, argtypes, _) in PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = argtypes
+    lib.mnv_debug_set_option.restype = C.c_int
+    lib.mnv_debug_set_option.argtypes = [C.c_char_p, C.c_int]
+    _tuning = lib
+    return lib
+
+
+def use_tuning():
+    """tools/ only: make the tuning build THE library of this process (load() returns it from now on)."""
+    global _lib
+    _lib = load_tuning()
+    return _lib
+
+
 _ERRS = {-1: "MNV_EINVAL", -2: "MNV_EUNSUPPORTED", -3: "MNV_EWORKSPACE"}
 
 
@@ -89,6 +121,6 @@ def check(rc, what):
         raise MnvError("%s failed: %s" % (what, _ERRS.get(rc, "cudaError %d" % rc)))
 
 
-def call(name, *args):
-    fn = getattr(load(), name)
+def call(name, *args, lib=None):
+    fn = getattr(lib or load(), name)
     check(fn(*args), name)

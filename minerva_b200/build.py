@@ -15,6 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libmnv_b200.so")
+TUNING_LIB = os.path.join(OUT_DIR, "libmnv_b200_tuning.so")   # -DMNV_TUNING: include/mnv_debug.h (tools, alternate-path tests)
 HOST_LIB = os.path.join(OUT_DIR, "libminerva_b200_host.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -51,8 +52,17 @@ def build(force=False, verbose=False):
         if force or _stale(obj, [path] + headers):
             cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             subprocess.check_call(cmd)
+    link = ["-lcudart", "-ccbin", "/usr/bin/g++", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     if force or _stale(LIB, objs):
-        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++", "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
+        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + link)
+    # the tuning build differs in gemm_conv.cu only (runtime-settable options + the SIMT checker kernel)
+    path = os.path.join(CSRC, "gemm_conv.cu")
+    tobj = os.path.join(OUT_DIR, "gemm_conv_tuning.o")
+    if force or _stale(tobj, [path] + headers + [os.path.join(ROOT, "include", "mnv_debug.h")]):
+        subprocess.check_call([NVCC] + ARCH + COMMON + ["-DMNV_TUNING", "-c", path, "-o", tobj])
+    tobjs = [tobj if o.endswith("gemm_conv.o") else o for o in objs]
+    if force or _stale(TUNING_LIB, tobjs):
+        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", TUNING_LIB] + tobjs + link)
     build_host(force)
     return LIB
 

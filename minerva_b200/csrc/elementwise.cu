@@ -200,6 +200,41 @@ __global__ void __launch_bounds__(kBlock) randn_kernel(float* __restrict__ dst, 
   }
 }
 
+// ---- in-place binary ops: acc[i] = op(acc[i], x[i]) -------------------------------------------------------------
+// The reference-shaped entries promise "outputs never alias inputs" and read through the non-coherent path
+// (__ldg, __restrict__); these two are the explicit in-place forms the gradient merge (acc += peer shard) and the
+// pooling-backward ReLU fallback need: the aliased pointer is read with plain loads and is not __restrict__.
+template <class Op>
+__global__ void __launch_bounds__(kBlock) ew_inplace_kernel(float* acc, const float* __restrict__ x, size_t n, int vec, Op op) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t n4 = vec ? n / 4 : 0;
+  float4* a4 = reinterpret_cast<float4*>(acc);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (size_t base = tid; base < n4; base += stride * kUnroll) {
+    float4 va[kUnroll], vx[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t i = base + u * stride;
+      if (i < n4) { va[u] = a4[i]; vx[u] = __ldg(x4 + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t i = base + u * stride;
+      if (i < n4) a4[i] = make_float4(op(va[u].x, vx[u].x, 0.f), op(va[u].y, vx[u].y, 0.f), op(va[u].z, vx[u].z, 0.f), op(va[u].w, vx[u].w, 0.f));
+    }
+  }
+  for (size_t i = n4 * 4 + tid; i < n; i += stride) acc[i] = op(acc[i], x[i], 0.f);
+}
+template <class Op>
+static int launch_inplace(float* acc, const float* x, size_t n, Op op, cudaStream_t s) {
+  if (n == 0) return MNV_OK;
+  if (!acc || !x) return MNV_EINVAL;
+  const int vec = aligned16(acc) && aligned16(x);
+  ew_inplace_kernel<Op><<<stream_grid(n / (4 * kUnroll) + 1), kBlock, 0, s>>>(acc, x, n, vec, op);
+  return finish_launch();
+}
+
 // ---- fused momentum SGD (in place): 3 reads + 2 writes = 20 B/param ------------------------------
 __global__ void __launch_bounds__(kBlock) sgd_kernel(float* __restrict__ w, float* __restrict__ delta,
                                                      const float* __restrict__ grad, size_t n, float mom,
@@ -340,6 +375,13 @@ int mnv_sgd_momentum_update(float* w, float* delta, const float* grad, size_t n,
   sgd_kernel<<<stream_grid(n / 4 + 1), kBlock, 0, as_stream(s)>>>(w, delta, grad, n, momentum,
                                                                     lr_over_batch, lr_times_wd, vec);
   return finish_launch();
+}
+
+int mnv_accumulate(float* acc, const float* x, size_t n, mnv_stream_t s) {
+  return launch_inplace(acc, x, n, AddOp{}, as_stream(s));
+}
+int mnv_relu_mask_inplace(float* dx, const float* x, size_t n, mnv_stream_t s) {
+  return launch_inplace(dx, x, n, ReluBackOp{}, as_stream(s));
 }
 
 int mnv_abi_version(void) { return 1; }

@@ -54,7 +54,10 @@ enum : int { A_COLMAJOR = 0, A_IM2COL_FWD = 1, A_IM2COL_BWD = 2, A_IM2COL_WGRAD 
 //                    own (tap, channel chunk)) the m axis => MN-major tile (backward-filter)
 //   TMA_A_TILED_K  : row-major (transposed) matrix: one 128-row x 32-k box per UMMA half => K-major tile (MatMult, A^T)
 enum : int { TMA_A_IM2COL_K = 1, TMA_A_TILED_MN = 2, TMA_A_IM2COL_MN = 3, TMA_A_TILED_K = 4 };
-enum : int { B_KMAJOR = 0, B_DY_WGRAD = 1 };
+enum : int { B_KMAJOR = 0, B_DY_WGRAD = 1,
+              // backward-data without a workspace: B[n = ci][k = (co, r, s)] read straight out of the filter as stored,
+              // filter[co][ci][r][s] (taps rotated by 180 degrees when GemmParams::b_flip) -- no re-laid-out copy
+              B_FILTER_T = 2 };
 
 struct GemmParams {
   const float* a;
@@ -92,6 +95,7 @@ struct GemmParams {
   int out_mode;         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
                         // 2: the same over a space-to-depth view (below): virtual (tap, channel) -> real filter element
   int r_ci, r_fh, r_fw, r_sv, r_sh;   // out_mode 2: the real convolution's channels, filter and strides
+  int b_flip;           // B_FILTER_T: 1 = taps rotated by 180 degrees (stride-1 backward-data run as a forward convolution)
 };
 
 constexpr int BM = 128;        // UMMA M (cta_group::1)
@@ -290,6 +294,10 @@ template <int BMD>
 __device__ __forceinline__ float b_elem(const GemmParams& p, int n, int k) {
   if (n >= p.N || k >= p.K) return 0.f;
   if (BMD == B_KMAJOR) return __ldg(p.b + static_cast<size_t>(n) * p.ldb + k);
+  if (BMD == B_FILTER_T) {
+    const int ff = p.fh * p.fw, co = k / ff, rs = k - co * ff;
+    return __ldg(p.b + (static_cast<size_t>(co) * p.N + n) * ff + (p.b_flip ? ff - 1 - rs : rs));
+  }
   int hw = p.Ho * p.Wo;
   int img = k / hw, pix = k - img * hw;
   return __ldg(p.b + (static_cast<size_t>(img) * p.Co + n) * hw + pix);
@@ -319,7 +327,8 @@ __device__ __forceinline__ size_t out_index(const GemmParams& p, int m, int n) {
 }
 
 // SIMT checker: one thread per output, sequential fp32 k loop.  Debug / cross-check only
-// (mnv_debug_set_option("simt", 1)); never selected by default.
+// (mnv_debug_set_option("simt", 1)); exists in the tuning build only.
+#ifdef MNV_TUNING
 template <int AM, int BMD>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmParams p) {
   size_t total = static_cast<size_t>(p.M) * p.N;
@@ -332,6 +341,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmParams p) {
     p.out[out_index(p, m, n)] = (p.relu && !(v > 0.f)) ? 0.f : v;
   }
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // fast gathers.  Every producer thread stages 16 floats of A per k-stage (4 chunks of 16 bytes):
@@ -542,6 +552,31 @@ __device__ __forceinline__ void b_gather(const GemmParams& p, int n_base, int b_
           if (k0 + 2 < p.K) v.z = __ldg(src + 2);
           if (k0 + 3 < p.K) v.w = __ldg(src + 3);
         }
+      }
+      vb[i] = v;
+    }
+  } else if (BMD == B_FILTER_T) {  // k = (co, r, s): filter[(co*N + n)*ff + tap]; same k decomposition for all rows
+    const int ff = p.fh * p.fw;
+    int co = k0 / ff, rs = k0 - co * ff;
+    long long off[4];
+    bool okk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      okk[e] = k0 + e < p.K;
+      off[e] = static_cast<long long>(co) * p.N * ff + (p.b_flip ? ff - 1 - rs : rs);
+      if (++rs == ff) { rs = 0; ++co; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= iters) break;
+      int row = b_row0 + 64 * i, n = n_base + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.bn && n < p.N) {
+        const float* src = p.b + static_cast<size_t>(n) * ff;
+        if (okk[0]) v.x = __ldg(src + off[0]);
+        if (okk[1]) v.y = __ldg(src + off[1]);
+        if (okk[2]) v.z = __ldg(src + off[2]);
+        if (okk[3]) v.w = __ldg(src + off[3]);
       }
       vb[i] = v;
     }
@@ -1383,27 +1418,47 @@ __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __g
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static std::atomic<int> g_opt_pf_dist{0};      // TMA L2-prefetch distance in k-stages (0 = off)
-static std::atomic<int> g_opt_wait_hint{100};  // mbarrier.try_wait suspend hint in ns (tuning)
-static std::atomic<int> g_opt_no_wide{0};     // 1: never use the wide (bn > 256) tile (tuning)
-static std::atomic<int> g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
-static std::atomic<int> g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
-static std::atomic<int> g_opt_no_tma{0};     // 1: gather B with threads even where TMA applies (debug)
-static std::atomic<int> g_opt_no_fwd_bwd{0};  // 1: use the generic backward-data gather for stride 1 too (debug)
-static std::atomic<int> g_opt_no_tma_a{0};   // bit 0: no TMA-im2col fprop/dgrad, bit 1: no TMA MatMult A, bit 2: no TMA wgrad (debug / tuning)
-static std::atomic<int> g_opt_tma_tf32{1};   // operand maps typed TFLOAT32: TMA then rounds fp32 -> tf32 to nearest on the way in (measured:
+// Tuning / debug options.  The PRODUCT library (libmnv_b200.so) is built without MNV_TUNING: every option is a
+// compile-time constant, there is no process-global mutable state and neither mnv_debug_set_option nor the
+// SIMT checker kernel exists in it.  The tuning build (libmnv_b200_tuning.so, -DMNV_TUNING; include/mnv_debug.h) is what
+// tools/ and the alternate-path parity tests load.
+#ifdef MNV_TUNING
+struct Opt {
+  std::atomic<int> v;
+  constexpr Opt(int d) : v(d) {}
+  int load() const { return v.load(std::memory_order_relaxed); }
+  int exchange(int x) { return v.exchange(x); }
+};
+#define MNV_OPT static Opt
+#else
+struct Opt {
+  int d;
+  constexpr Opt(int d_) : d(d_) {}
+  constexpr int load() const { return d; }
+};
+#define MNV_OPT static constexpr Opt
+#endif
+MNV_OPT g_opt_pf_dist{0};      // TMA L2-prefetch distance in k-stages (0 = off)
+MNV_OPT g_opt_wait_hint{100};  // mbarrier.try_wait suspend hint in ns (tuning)
+MNV_OPT g_opt_no_wide{0};     // 1: never use the wide (bn > 256) tile (tuning)
+MNV_OPT g_opt_simt{0};       // 1: run the SIMT checker instead of tcgen05 (debug only)
+MNV_OPT g_opt_max_splits{0}; // >0: clamp split-K (debug / tuning)
+MNV_OPT g_opt_no_tma{0};     // 1: gather B with threads even where TMA applies (debug)
+MNV_OPT g_opt_no_fwd_bwd{0};  // 1: use the generic backward-data gather for stride 1 too (debug)
+MNV_OPT g_opt_no_tma_a{0};   // bit 0: no TMA-im2col fprop/dgrad, bit 1: no TMA MatMult A, bit 2: no TMA wgrad (debug / tuning)
+MNV_OPT g_opt_tma_tf32{1};   // operand maps typed TFLOAT32: TMA then rounds fp32 -> tf32 to nearest on the way in (measured:
                                              // norm-rel error vs fp64 2.9e-4 unbiased, against 7.7e-4 with a -7e-4 bias for FLOAT32 maps,
                                              // whose low mantissa bits the tensor core just drops); 0 = FLOAT32 maps (debug)
-static std::atomic<int> g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it applies, ignoring the profitability rule (tuning)
-static std::atomic<int> g_opt_no_klane{0};   // 1: strided convs keep the lanes-along-pixels gathers (debug / tuning)
-static std::atomic<int> g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
-static std::atomic<int> g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
-static std::atomic<int> g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
-static std::atomic<int> g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
-static std::atomic<int> g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
-static std::atomic<int> g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
-static std::atomic<int> g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
-static std::atomic<int> g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
+MNV_OPT g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it applies, ignoring the profitability rule (tuning)
+MNV_OPT g_opt_no_klane{0};   // 1: strided convs keep the lanes-along-pixels gathers (debug / tuning)
+MNV_OPT g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
+MNV_OPT g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
+MNV_OPT g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
+MNV_OPT g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
+MNV_OPT g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
+MNV_OPT g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
+MNV_OPT g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
+MNV_OPT g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1736,7 +1791,7 @@ __global__ void __launch_bounds__(256) rowsum_fold_kernel(const float* __restric
 // persistent kernel (an overlapped NCCL all-reduce) holds a few SMs, a 148-CTA grid runs its last CTAs as a second
 // wave and the launch takes up to twice as long; the data-parallel trainer therefore leaves NCCL's SMs out
 // ("sm_budget" option; default = all 148).
-static std::atomic<int> g_opt_sm_budget{kNumSMs};
+MNV_OPT g_opt_sm_budget{kNumSMs};
 static int sm_budget() {
   int v = g_opt_sm_budget.load();
   return v < 1 ? 1 : v > kNumSMs ? kNumSMs : v;
@@ -1812,7 +1867,7 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
 // Tail split (see GemmParams): when the tile grid ends in a last wave that fills at most half the machine, the tiles of
 // that wave are K-split over the idle CTAs.  Partials use the split-K layout partial[split][n][m] (only the tail tiles'
 // entries are touched); splitk_tail_reduce_kernel folds them.
-static std::atomic<int> g_opt_no_tail{0};    // 1: no tail split (tuning)
+MNV_OPT g_opt_no_tail{0};    // 1: no tail split (tuning)
 static void plan_tail(GemmParams& p, void* ws, size_t ws_bytes) {
   p.tail_splits = 0;
   if (g_opt_no_tail.load() || p.splits != 1 || !ws) return;
@@ -1879,11 +1934,13 @@ static int launch_umma_tma(const GemmParams& p, const CUtensorMap& tm_a, const C
 
 template <int AM, int BMD>
 static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s) {
+#ifdef MNV_TUNING
   if (g_opt_simt.load()) {
     p.splits = 1; p.partial = nullptr;
     simt_gemm_kernel<AM, BMD><<<stream_grid(static_cast<size_t>(p.M) * p.N), 256, 0, s>>>(p);
     return finish_launch();
   }
+#endif
   // A K-major B whose rows are not 16-byte pitched/aligned (conv1: K = 363; odd GEMM k) is re-pitched into the
   // workspace once (B is the small operand: filters, or the batch-side matrix of an FC layer) so that it can
   // still come through TMA and the kernel can run the grouped-producer path.
@@ -1946,7 +2003,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -2086,7 +2143,8 @@ using namespace mnv;
 
 extern "C" {
 
-// Debug / tuning hook (not part of the reference surface).  Keys: "simt" (1 routes GEMM/conv through
+#ifdef MNV_TUNING
+// Debug / tuning hook (not part of the reference surface; declared in include/mnv_debug.h, tuning build only).  Keys: "simt" (1 routes GEMM/conv through
 // the SIMT checker kernel), "max_splits" (clamp split-K), "no_tma" (gather B with threads),
 // "no_fwd_bwd" (generic backward-data gather for stride 1).  Returns the previous value, -1 for a bad key.
 __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key, int value) {
@@ -2115,6 +2173,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   return -1;
 }
+#endif
 
 int mnv_matmult(const float* a, const float* b, float* c, int m, int n, int k, void* workspace,
                 size_t workspace_bytes, mnv_stream_t stream) {
@@ -2257,12 +2316,30 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
   if (!top_diff || !filter || !bottom_diff) return MNV_EINVAL;
   // the filter is re-laid out as [ci][(co,r,s)] in the workspace (a few MB at most, once per call)
   size_t wt_bytes = (static_cast<size_t>(Co) * Ci * fh * fw * sizeof(float) + 255) / 256 * 256;
-  if (!workspace || workspace_bytes < wt_bytes) return MNV_EWORKSPACE;
-  float* wt = static_cast<float*>(workspace);
   const int Ho = (H + 2 * ph - fh) / sv + 1, Wo = (W + 2 * pw - fw) / sh + 1;
   // stride 1: backward-data == forward convolution of top_diff with the swapped, 180-degree-rotated
   // filter and pad' = f-1-pad, so it runs on the (fast) forward gather.
   const bool as_forward = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && !g_opt_no_fwd_bwd.load();
+  if (!workspace || workspace_bytes < wt_bytes) {
+    // scratch-free schedule (mnv.h: a null / short workspace is legal): the producer warps gather B straight out of the
+    // filter as stored, [co][ci][r][s] read as B[ci][(co,r,s)]
+    GemmParams p;
+    zero_conv(p);
+    long long M = static_cast<long long>(N) * H * W, K = static_cast<long long>(Co) * fh * fw;
+    if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * Co * Ho * Wo)) return MNV_EUNSUPPORTED;
+    p.a = top_diff; p.b = filter; p.out = bottom_diff;
+    p.M = static_cast<int>(M); p.N = Ci; p.K = static_cast<int>(K);
+    p.P = H * W; p.img_stride = static_cast<long long>(Ci) * p.P; p.col_stride = p.P;
+    p.fh = fh; p.fw = fw; p.b_flip = as_forward ? 1 : 0;
+    if (as_forward) {
+      p.Ci = Co; p.Co = Ci; p.H = Ho; p.W = Wo; p.Ho = H; p.Wo = W;
+      p.ph = fh - 1 - ph; p.pw = fw - 1 - pw; p.sv = 1; p.sh = 1;
+      return launch_gemm<A_IM2COL_FWD, B_FILTER_T>(p, nullptr, 0, as_stream(stream));
+    }
+    p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.ph = ph; p.pw = pw; p.sv = sv; p.sh = sh;
+    return launch_gemm<A_IM2COL_BWD, B_FILTER_T>(p, nullptr, 0, as_stream(stream));
+  }
+  float* wt = static_cast<float*>(workspace);
   if (as_forward) {
     // B[n = ci][k = (tap, co)] = filter[co][ci][tap]: the two 180-degree rotations (true convolution, transposed
     // operator) cancel

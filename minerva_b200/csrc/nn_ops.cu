@@ -1270,8 +1270,8 @@ int mnv_max_pooling_backward_relu(const float* x, const float* y, const float* d
   bool relu = true;
   int rc = max_pooling_backward_impl(x, y, dy, dx, N, C, H, W, sv, sh, wh, ww, ph, pw, s, &relu);
   if (rc || relu) return rc;
-  // geometries without a fused kernel: the mask as a second, in-place elementwise pass (thread i reads and writes element i only)
-  return mnv_relu_backward(x, x, dx, dx, N, C, H, W, s);
+  // geometries without a fused kernel: the mask as a second, explicitly in-place elementwise pass
+  return mnv_relu_mask_inplace(dx, x, static_cast<size_t>(N) * C * H * W, s);
 }
 int mnv_max_pooling_idx_supported(int N, int C, int H, int W, int sv, int sh, int wh, int ww, int ph, int pw) {
   PoolGeom g;

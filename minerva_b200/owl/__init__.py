@@ -60,3 +60,8 @@ def set_seed(seed):
     """Generators are keyed by (seed, call counter) instead of the wall clock
     (minerva/op/impl/cuda.cpp:601,606) so runs are reproducible."""
     _rt.set_seed(seed)
+
+
+def set_rank_salt(rank):
+    """Mix the data-parallel rank into the dropout (randb) seeds; weights (randn) stay identical across ranks."""
+    _rt.set_rank_salt(rank)

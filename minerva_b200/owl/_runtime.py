@@ -21,7 +21,7 @@ class _Gpu:
 
 _devices = []      # id -> _Gpu or CPU_DEVICE
 _current = None
-_seed = [0x5EED, 0]
+_seed = [0x5EED, 0, 0]   # seed, call counter, rank salt (dropout masks only)
 profiler = None    # set to an object with begin(name, args, dev) / end(token, dev) to time every C-ABI call
 
 
@@ -99,6 +99,13 @@ def set_seed(seed):
     _seed[1] = 0
 
 
-def next_seed():
+def set_rank_salt(rank):
+    """Data-parallel replicas share one seed (identical initial weights) but must not share dropout masks:
+    the trainer mixes the rank into the Bernoulli generator's seed only."""
+    _seed[2] = int(rank) & 0xFFFF
+
+
+def next_seed(salted=False):
     _seed[1] += 1
-    return (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF
+    s = (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF
+    return (s ^ (_seed[2] * 0xC2B2AE35)) & 0xFFFFFFFF if salted else s

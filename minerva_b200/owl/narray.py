@@ -89,8 +89,11 @@ class NArray:
     def _materialize(self):
         src, self._lazy_src = self._lazy_src, None
         m, n = src._shape
-        self._buf = torch.empty(max(m * n, 0), dtype=torch.float32, device=self._dev.device)
-        NArray._call("mnv_transpose", self._dev, src._on(self._dev).data_ptr(), self._buf.data_ptr(), m, n)
+        # the C ABI wants pointers and stream on the CURRENT device: the view may be read first after
+        # owl.set_device(other_gpu) (the reference's single-process multi-GPU loop), so materialise on its own device
+        with torch.cuda.device(self._dev.index):
+            self._buf = torch.empty(max(m * n, 0), dtype=torch.float32, device=self._dev.device)
+            NArray._call("mnv_transpose", self._dev, src._on(self._dev).data_ptr(), self._buf.data_ptr(), m, n)
 
     def _flush_views(self):
         """Materialise pending lazy transposes of this array (called before it is modified in place)."""
@@ -595,7 +598,7 @@ class NArray:
     def randb(s, p):
         dev = _rt.current_device()
         out = NArray._new(s, dev)
-        NArray._call("mnv_rand_bernoulli", dev, out._t.data_ptr(), out.size, _rt.next_seed(), float(p))
+        NArray._call("mnv_rand_bernoulli", dev, out._t.data_ptr(), out.size, _rt.next_seed(salted=True), float(p))
         return out
 
     @staticmethod

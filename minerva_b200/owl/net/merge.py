@@ -15,7 +15,7 @@ local sum of a 1/W shard:
   per bucket, on a side stream, as soon as its last gradient has been copied into `flat`:
       barrier                                     every rank's bucket is in place
       pull   recv[p] <- peer p's flat[bucket shard r]          (W-1 copy-engine transfers, shard r = this rank's)
-      sum    flat[shard r] += recv[p], p in rank order         (mnv_add on the side stream, 1/W of the bucket)
+      sum    flat[shard r] += recv[p], p in rank order         (mnv_accumulate on the side stream, 1/W of the bucket)
       barrier                                     every shard is reduced, nobody still reads unreduced data
       pull   flat[shard p] <- peer p's flat[shard p]           (W-1 copy-engine transfers)
       barrier                                     nobody overwrites `flat` while a peer still pulls
@@ -141,9 +141,9 @@ class PeerGradMerge(object):
             self._pull_all([(self.recv[p, :shard], hdl.get_buffer(p, (shard,), torch.float32, boff + r * shard)) for p in peers])
             for p in range(W):           # rank order: the same sum on whichever rank owns the shard
                 if p != r:
-                    rc = lib.mnv_add(mine.data_ptr(), self.recv[p].data_ptr(), mine.data_ptr(), shard, self.comm.cuda_stream)
+                    rc = lib.mnv_accumulate(mine.data_ptr(), self.recv[p].data_ptr(), shard, self.comm.cuda_stream)
                     if rc:
-                        _lib.check(rc, "mnv_add")
+                        _lib.check(rc, "mnv_accumulate")
             hdl.barrier(channel=0)
             self._pull_all([(self.flat[boff + p * shard: boff + (p + 1) * shard],
                              hdl.get_buffer(p, (shard,), torch.float32, boff + p * shard)) for p in peers])

@@ -1,4 +1,6 @@
 """Compute units and the Net DAG (reference: owl/owl/net/net.py:24-1139)."""
+import zlib
+
 import numpy as np
 
 
@@ -72,7 +74,9 @@ class WeightedComputeUnit(ComputeUnitSimple):
         owl = self.B.owl
         if self.weight_filler == "xavier":       # net.py:222-224
             scale = float(np.sqrt(3.0 / self.fan_in))
-            rs = np.random.RandomState(1234 + len(self.name))
+            # seeded by a stable hash of the FULL unit name: same-length names (inception_4b/5x5_reduce vs
+            # inception_4c/5x5_reduce) must not draw identical weights; identical on every data-parallel rank
+            rs = np.random.RandomState((zlib.crc32(self.name.encode()) ^ 1234) & 0x7FFFFFFF)
             self.weight = owl.from_numpy(rs.uniform(-scale, scale, list(reversed(self.wshape))).astype(np.float32))
         else:
             self.weight = owl.randn(self.wshape, 0.0, self.weight_std)
@@ -430,14 +434,20 @@ class Net(object):
         self._blobs = blobs
 
     def backward(self, phase="TRAIN"):
+        # `sens[name]` is the sensitivity of the CURRENT version of blob `name`: a unit takes (pops) its tops'
+        # sensitivities before it writes its bottoms', so an in-place unit (top name == bottom name, the Caffe
+        # convention for relu / dropout) replaces the entry instead of adding to it, and only contributions of
+        # different consumers of one blob version are summed -- what the reference's per-unit dicts do
+        # (owl/owl/net/net.py:1102-1114).
         sens = {}
         for u in reversed(self.units):
             if isinstance(u, DataUnit):
                 continue
-            if not isinstance(u, SoftmaxUnit) and any(sens.get(t) is None for t in u.top_names):
+            top_sens = {t: sens.pop(t, None) for t in u.top_names}
+            if not isinstance(u, SoftmaxUnit) and any(v is None for v in top_sens.values()):
                 continue
             out = {}
-            u.backward(sens, out, phase)
+            u.backward(top_sens, out, phase)
             for k, v in out.items():
                 if v is None:
                     continue

@@ -25,6 +25,8 @@ class NetTrainer(object):
         self._pending = []
         self.peer = None
         self.merge_kind = "none (1 GPU)"
+        if self.dist and hasattr(net.B.owl, "set_rank_salt"):
+            net.B.owl.set_rank_salt(self.dist.get_rank())     # replicas draw different dropout masks, same weights
         if self.dist:
             self.merge_kind = "NCCL all-reduce per weighted unit, overlapped with backward"
             if merge in ("auto", "peer") and self.dist.get_backend() == "nccl":

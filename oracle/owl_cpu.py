@@ -10,7 +10,7 @@ import numpy as np
 
 from . import pyoracle as orc
 
-_seed = [0x5EED, 0]
+_seed = [0x5EED, 0, 0]
 _use_ref = [False]
 
 
@@ -24,9 +24,14 @@ def set_seed(seed):
     _seed[1] = 0
 
 
-def _next_seed():
+def set_rank_salt(rank):
+    _seed[2] = int(rank) & 0xFFFF
+
+
+def _next_seed(salted=False):
     _seed[1] += 1
-    return (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF
+    s = (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF
+    return (s ^ (_seed[2] * 0xC2B2AE35)) & 0xFFFFFFFF if salted else s
 
 
 def _prod(s):
@@ -176,7 +181,7 @@ def randn(shape, mu, var):
 
 
 def randb(shape, prob):
-    return NArray(orc.rand_bernoulli(_prod(shape), _next_seed(), prob), shape)
+    return NArray(orc.rand_bernoulli(_prod(shape), _next_seed(salted=True), prob), shape)
 
 
 def from_numpy(n):

@@ -22,9 +22,25 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Alternate kernel paths are forced through the TUNING build (include/mnv_debug.h); while any option is off its
+# default, run() routes calls there, otherwise through the product library.
+_OPT_DEFAULTS = {"tall_min_stages": 64, "tma_tf32": 1, "wait_hint": 100, "sm_budget": 148}
+_nondefault = {}
+
+
+def set_option(key, val):
+    prev = _lib.load_tuning().mnv_debug_set_option(key.encode(), int(val))
+    assert prev != -1 or val == -1, "unknown tuning option %r" % key
+    if int(val) == _OPT_DEFAULTS.get(key, 0):
+        _nondefault.pop(key, None)
+    else:
+        _nondefault[key] = int(val)
+    return prev
+
+
 def run(name, *args):
     conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
-    _lib.call(name, *conv, stream())
+    _lib.call(name, *conv, stream(), lib=_lib.load_tuning() if _nondefault else None)
     torch.cuda.synchronize()
 
 

@@ -28,6 +28,25 @@ def test_library_exports_every_declared_symbol():
         assert forbidden not in ldd
 
 
+def test_product_library_has_no_tuning_state():
+    """SURVEY 8b "no global mutable state": the runtime-settable options and the SIMT checker exist only in the tuning
+    build (include/mnv_debug.h); the product library does not export the hook."""
+    from minerva_b200 import _lib, build
+    build.build()
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "mnv_debug_set_option" not in nm
+    nm_t = subprocess.run(["nm", "-D", "--defined-only", _lib.TUNING_LIB_PATH], capture_output=True, text=True).stdout
+    assert "mnv_debug_set_option" in nm_t
+    assert "mnv_debug_set_option" not in _lib.parse_header()
+    hdr = open(os.path.join(ROOT, "include", "mnv_debug.h")).read()
+    assert "int mnv_debug_set_option(const char* key, int value);" in hdr
+    tun = _lib.load_tuning()
+    assert tun.mnv_debug_set_option(b"no_such_key", 1) == -1
+    assert tun.mnv_debug_set_option(b"no_tail", 0) == 0
+    for name in _lib.parse_header():
+        assert hasattr(tun, name), name
+
+
 def test_header_covers_reference_table():
     """One entry per row of minerva/op/impl/cuda/cuda_perform.h:12-76 (53 functions)."""
     from minerva_b200 import _lib

@@ -55,6 +55,21 @@ def test_arithmetic_edges_and_misaligned(g):
     g.assert_bits_equal(g.host(dc), orc.dot_mult(a, a), "aliased inputs")
 
 
+@pytest.mark.parametrize("n", [1, 720, 4099, (1 << 20) + 3])
+def test_in_place_forms(g, n):
+    """mnv_accumulate / mnv_relu_mask_inplace: the explicit in-place entries (the reference-shaped ones never alias an
+    output with an input) give the bits of the out-of-place ops."""
+    acc = rng.normal(0, 1, n + 1).astype(np.float32)
+    x = rng.normal(0, 1, n + 1).astype(np.float32)
+    for off in (0, 1):           # off = 1: a view 4 bytes into the allocation takes the scalar path
+        da, dx = g.dev(acc), g.dev(x)
+        g.run("mnv_accumulate", da[off:], dx[off:], n)
+        g.assert_bits_equal(g.host(da)[off:off + n], orc.add(acc[off:off + n], x[off:off + n]), "accumulate")
+        da = g.dev(acc)
+        g.run("mnv_relu_mask_inplace", da[off:], dx[off:], n)
+        g.assert_bits_equal(g.host(da)[off:off + n], orc.relu_backward(x[off:off + n], x[off:off + n], acc[off:off + n]), "relu mask")
+
+
 @pytest.mark.parametrize("n", [720, 4099, (1 << 18) + 1])
 def test_arithmetic_const_bit_exact(g, n):
     x = rng.normal(0, 5, n).astype(np.float32)

@@ -2,7 +2,6 @@
 ABI vs the CPU oracle.  Tolerance (north_star): <= 5e-3 norm-relative for TF32 conv and GEMM.  The
 SIMT checker kernel (fp32) is run on the small cases too, as an independent statement of the index
 math; it must agree with the oracle to 1e-4."""
-import ctypes
 import json
 import os
 
@@ -24,11 +23,9 @@ def g():
 
 
 def _set(key, val):
-    from minerva_b200 import _lib
-    fn = _lib.load().mnv_debug_set_option
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_char_p, ctypes.c_int]
-    return fn(key.encode(), val)
+    """Force an alternate kernel path: routed through the tuning build of the library (tests/gpu_util.py)."""
+    from tests import gpu_util
+    return gpu_util.set_option(key, val)
 
 
 def _matmult(g, a, b, m, n, k, use_ws=True):
@@ -111,7 +108,7 @@ def _conv_all(g, case, x, w, b, dy, use_ws=True):
     y = g.empty(N * Co * Ho * Wo); y.fill_(float("nan"))
     g.run("mnv_conv_forward", g.dev(x), g.dev(w), g.dev(b), y, *geo, wsp, wsb)
     dx = g.empty(x.size); dx.fill_(float("nan"))
-    g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, ws, ws.numel())
+    g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, wsp, wsb)   # no workspace: filter gathered as stored
     dw = g.empty(w.size); dw.fill_(float("nan"))
     g.run("mnv_conv_backward_filter", g.dev(x), g.dev(dy), dw, *geo, wsp, wsb)
     return g.host(y), g.host(dx), g.host(dw)
@@ -210,7 +207,7 @@ def test_conv_tail_split(g, case):
             yr = g.empty(wy.size); yr.fill_(float("nan"))
             g.run("mnv_conv_forward_relu", g.dev(x), g.dev(w), g.dev(b), yr, *geo, ws, ws.numel())
             dx = g.empty(x.size); dx.fill_(float("nan"))
-            g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, ws, ws.numel())
+            g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, wsp, wsb)   # no workspace: filter gathered as stored
         finally:
             _set("no_tail", 0)
             _set("force_tma_a", 0)

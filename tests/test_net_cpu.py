@@ -220,3 +220,66 @@ def test_fusion_plan_flags():
             assert not x.use_idx
         if isinstance(x, ConvConnection):
             assert not x.fuse_grads
+
+
+def test_in_place_units_match_distinct_names():
+    """Caffe's in-place naming (relu / dropout with top == bottom, what every reference prototxt uses): the
+    sensitivities are tracked per blob VERSION, so gradients equal those of the same net with distinct names
+    (owl/owl/net/net.py:1102-1114 keeps per-unit dicts for the same reason)."""
+    from oracle import owl_cpu
+    from minerva_b200.owl.net.net import (Net, DataUnit, ConvConnection, ReluUnit, PoolingUnit, FullyConnection,
+                                          DropoutUnit, SoftmaxUnit, ConcatUnit)
+
+    def build(inplace):
+        B = owl_cpu.Backend()
+        owl_cpu.set_seed(9)
+        n = (lambda a, b: a) if inplace else (lambda a, b: b)
+        net = Net(B)
+        net.add_unit(DataUnit("data", ["data", "label"]))
+        net.add_unit(ConvConnection("conv1", "data", "conv1", 6, 3, 2, 0, weight_std=0.3))
+        net.add_unit(ReluUnit("relu1", "conv1", n("conv1", "c1r")))
+        # two consumers of the rectified blob: their contributions ARE summed
+        net.add_unit(PoolingUnit("poolA", n("conv1", "c1r"), "pa", 2, 2))
+        net.add_unit(PoolingUnit("poolB", n("conv1", "c1r"), "pb", 2, 2, pool="avg"))
+        net.add_unit(ConcatUnit("cat", ["pa", "pb"], "cat"))
+        net.add_unit(FullyConnection("fc1", "cat", "fc1", 12, weight_std=0.2, bias_value=0.1))
+        net.add_unit(ReluUnit("relu2", "fc1", n("fc1", "f1r")))
+        net.add_unit(DropoutUnit("drop", n("fc1", "f1r"), n("fc1", "f1d"), 0.5))
+        net.add_unit(FullyConnection("fc2", n("fc1", "f1d"), "fc2", 5, weight_std=0.2))
+        net.add_unit(SoftmaxUnit("loss", "fc2", "label", "prob"))
+        du = net.get_data_unit()
+        du.data, du.label = _batch(B, 6)
+        net.batch_size = 6
+        net.forward("TRAIN")
+        net.backward("TRAIN")
+        return net
+
+    a, b = build(True), build(False)
+    assert abs(a.get_loss_units()[0].getloss() - b.get_loss_units()[0].getloss()) == 0.0
+    for uid in a.get_weighted_unit_ids():
+        np.testing.assert_array_equal(a.units[uid].weightgrad.a, b.units[uid].weightgrad.a, err_msg=a.units[uid].name)
+        np.testing.assert_array_equal(a.units[uid].biasgrad.a, b.units[uid].biasgrad.a, err_msg=a.units[uid].name)
+
+
+def test_xavier_seeds_and_rank_salt():
+    """Same-length unit names draw different xavier weights; ranks share weights but not dropout masks."""
+    from oracle import owl_cpu
+    from minerva_b200.owl.net.net import ConvConnection
+    B = owl_cpu.Backend()
+    ws = []
+    for name in ("inception_4b/5x5_reduce", "inception_4c/5x5_reduce"):
+        u = ConvConnection(name, "x", name, 24, 1, weight_filler="xavier")
+        u.B = B
+        u.wshape, u.bshape, u.fan_in = [1, 1, 512, 24], [24], 512
+        u.init_weights_with_filler()
+        ws.append(u.weight.a.copy())
+    assert not np.array_equal(ws[0], ws[1])
+    masks, weights = [], []
+    for rank in (0, 1):
+        owl_cpu.set_seed(4)
+        owl_cpu.set_rank_salt(rank)
+        weights.append(B.owl.randn([64], 0.0, 1.0).a.copy())
+        masks.append(B.owl.randb([4096], 0.5).a.copy())
+    owl_cpu.set_rank_salt(0)
+    np.testing.assert_array_equal(weights[0], weights[1])
+    assert not np.array_equal(masks[0], masks[1])

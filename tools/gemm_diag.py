@@ -14,7 +14,7 @@ from minerva_b200 import _lib
 from oracle import pyoracle as orc
 from tests import gpu_util as g
 
-lib = _lib.load()
+lib = _lib.use_tuning()   # include/mnv_debug.h: runtime-settable options exist in the tuning build only
 lib.mnv_debug_set_option.restype = ctypes.c_int
 lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
 rng = np.random.default_rng(0)

@@ -9,7 +9,7 @@ import torch
 
 from minerva_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.use_tuning()   # include/mnv_debug.h: runtime-settable options exist in the tuning build only
 name = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 for kv in sys.argv[3:]:      # KEY=INT tuning / debug options (mnv_debug_set_option)

@@ -21,7 +21,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--mnv-opt", action="append", default=[], metavar="KEY=INT", help="mnv_debug_set_option before timing (tuning)")
 args = ap.parse_args()
 
-lib = _lib.load()
+lib = _lib.use_tuning() if args.mnv_opt else _lib.load()   # options exist in the tuning build only
 if args.mnv_opt:
     import ctypes
     lib.mnv_debug_set_option.restype = ctypes.c_int

@@ -9,7 +9,7 @@ from minerva_b200 import _lib
 from oracle import pyoracle as orc
 
 import ctypes
-lib = _lib.load()
+lib = _lib.use_tuning()   # include/mnv_debug.h: runtime-settable options exist in the tuning build only
 st = torch.cuda.current_stream().cuda_stream
 _so = lib.mnv_debug_set_option
 _so.restype = ctypes.c_int

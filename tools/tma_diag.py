@@ -14,7 +14,7 @@ import torch
 from minerva_b200 import _lib
 from tests import gpu_util as g
 
-lib = _lib.load()
+lib = _lib.use_tuning()   # include/mnv_debug.h: runtime-settable options exist in the tuning build only
 lib.mnv_debug_set_option.restype = ctypes.c_int
 lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
 gen = torch.Generator(device="cuda").manual_seed(0)

@@ -10,7 +10,7 @@ import torch
 
 from minerva_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.use_tuning()   # include/mnv_debug.h: runtime-settable options exist in the tuning build only
 lib.mnv_debug_set_option.restype = ctypes.c_int
 lib.mnv_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
 key, vals, ops = sys.argv[1], [int(v, 0) for v in sys.argv[2].split(",")], sys.argv[3:]
