@@ -12,6 +12,19 @@ from . import pyoracle as orc
 
 _seed = [0x5EED, 0, 0]
 _use_ref = [False]
+_tf32 = [False]
+
+
+def set_tf32_operands(flag):
+    """True: MatMult and the three convolution directions round their two operands to TF32 first (orc.tf32_round) and
+    then run the reference's fp32 algorithm -- the arithmetic north_star specifies for the tensor-core ops.  Whole-step
+    parity tests compare the GPU with this AND with the plain fp32 oracle (a tiny batch amplifies the operand rounding
+    through ReLU / arg-max switches, which is a property of TF32, not of a kernel)."""
+    _tf32[0] = bool(flag)
+
+
+def _op(a):
+    return orc.tf32_round(a) if _tf32[0] else a
 
 
 def use_reference(flag):
@@ -92,7 +105,7 @@ class NArray:
             m, k, n = self._shape[0], self._shape[1], r._shape[1]
             assert k == r._shape[0]
             f = orc.Ref.matmult if _use_ref[0] else orc.matmult
-            return NArray(f(self.a, r.a, m, n, k), [m, n])
+            return NArray(f(_op(self.a), _op(r.a), m, n, k), [m, n])
         return NArray(orc.scale(self.a, r), self._shape)
 
     def __rmul__(self, l):
@@ -280,14 +293,14 @@ class _Co:
         def ff(self, x, w, b):
             geo = self._geo(x, w)
             N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = geo
-            y = orc.conv_forward(x.a, w.a, b.a, *geo)
+            y = orc.conv_forward(_op(x.a), _op(w.a), b.a, *geo)
             return NArray(y, [orc.conv_out(W, pw, fw, sh), orc.conv_out(H, ph, fh, sv), Co, N])
 
         def bp(self, y, x, w):
-            return NArray(orc.conv_backward_data(y.a, w.a, *self._geo(x, w)), x.shape)
+            return NArray(orc.conv_backward_data(_op(y.a), _op(w.a), *self._geo(x, w)), x.shape)
 
         def weight_grad(self, y, x, w):
-            return NArray(orc.conv_backward_filter(x.a, y.a, *self._geo(x, w)), w.shape)
+            return NArray(orc.conv_backward_filter(_op(x.a), _op(y.a), *self._geo(x, w)), w.shape)
 
         def bias_grad(self, y):
             W, H, C, N = y.shape

@@ -362,6 +362,16 @@ def sgd_momentum_update(w, delta, grad, mom, lr_over_batch, lr_times_wd):
     return w, delta
 
 
+def tf32_round(a):
+    """fp32 -> TF32 operand rounding as the tensor-core operand path does it (cvt.rna.tf32.f32: nearest, ties away
+    from zero; 10 explicit mantissa bits kept).  Used by the whole-step parity tests to state what "TF32 conv / GEMM with
+    fp32 accumulation" (north_star) computes: the reference's fp32 algorithm on TF32-rounded operands."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    finite = (u & 0x7F800000) != 0x7F800000
+    r = np.where(finite, (u + 0x1000) & 0xFFFFE000, u).astype(np.uint32)
+    return r.view(np.float32)
+
+
 # ---- the compiled reference (oracle/_ref) ---------------------------------------------------
 class Ref:
     """Thin numpy wrappers over the reference's own basic:: functions."""

@@ -207,7 +207,7 @@ def test_conv_tail_split(g, case):
             yr = g.empty(wy.size); yr.fill_(float("nan"))
             g.run("mnv_conv_forward_relu", g.dev(x), g.dev(w), g.dev(b), yr, *geo, ws, ws.numel())
             dx = g.empty(x.size); dx.fill_(float("nan"))
-            g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, wsp, wsb)   # no workspace: filter gathered as stored
+            g.run("mnv_conv_backward_data", g.dev(dy), g.dev(w), dx, *geo, ws, ws.numel())
         finally:
             _set("no_tail", 0)
             _set("force_tma_a", 0)
