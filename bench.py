@@ -5,12 +5,16 @@ the metric BASELINE.json names, measured through the owl API over the sm_100a ke
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (the reference's CPU path on the host cores)
 
-One JSON line on stdout (rank 0).  `value` times K training steps (forward, backward, NCCL gradient
-all-reduce overlapped with backward, momentum-SGD update) with inputs resident in HBM, CUDA events
-on the compute stream, max over ranks.  `e2e` is the same step fed from pinned host memory (H2D of
-the batch every step, prefetched on a copy stream) with the loss read back every step.  `roofline`
-describes the dominant kernel (the tcgen05 GEMM/implicit-GEMM conv kernel) from per-launch CUDA
-events; `cpu_baseline` is the CPU oracle restatement of the same step on a bounded sample.
+One JSON line on stdout (rank 0).  `value` times K training steps (forward, backward, gradient merge over
+NVLink overlapped with backward, momentum-SGD update) with inputs resident in HBM, CUDA events on the
+compute stream, max over ranks.  `e2e` is the same step fed from pinned host memory every step (the uint8
+image batch the reference's data layer reads, converted on the device; the fp32 feed is reported beside it)
+with the loss read back every step.  `roofline` describes the dominant kernel (the tcgen05 GEMM /
+implicit-GEMM conv kernel) from per-call CUDA events; `op_table` carries every C-ABI call's algorithmic
+bytes / flops, achieved GB/s / TFLOP/s and roofline fraction (BASELINE metric: "per-op HBM GB/s and
+tensor-pipe %"); `other_configs` are the remaining BASELINE.json configs measured after the headline;
+`cpu_baseline` / `cpu_reference_ops` time the CPU oracle / the reference's own basic:: functions on the
+host; at N>1 `merge_check` proves the data-parallel gradient merge before anything is timed.
 """
 import argparse
 import json
@@ -34,11 +38,11 @@ def emit(line):
 
 
 WORKLOADS = {
-    "alexnet": dict(builder="build_alexnet", batch=256, classes=1000,
+    "alexnet": dict(builder="build_alexnet", batch=256, classes=1000, uniform=False,
                     name="owl AlexNet (bvlc_alexnet train_val, no groups), batch 256/GPU, random-init weights"),
-    "lenet": dict(builder="build_lenet", batch=256, classes=10, name="apps/mnist_cnn LeNet-style CNN, batch 256"),
-    "mlp": dict(builder="build_mnist_mlp", batch=256, classes=10, name="apps/mnist_mlp 784-256-10 MLP, batch 256"),
-    "googlenet": dict(builder="build_googlenet", batch=120, classes=1000,
+    "lenet": dict(builder="build_lenet", batch=256, classes=10, uniform=True, name="apps/mnist_cnn LeNet-style CNN, batch 256"),
+    "mlp": dict(builder="build_mnist_mlp", batch=256, classes=10, uniform=True, name="apps/mnist_mlp 784-256-10 MLP, batch 256"),
+    "googlenet": dict(builder="build_googlenet", batch=120, classes=1000, uniform=False,
                       name="owl GoogLeNet (bvlc_googlenet train_val), batch 120/GPU, random-init weights"),
 }
 
@@ -54,25 +58,28 @@ def parse():
     ap.add_argument("--unfused-update", action="store_true", help="use the reference's ten-op SGD chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the GoogLeNet / LeNet / MLP lines after the headline")
     ap.add_argument("--merge", default="auto", choices=["auto", "peer", "nccl", "off"], help="N>1 gradient merge (owl/net/merge.py)")
     ap.add_argument("--nccl-ctas", type=int, default=0,
                     help="N>1: SMs left to NCCL (NCCL_MAX_CTAS) and kept out of the persistent tensor-core kernel's grid; 0 = do not manage")
     ap.add_argument("--mnv-opt", action="append", default=[], metavar="KEY=INT",
-                    help="tuning: set a mnv_debug_set_option key before the run (recorded in config.tuning)")
+                    help="tuning: switch to the tuning build of the library and set a mnv_debug_set_option key (recorded in config.tuning)")
     return ap.parse_args()
 
 
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tensor-core kernel, averaged over the launches of one
-    ncu launch-list capture of this command (profiles/r01_launch_list_summary.json, tools/launch_summary.py); null for
+    ncu launch-list capture of this command (profiles/r0N_launch_list_summary.json, tools/launch_summary.py); null for
     workloads that have no committed capture."""
     if workload != "alexnet":
         return None
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_launch_list_summary.json")) as f:
-            return float(json.load(f)["umma_gemm_kernel"]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_launch_list_summary.json", "r01_launch_list_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["umma_gemm_kernel"]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def peaks():
@@ -91,7 +98,8 @@ def peaks():
 def host_batch(wl, shape, batch, seed):
     import numpy as np
     rs = np.random.RandomState(seed)
-    x = rs.standard_normal([batch] + list(reversed(shape))).astype(np.float32)
+    dims = [batch] + list(reversed(shape))
+    x = (rs.uniform(0, 1, dims) if wl.get("uniform") else rs.standard_normal(dims)).astype(np.float32)
     lab = rs.randint(0, wl["classes"], batch)
     onehot = np.zeros((batch, wl["classes"]), np.float32)
     onehot[np.arange(batch), lab] = 1
@@ -127,7 +135,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def summary(self):
         s = sorted(self.samples)
@@ -136,22 +144,121 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# algorithmic work of one C-ABI call for the roofline of the dominant kernel
+# algorithmic work of one C-ABI call: ("tensor", flops) or ("hbm", bytes)
 # ------------------------------------------------------------------------------------------------
-def gemm_flops(name, a):
+def _prod(v):
+    p = 1
+    for x in v:
+        p *= int(x)
+    return p
+
+
+def _pooled(x, pad, win, stride):
+    p = (x + 2 * pad - win + stride - 1) // stride + 1
+    return p - 1 if (p - 1) * stride >= x + pad else p
+
+
+def op_work(name, a):
     if name in ("mnv_matmult", "mnv_matmult_ex"):
-        return 2.0 * a[3] * a[4] * a[5]
+        return "tensor", 2.0 * a[3] * a[4] * a[5]
     if name in ("mnv_conv_forward", "mnv_conv_forward_relu", "mnv_conv_backward_data", "mnv_conv_backward_filter",
                 "mnv_conv_backward_filter_bias"):
         off = 4 if name.startswith("mnv_conv_forward") or name.endswith("_bias") else 3
         N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = a[off:off + 11]
         Ho, Wo = (H + 2 * ph - fh) // sv + 1, (W + 2 * pw - fw) // sh + 1
-        return 2.0 * N * Ho * Wo * Co * Ci * fh * fw
-    return None
+        return "tensor", 2.0 * N * Ho * Wo * Co * Ci * fh * fw
+    if name in ("mnv_add", "mnv_sub", "mnv_dot_mult", "mnv_dot_div"):
+        return "hbm", 12.0 * a[3]
+    if name == "mnv_accumulate":
+        return "hbm", 12.0 * a[2]
+    if name == "mnv_scale":
+        return "hbm", 8.0 * a[2]
+    if name in ("mnv_const_add", "mnv_left_const_sub", "mnv_left_const_div", "mnv_const_div"):
+        return "hbm", 8.0 * a[3]
+    if name in ("mnv_elewise_exp", "mnv_elewise_ln", "mnv_elewise_negative", "mnv_copy"):
+        return "hbm", 8.0 * a[2]
+    if name == "mnv_reshape":
+        return "hbm", 2.0 * a[2]
+    if name in ("mnv_sigmoid_forward", "mnv_relu_forward", "mnv_tanh_forward"):
+        return "hbm", 8.0 * _prod(a[2:6])
+    if name in ("mnv_sigmoid_backward", "mnv_relu_backward", "mnv_tanh_backward"):
+        return "hbm", 12.0 * _prod(a[4:8])
+    if name.startswith("mnv_norm_"):
+        return "hbm", 8.0 * a[3] * a[4] + 4.0 * max(a[3], a[4])
+    if name.startswith("mnv_reduction_") or name.startswith("mnv_max_index_"):
+        m, n = a[2], a[3]
+        return "hbm", 4.0 * (m * n + (n if name.endswith("_col") else m))
+    if name == "mnv_transpose":
+        return "hbm", 8.0 * a[2] * a[3]
+    if name == "mnv_copy_strided":
+        return "hbm", 8.0 * a[2] * a[3]
+    if name == "mnv_conv_backward_bias":
+        return "hbm", 4.0 * (_prod(a[2:6]) + a[3])
+    if name.endswith("_softmax_forward"):
+        return "hbm", 8.0 * _prod(a[2:6])
+    if name.endswith("_softmax_backward"):
+        return "hbm", 12.0 * _prod(a[3:7])
+    if name in ("mnv_max_pooling_forward", "mnv_average_pooling_forward", "mnv_max_pooling_forward_idx"):
+        off = 3 if name.endswith("_idx") else 2
+        N, C, H, W, sv, sh, wh, ww, ph, pw = a[off:off + 10]
+        ein, eout = N * C * H * W, N * C * _pooled(H, ph, wh, sv) * _pooled(W, pw, ww, sh)
+        return "hbm", 4.0 * ein + (5.0 if name.endswith("_idx") else 4.0) * eout
+    if name in ("mnv_max_pooling_backward", "mnv_max_pooling_backward_relu", "mnv_average_pooling_backward", "mnv_max_pooling_backward_idx"):
+        N, C, H, W, sv, sh, wh, ww, ph, pw = a[4:14]
+        ein, eout = N * C * H * W, N * C * _pooled(H, ph, wh, sv) * _pooled(W, pw, ww, sh)
+        if name.endswith("_idx"):
+            return "hbm", 5.0 * eout + 4.0 * ein + (4.0 * eout if a[2] else 0.0)
+        if name.startswith("mnv_average"):
+            return "hbm", 4.0 * (ein + eout)
+        return "hbm", 4.0 * (2 * ein + 2 * eout)
+    if name == "mnv_lrn_forward":
+        return "hbm", 12.0 * _prod(a[6:10])
+    if name in ("mnv_lrn_backward", "mnv_lrn_backward_relu"):
+        return "hbm", 20.0 * _prod(a[8:12])
+    if name == "mnv_lrn_forward_lite":
+        return "hbm", 8.0 * _prod(a[5:9])
+    if name == "mnv_lrn_backward_lite":
+        return "hbm", 12.0 * _prod(a[6:10])
+    if name in ("mnv_fill", "mnv_randn", "mnv_rand_bernoulli"):
+        return "hbm", 4.0 * a[1]
+    if name == "mnv_sgd_momentum_update":
+        return "hbm", 20.0 * a[3]
+    if name == "mnv_image_transform_u8":
+        return "hbm", 5.0 * a[4] * a[5] * a[8] * a[9]        # 1 B in + 4 B out per element (the mean image stays in L2)
+    return None, 0.0
+
+
+def op_table_from(table, steps, pk):
+    """table: [(name, args, ms)] over `steps` instrumented steps -> ({name: row}, totals of the tensor / HBM-bound calls)."""
+    per = {}
+    for name, a, ms in table:
+        kind, work = op_work(name, a)
+        d = per.setdefault(name, {"n": 0, "ms": 0.0, "work": 0.0, "kind": kind})
+        d["n"] += 1
+        d["ms"] += ms
+        d["work"] += work
+    total_ms = sum(v["ms"] for v in per.values())
+    tf32_burst, hbm = pk["bf16_tflops"] / 2.0, pk["hbm_gbs"]
+    out = {}
+    for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"calls_per_step": v["n"] / steps, "ms_per_step": v["ms"] / steps, "share": v["ms"] / total_ms if total_ms else 0.0}
+        sec = v["ms"] * 1e-3
+        if v["kind"] == "tensor" and sec > 0:
+            row.update(bound="tensor", flops_per_step=v["work"] / steps, tflops=v["work"] / sec / 1e12,
+                       frac=v["work"] / sec / 1e12 / tf32_burst)
+        elif v["kind"] == "hbm" and sec > 0:
+            row.update(bound="hbm", bytes_algorithmic_per_step=v["work"] / steps, gbs=v["work"] / sec / 1e9,
+                       frac=v["work"] / sec / 1e9 / hbm)
+        out[k] = row
+    g = [v for v in per.values() if v["kind"] == "tensor"]
+    g_flops, g_ms, g_n = sum(v["work"] for v in g), sum(v["ms"] for v in g), sum(v["n"] for v in g)
+    h = [v for v in per.values() if v["kind"] == "hbm"]
+    h_bytes, h_ms = sum(v["work"] for v in h), sum(v["ms"] for v in h)
+    return out, (g_flops, g_ms, g_n, total_ms, h_bytes, h_ms)
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU leg: the same owl.net graph on the oracle backend (test infrastructure used as a baseline only)
+# CPU legs: the same owl.net graph on the oracle backend (test infrastructure used as a baseline only)
 # ------------------------------------------------------------------------------------------------
 def cpu_step_rate(wl, sample_batch, steps, warmup, use_ref=True):
     from oracle import owl_cpu
@@ -172,6 +279,65 @@ def cpu_step_rate(wl, sample_batch, steps, warmup, use_ref=True):
         tr.step()
     dt = time.time() - t0
     return sample_batch * steps / dt, dt, used_ref
+
+
+def cpu_reference_ops(budget_s=20.0):
+    """the reference's OWN CPU functions (minerva/op/impl/basic.cpp compiled into oracle/_ref)
+    timed one op at a time, single-threaded -- that is how the reference's CpuDevice runs an op -- at the shapes the
+    AlexNet step issues (MatMult is the naive triple loop of basic.cpp:164-171: the fc8 shape only, fc6 would take minutes).
+    -> {op: {shape, ms, GB/s | GFLOP/s}} or {"unavailable": why}."""
+    import numpy as np
+    from oracle import pyoracle as orc
+    if not orc.have_ref():
+        return {"unavailable": "oracle/_ref/libminerva_ref.so not built (needs /root/reference at build time)"}
+    R = orc.Ref
+    rs = np.random.RandomState(5)
+    out = {"how": "reference basic:: functions (oracle/_ref), one thread per op as on the reference's CpuDevice, best of 2"}
+    t_start = time.time()
+
+    def timed(fn):
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best
+
+    def add(name, shape, fn, bytes_=None, flops=None):
+        if time.time() - t_start > budget_s:
+            return
+        dt = timed(fn)
+        row = {"shape": shape, "ms": dt * 1e3}
+        if bytes_ is not None:
+            row["gbs"] = bytes_ / dt / 1e9
+        if flops is not None:
+            row["gflops"] = flops / dt / 1e9
+        out[name] = row
+
+    E = 290400 * 256 // 4            # a quarter of the conv1 activations (18.6 M): bounded sample, same access pattern
+    a, b = rs.standard_normal(E).astype(np.float32), rs.standard_normal(E).astype(np.float32)
+    add("Arithmetic add", "18.6 M (conv1 activations / 4)", lambda: R.arithmetic("add", a, b), bytes_=12.0 * E)
+    add("ArithmeticConst mult", "18.6 M", lambda: R.arithmetic_const("mult", 0, 0.5, a), bytes_=8.0 * E)
+    add("ReluForward", "18.6 M", lambda: R.activation("relu", a), bytes_=8.0 * E)
+    s = a[:4096 * 256 * 4]
+    add("SigmoidForward", "4.2 M", lambda: R.activation("sigmoid", s), bytes_=8.0 * s.size)
+    add("TanhForward", "4.2 M", lambda: R.activation("tanh", s), bytes_=8.0 * s.size)
+    add("Elewise exp", "4.2 M", lambda: R.elewise("exp", s), bytes_=8.0 * s.size)
+    m = a[:4096 * 256]
+    v = b[:4096]
+    add("NormArithmetic add (fc bias)", "{4096,256} + {4096,1}", lambda: R.norm_arithmetic("add", 1, m, v, 4096, 256), bytes_=8.0 * m.size)
+    add("Reduction sum (fc bias grad)", "{4096,256} -> {4096,1}", lambda: R.reduction("sum", 1, m, 4096, 256), bytes_=4.0 * (m.size + 4096))
+    x = a[:1000 * 256]
+    add("MaxIndex", "{1000,256} -> {1,256}", lambda: R.max_index(0, x, 1000, 256), bytes_=4.0 * (x.size + 256))
+    add("SoftmaxForward", "{1000,1,1,256}", lambda: R.softmax_forward(x, 1000, 1, 1, 256), bytes_=8.0 * x.size)
+    t = a[:4096 * 4096]
+    add("Transpose (fc7 weight)", "{4096,4096}", lambda: R.transpose(t, 4096, 4096), bytes_=8.0 * t.size)
+    w8, a8 = a[:1000 * 4096], b[:4096 * 256]
+    add("MatMult (fc8 forward)", "1000 x 256 x 4096", lambda: R.matmult(w8, a8, 1000, 256, 4096), flops=2.0 * 1000 * 256 * 4096)
+    w1, a1 = a[:256 * 784], b[:784 * 256]
+    add("MatMult (mnist_mlp fc1)", "256 x 256 x 784", lambda: R.matmult(w1, a1, 256, 256, 784), flops=2.0 * 256 * 256 * 784)
+    return out
 
 
 def run_reference(args):
@@ -209,6 +375,181 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def merge_check(C, net, trainer):
+    """N>1, before anything is timed: (i) the product gradient merge (peer exchange or per-unit NCCL all-reduce) gives,
+    on every rank, the NCCL all-reduce of the ranks' local gradients to <= 1e-5 relative per tensor; (ii) after a full
+    step every rank holds bit-identical weights (MIN == MAX of an exact integer checksum).  Same inputs, weights and
+    dropout seeds in both passes, so the local gradients are the same bits."""
+    torch, dist, owl = C.torch, C.dist, C.owl
+    wids = net.get_weighted_unit_ids()
+    hook = net.on_weight_grad
+
+    def one_pass(with_merge):
+        owl.set_seed(4242)
+        net.on_weight_grad = hook if with_merge else None
+        if trainer.peer is not None:
+            trainer.peer.begin_step()
+        net.forward("TRAIN")
+        net.backward("TRAIN")
+        if with_merge:
+            trainer._wait_merge()
+        return [g for uid in wids for g in (net.units[uid].weightgrad, net.units[uid].biasgrad)]
+
+    ref = []
+    for g in one_pass(False):
+        t = g.as_torch().clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ref.append(t)
+    merged = one_pass(True)
+    worst = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for g, r in zip(merged, ref):
+        err = (g.as_torch().double() - r.double()).abs().max() / r.double().abs().max().clamp_min(1e-30)
+        worst = torch.maximum(worst, err.reshape(1))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    net.on_weight_grad = hook
+    owl.set_seed(1234 + 77)
+    trainer.step()                                   # a full step incl. the update
+    sums = torch.stack([net.units[uid].weight.as_torch().view(torch.int32).to(torch.int64).sum() for uid in wids] +
+                       [net.units[uid].bias.as_torch().view(torch.int32).to(torch.int64).sum() for uid in wids])
+    lo, hi = sums.clone(), sums.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool(torch.equal(lo, hi))
+    res = {"grad_max_rel_err_vs_nccl_allreduce": float(worst.item()), "tolerance": 1e-5, "tensors": len(ref),
+           "weights_bit_identical_across_ranks": identical, "ranks": C.world, "merge": trainer.merge_kind.split(",")[0]}
+    res["ok"] = bool(res["grad_max_rel_err_vs_nccl_allreduce"] <= 1e-5 and identical)
+    return res
+
+
+def measure(C, args, wl_key, headline):
+    """Build the net of one BASELINE config, warm up, time `steps` training steps with resident inputs (device-timed, max
+    over ranks), then the end-to-end loop.  -> result dict (+ net / trainer for the headline's extra sections)."""
+    torch, owl, onet, rt, lib = C.torch, C.owl, C.onet, C.rt, C.lib
+    wl = WORKLOADS[wl_key]
+    world, rank = C.world, C.rank
+    owl.set_seed(1234)                      # identical initial weights on every rank
+    batch = (args.batch if headline and args.batch else 0) or wl["batch"]
+    net = getattr(onet, wl["builder"])()
+    net.batch_size = batch * world          # the update divisor is the global batch
+    x, onehot = host_batch(wl, net.input_shape, batch, 100 + rank)
+    du = net.get_data_unit()
+    du.data, du.label = owl.from_numpy(x), owl.from_numpy(onehot)
+    trainer = onet.NetTrainer(net, C.dist if world > 1 else None, fused_update=not args.unfused_update, merge=args.merge)
+    gdev = rt.current_device()
+    res = {"workload": wl["name"], "per_gpu_batch": batch, "global_batch": batch * world}
+
+    for _ in range(max(3, args.warmup)):
+        trainer.step()
+    C.sync_all()
+    if world > 1:
+        res["merge_check"] = merge_check(C, net, trainer)
+        C.sync_all()
+        if not res["merge_check"]["ok"]:
+            return res, net, trainer, du, (x, onehot)
+    sampler = ClockSampler(C.local) if headline else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.mnv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(gdev.stream)
+    for _ in range(args.steps):
+        trainer.step()
+    e1.record(gdev.stream)
+    C.sync_all()
+    launches = lib.mnv_launch_count() - launches0
+    if sampler:
+        sampler.stop_flag = True
+        res["clocks"] = sampler.summary()
+    ms_total = C.max_over_ranks(e0.elapsed_time(e1))
+    res.update(value=batch * world * args.steps / (ms_total * 1e-3), ms_per_step=ms_total / args.steps,
+               gpu_launches=int(launches), loss=float(net.get_loss_units()[-1].getloss()),
+               gradient_merge=trainer.merge_kind)
+    if hasattr(trainer, "merge_note"):
+        res["gradient_merge_note"] = trainer.merge_note
+    if not args.no_e2e:
+        res["e2e"] = run_e2e(C, args, net, trainer, du, x, onehot, batch)
+    return res, net, trainer, du, (x, onehot)
+
+
+def run_e2e(C, args, net, trainer, du, x, onehot, batch):
+    """The same step fed from pinned host memory EVERY step through the data unit (owl/net/data.py: double-buffered,
+    copy stream, stream-ordered hand-over), loss read back every step (one step late, like the reference's asynchronous
+    trainer prints).  Two feeds: "u8" -- the uint8 image batch a real data layer reads from disk (owl/owl/net/netio.py:
+    259-339 converts and mean-subtracts on the HOST; here the bytes are uploaded and converted by one kernel on the device)
+    -- and "f32" -- the already converted fp32 batch (4x the bytes)."""
+    import numpy as np
+    torch, owl, rt = C.torch, C.owl, C.rt
+    from minerva_b200.owl.net.data import HostFeed
+    gdev = rt.current_device()
+    steps, world = args.steps, C.world
+    host_loss = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    lu = net.get_loss_units()[-1]
+
+    def loop(feed, nsteps, pipelined):
+        loss_val, pending = None, None
+        feed.start()
+        for it in range(nsteps):
+            cur = it % 2
+            du.data, du.label = feed.next()              # waits (on the stream, not the host) for this step's upload
+            trainer.step()
+            feed.done()                                  # the buffers may be overwritten once this step has read them
+            if not pipelined:
+                loss_val = lu.getloss()
+                continue
+            dsum, n = lu.getloss_device()
+            host_loss[cur].copy_(dsum.as_torch(), non_blocking=True)
+            loss_ready[cur].record(gdev.stream)
+            if pending is not None:
+                loss_ready[pending[0]].synchronize()
+                loss_val = -float(host_loss[pending[0]][0]) / pending[1]
+            pending = (cur, n)
+        if pending is not None:
+            loss_ready[pending[0]].synchronize()
+            loss_val = -float(host_loss[pending[0]][0]) / pending[1]
+        feed.stop()
+        return loss_val
+
+    def timed(feed, pipelined=True):
+        loop(feed, max(2, min(args.warmup, 4)), pipelined)
+        C.sync_all()
+        t0 = time.perf_counter()
+        loss = loop(feed, steps, pipelined)
+        C.sync_all()
+        return C.max_over_ranks(time.perf_counter() - t0), loss
+
+    # uint8 feed: stored images as the reference's LMDB holds them (256 x 256 for the ImageNet nets, cropped to the net's
+    # input and mirrored per image, netio.py:303-311; 28 x 28 for MNIST), synthetic bytes, scaled to about unit variance
+    rs = np.random.RandomState(7 + C.rank)
+    if x.ndim == 4 and x.shape[1] == 3:
+        stored = rs.randint(0, 256, (batch, 3, 256, 256), dtype=np.uint8)
+        feed_u8 = HostFeed(owl, rt, data_u8=stored, mean=np.full((3, 256, 256), 127.5, np.float32), scale=1.0 / 73.9,
+                           crop=(x.shape[2], x.shape[3]), mirror=True, label=onehot, seed=C.rank)
+    else:
+        stored = rs.randint(0, 256, x.shape, dtype=np.uint8)
+        feed_u8 = HostFeed(owl, rt, data_u8=stored, scale=1.0 / 255.0, label=onehot)
+    dt, loss = timed(feed_u8)
+    out = {"value": batch * world * steps / dt, "unit": "images/s",
+           "feed": "stored uint8 images %s -> device-side mean-subtract / random crop / mirror / scale to fp32 (mnv_image_transform_u8)" % (list(stored.shape[1:]),),
+           "h2d_bytes_per_step": feed_u8.bytes_per_step(), "d2h_bytes_per_step": 4, "last_loss": float(loss),
+           "loss_read": "every step's loss is reduced on the device, copied to pinned host memory and read one step later, "
+                        "inside the timed region"}
+    feed_f32 = HostFeed(owl, rt, data_f32=x, label=onehot)
+    dt32, loss32 = timed(feed_f32)
+    out["f32_feed"] = {"value": batch * world * steps / dt32, "h2d_bytes_per_step": int(x.size * 4 + onehot.size * 4), "last_loss": float(loss32)}
+    dtb, _ = timed(feed_f32, pipelined=False)
+    out["blocking_read_value"] = batch * world * steps / dtb
+    out["blocking_read_note"] = "fp32 feed with a blocking loss read after every step (drains the launch queue)"
+    du.data, du.label = feed_f32.resident()
+    return out
+
+
 def main():
     args = parse()
     # a wedged collective must not burn the GPU lease: hard exit after 15 minutes
@@ -224,14 +565,14 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    C = Ctx()
+    C.torch, C.dist = torch, dist
+    C.rank = rank = int(os.environ.get("RANK", "0"))
+    C.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    C.local = local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -257,18 +598,8 @@ def main():
     for kv in args.mnv_opt:
         k, v = kv.split("=")
         lib.mnv_debug_set_option(k.encode(), int(v))
-
-    dev_id = owl.create_gpu_device(local)
-    owl.set_device(dev_id)
-    owl.set_seed(1234)                      # identical initial weights on every rank
-    batch = args.batch or wl["batch"]
-    net = getattr(onet, wl["builder"])()
-    net.batch_size = batch * world          # the update divisor is the global batch
-    x, onehot = host_batch(wl, net.input_shape, batch, 100 + rank)
-    du = net.get_data_unit()
-    du.data, du.label = owl.from_numpy(x), owl.from_numpy(onehot)
-    trainer = onet.NetTrainer(net, dist if world > 1 else None, fused_update=not args.unfused_update, merge=args.merge)
-    gdev = rt.current_device()
+    C.owl, C.onet, C.rt, C.lib = owl, onet, rt, lib
+    owl.set_device(owl.create_gpu_device(local))
 
     def sync_all():
         owl.wait_for_all()
@@ -283,105 +614,20 @@ def main():
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+    C.sync_all, C.max_over_ranks = sync_all, max_over_ranks
 
-    # ---- warm-up, then the timed region: inputs resident in HBM --------------------------------------
-    for _ in range(max(3, args.warmup)):
-        trainer.step()
-    sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = lib.mnv_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(gdev.stream)
-    for _ in range(args.steps):
-        trainer.step()
-    e1.record(gdev.stream)
-    sync_all()
-    launches = lib.mnv_launch_count() - launches0
-    sampler.stop_flag = True
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    value = batch * world * args.steps / (ms_total * 1e-3)
-    loss = net.get_loss_units()[-1].getloss()
+    wl = WORKLOADS[args.workload]
+    head, net, trainer, du, _ = measure(C, args, args.workload, True)
+    if world > 1 and not head["merge_check"]["ok"]:
+        if rank == 0:
+            emit({"metric": "AlexNet train images/s", "value": None, "unit": "images/s", "n_gpus": world, "error": "merge_check failed",
+                  "merge_check": head["merge_check"]})
+        dist.destroy_process_group()
+        sys.exit(1)
 
-    # ---- end to end: the batch comes from pinned host memory every step, the loss goes back ----------
-    e2e = None
-    if not args.no_e2e:
-        hx = torch.from_numpy(x.reshape(-1)).pin_memory()
-        hy = torch.from_numpy(onehot.reshape(-1)).pin_memory()
-        copy_stream = torch.cuda.Stream()
-        bufs = [(owl.zeros(du.data.shape), owl.zeros(du.label.shape)) for _ in range(2)]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def prefetch(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i])
-                bufs[i][0].as_torch().copy_(hx, non_blocking=True)
-                bufs[i][1].as_torch().copy_(hy, non_blocking=True)
-                ready[i].record(copy_stream)
-
-        for i in range(2):
-            consumed[i].record(gdev.stream)
-        sync_all()
-        steps = args.steps
-
-        host_loss = [torch.zeros(1).pin_memory() for _ in range(2)]
-        loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def run(nsteps, pipelined):
-            """pipelined: the step's loss is reduced on the device, copied to pinned host memory asynchronously and
-            READ one step later (every step's loss is read inside the loop, the last one right after it), so the launch
-            queue never drains; otherwise a blocking read after every step."""
-            loss_val, pending = None, None
-            prefetch(0)
-            for it in range(nsteps):
-                cur = it % 2
-                if it + 1 < nsteps:
-                    prefetch(1 - cur)
-                gdev.stream.wait_event(ready[cur])
-                du.data, du.label = bufs[cur]
-                trainer.step()
-                consumed[cur].record(gdev.stream)
-                lu = net.get_loss_units()[-1]
-                if not pipelined:
-                    loss_val = lu.getloss()                       # blocking D2H read of the step's result
-                    continue
-                dsum, n = lu.getloss_device()
-                host_loss[cur].copy_(dsum.as_torch(), non_blocking=True)    # D2H on the compute stream
-                loss_ready[cur].record(gdev.stream)
-                if pending is not None:                           # the previous step's loss: read it now
-                    loss_ready[pending[0]].synchronize()
-                    loss_val = -float(host_loss[pending[0]][0]) / pending[1]
-                pending = (cur, n)
-            if pending is not None:
-                loss_ready[pending[0]].synchronize()
-                loss_val = -float(host_loss[pending[0]][0]) / pending[1]
-            return loss_val
-
-        run(max(2, min(args.warmup, 4)), True)      # untimed: first-touch cost of the pinned staging path
-        sync_all()
-        t0 = time.perf_counter()
-        step_loss = run(steps, True)
-        sync_all()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        sync_all()
-        t0 = time.perf_counter()
-        step_loss_b = run(steps, False)
-        sync_all()
-        dt_b = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": batch * world * steps / dt, "unit": "images/s",
-               "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4), "d2h_bytes_per_step": 4,
-               "last_loss": float(step_loss),
-               "loss_read": "every step's loss is reduced on the device, copied to pinned host memory and read one step "
-                            "later (double-buffered like the input), inside the timed region",
-               "blocking_read_value": batch * world * steps / dt_b,
-               "blocking_read_note": "same loop with a blocking loss read after every step (drains the launch queue)"}
-        du.data, du.label = bufs[0]
-
-    # ---- per-launch device times of the dominant kernel (rank 0) -------------------------------------
+    # ---- per-call device times (every rank runs the two instrumented steps: they contain the gradient merge) ----------
     roofline, optable = None, None
     pk = peaks()
-    # every rank takes the two instrumented steps (they contain the gradient all-reduce); rank 0 records
     if rank == 0:
         rt.profiler = rt.EventProfiler()
     for _ in range(2):
@@ -390,34 +636,44 @@ def main():
     if rank == 0:
         table = rt.profiler.table()
         rt.profiler = None
-        per = {}
-        g_flops = g_ms = 0.0
-        g_n = 0
-        for name, a, ms in table:
-            d = per.setdefault(name, [0, 0.0])
-            d[0] += 1
-            d[1] += ms
-            fl = gemm_flops(name, a)
-            if fl is not None:
-                g_flops += fl
-                g_ms += ms
-                g_n += 1
-        total_ms = sum(v[1] for v in per.values())
-        optable = {k: {"calls_per_step": v[0] / 2, "ms_per_step": v[1] / 2, "share": v[1] / total_ms}
-                   for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])}
-        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        optable, (g_flops, g_ms, g_n, total_ms, h_bytes, h_ms) = op_table_from(table, 2, pk)
+        burst, sustained = pk["bf16_tflops"] / 2.0, pk["bf16_tflops_sustained"] / 2.0
         achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf32_peak, "traffic": ncu_traffic(args.workload),
-                    "kernel": "mnv::umma_gemm_kernel + mnv::conv_shift_fwd_kernel (tcgen05 TF32: MatMult + conv fwd/bwd-data/bwd-filter, pre-passes included)",
+        clocks = head.get("clocks") or {}
+        capped = "sw_power_cap" in (clocks.get("reasons") or [])
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                    "frac_burst": achieved / burst, "frac_sustained": achieved / sustained,
+                    "traffic": ncu_traffic(args.workload),
+                    "kernel": "mnv::umma_gemm_kernel + shift-GEMM conv kernels (tcgen05 TF32: MatMult + conv fwd/bwd-data/bwd-filter, "
+                              "every pre/post pass of those calls included)",
                     "launches_timed": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
                     "share_of_step": g_ms / total_ms if total_ms else None,
-                    "peak_source": "%s bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate)" % pk["source"]}
+                    "peak_source": "%s bf16_tflops/2 = burst dense TF32 (the timed region is ~0.1 s at %s MHz, power cap seen: %s); "
+                                   "frac_sustained divides by bf16_tflops_sustained/2" % (pk["source"], clocks.get("sm_mhz"), capped),
+                    "hbm_bound_calls": {"achieved_gbs": h_bytes / (h_ms * 1e-3) / 1e9 if h_ms else None, "peak_gbs": pk["hbm_gbs"],
+                                        "frac": h_bytes / (h_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if h_ms else None,
+                                        "share_of_step": h_ms / total_ms if total_ms else None}}
     if world > 1:
         dist.barrier()
 
-    # ---- CPU baseline on a bounded sample (rank 0, N == 1) ---------------------------------------------
-    cpu_baseline = None
+    # ---- the other BASELINE configs (same warm-up / step rule, measured after the headline) ---------------------------
+    others = {}
+    if not args.no_other_configs and args.workload == "alexnet" and not args.batch:
+        del net, trainer, du
+        torch.cuda.empty_cache()
+        for key in ("googlenet", "lenet", "mlp"):
+            try:
+                r, n2, t2, d2, _ = measure(C, args, key, False)
+                del n2, t2, d2
+                torch.cuda.empty_cache()
+                others["%s_b%d" % (key, r["per_gpu_batch"])] = r
+            except Exception as ex:     # reported, never load-bearing for the headline
+                others[key] = {"error": repr(ex)}
+                if world > 1:
+                    break                # a rank-local failure would desynchronise the collectives of the next config
+
+    # ---- CPU baselines on bounded samples (rank 0, N == 1) --------------------------------------------------------------
+    cpu_baseline, cpu_ops = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
@@ -429,23 +685,31 @@ def main():
                                       "exists: %s" % (dt, used_ref)}
         except Exception as ex:   # the baseline is reported, never load-bearing
             cpu_baseline = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+        try:
+            cpu_ops = cpu_reference_ops()
+        except Exception as ex:
+            cpu_ops = {"unavailable": repr(ex)}
 
     if rank == 0:
         metric = "AlexNet train images/s" if args.workload == "alexnet" else args.workload + " train images/s"
         line = {
-            "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "metric": metric, "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32 tensor-core conv/GEMM, f32 elsewhere",
             "data": "synthetic",
-            "config": {"workload": wl["name"], "global_batch": batch * world, "per_gpu_batch": batch,
+            "config": {"workload": wl["name"], "global_batch": head["global_batch"], "per_gpu_batch": head["per_gpu_batch"],
                        "parallelism": "dp%d" % world, "update": "chain" if args.unfused_update else "fused momentum-SGD kernel",
                        "l2": "working set per step (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                       "gradient_merge": trainer.merge_kind, **({"gradient_merge_note": trainer.merge_note} if hasattr(trainer, "merge_note") else {}),
+                       "gradient_merge": head["gradient_merge"],
+                       **({"gradient_merge_note": head["gradient_merge_note"]} if "gradient_merge_note" in head else {}),
                        **({"tuning": args.mnv_opt} if args.mnv_opt else {})},
-            "clocks": sampler.summary(), "gpu_launches": int(launches), "loss": float(loss),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,
+            "clocks": head.get("clocks"), "gpu_launches": head["gpu_launches"], "loss": head["loss"],
+            "e2e": head.get("e2e"), "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,
+            "other_configs": others, "cpu_reference_ops": cpu_ops,
             "peaks": {k: pk.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
         }
+        if world > 1:
+            line["merge_check"] = head["merge_check"]
         emit(line)
     if world > 1:
         dist.destroy_process_group()

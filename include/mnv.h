@@ -303,6 +303,18 @@ int mnv_max_pooling_backward_idx(const float* top_diff, const unsigned char* idx
                                  int stride_horizontal, int window_height, int window_width,
                                  int pad_height, int pad_width, mnv_stream_t stream);
 
+/* ---- the data layer's transform on the device -----------------------------
+ * The reference converts every minibatch on the HOST (owl/owl/net/netio.py:300-311: uint8 Datum - mean image, random
+ * crop, optional mirror, astype(float32)) and uploads 4 bytes per pixel through ArrayLoader on the default stream
+ * (op/impl/cuda.cpp:592-597).  Here the stored uint8 images are uploaded (1 byte per pixel) and transformed by one
+ * kernel:  dst[n][c][y][x] = (float(src[n][c][oy+y][ox+xs]) - mean[c][oy+y][ox+xs]) * scale,  xs = mirror ? crop_w-1-x : x.
+ *   src   uint8 [N][C][src_h][src_w];   mean fp32 [C][src_h][src_w] or NULL (no subtraction);
+ *   crop_mirror  int32 [N][3] = (oy, ox, mirror) per image, or NULL = (0, 0, 0);   dst fp32 [N][C][crop_h][crop_w].
+ * Bit-exact against the host computation (one subtraction, one multiplication, both rounded to nearest). */
+int mnv_image_transform_u8(const unsigned char* src, const float* mean, const int* crop_mirror, float* dst,
+                           int num_images, int num_channels, int src_height, int src_width, int crop_height,
+                           int crop_width, float scale, mnv_stream_t stream);
+
 /* ---- explicit in-place forms ------------------------------------------------------------------
  * The entries above never alias an output with an input.  Two callers need to: the data-parallel gradient merge
  * (owl/net/merge.py: shard += peer's shard; the reference's `wgrad[upd_gpu] += wgrad[gid]`, owl/owl/net/trainer.py:131-135)

@@ -235,6 +235,45 @@ static int launch_inplace(float* acc, const float* x, size_t n, Op op, cudaStrea
   return finish_launch();
 }
 
+// ---- data-layer transform: uint8 stored images -> mean-subtracted, cropped, mirrored fp32 batch -----------------------
+// One thread per 4 consecutive output pixels of a row: 4 byte loads (or one 32-bit load when the source is aligned and
+// not mirrored), 4 mean loads, one 16-byte store.  HBM-bound: 1 + 4 (mean, L2-resident: one image) + 4 B per element.
+__global__ void __launch_bounds__(kBlock) image_transform_u8_kernel(const unsigned char* __restrict__ src, const float* __restrict__ mean,
+                                                                    const int* __restrict__ off, float* __restrict__ dst, int C, int sh, int sw,
+                                                                    int ch, int cw, float scale, size_t groups, int gpr) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const int xg = static_cast<int>(g % gpr);
+    size_t r = g / gpr;
+    const int y = static_cast<int>(r % ch);
+    r /= ch;
+    const int c = static_cast<int>(r % C);
+    const size_t n = r / C;
+    int oy = 0, ox = 0, mir = 0;
+    if (off) { oy = __ldg(off + 3 * n); ox = __ldg(off + 3 * n + 1); mir = __ldg(off + 3 * n + 2); }
+    const size_t srow = ((n * C + c) * sh + oy + y) * static_cast<size_t>(sw) + ox;
+    const size_t mrow = (static_cast<size_t>(c) * sh + oy + y) * static_cast<size_t>(sw) + ox;
+    float* d = dst + ((n * C + c) * ch + y) * static_cast<size_t>(cw) + 4 * xg;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = 4 * xg + j;
+      if (x < cw) {
+        const int xs = mir ? cw - 1 - x : x;
+        const float px = static_cast<float>(__ldg(src + srow + xs));
+        v[j] = __fmul_rn(mean ? __fsub_rn(px, __ldg(mean + mrow + xs)) : px, scale);
+      } else {
+        v[j] = 0.f;
+      }
+    }
+    if (4 * xg + 4 <= cw && (reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
+      *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int j = 0; j < 4 && 4 * xg + j < cw; ++j) d[j] = v[j];
+    }
+  }
+}
+
 // ---- fused momentum SGD (in place): 3 reads + 2 writes = 20 B/param ------------------------------
 __global__ void __launch_bounds__(kBlock) sgd_kernel(float* __restrict__ w, float* __restrict__ delta,
                                                      const float* __restrict__ grad, size_t n, float mom,
@@ -384,7 +423,19 @@ int mnv_relu_mask_inplace(float* dx, const float* x, size_t n, mnv_stream_t s) {
   return launch_inplace(dx, x, n, ReluBackOp{}, as_stream(s));
 }
 
-int mnv_abi_version(void) { return 1; }
+int mnv_image_transform_u8(const unsigned char* src, const float* mean, const int* crop_mirror, float* dst, int N, int C,
+                           int src_h, int src_w, int crop_h, int crop_w, float scale, mnv_stream_t s) {
+  if (N < 0 || C <= 0 || src_h <= 0 || src_w <= 0 || crop_h <= 0 || crop_w <= 0 || crop_h > src_h || crop_w > src_w) return MNV_EINVAL;
+  if (N == 0) return MNV_OK;
+  if (!src || !dst) return MNV_EINVAL;
+  const int gpr = (crop_w + 3) / 4;
+  const size_t groups = static_cast<size_t>(N) * C * crop_h * gpr;
+  image_transform_u8_kernel<<<stream_grid(groups), kBlock, 0, as_stream(s)>>>(src, mean, crop_mirror, dst, C, src_h, src_w, crop_h, crop_w,
+                                                                              scale, groups, gpr);
+  return finish_launch();
+}
+
+int mnv_abi_version(void) { return 2; }
 const char* mnv_build_info(void) {
   return "minerva_b200 kernels: sm_100a, nvcc " __VERSION__ ", built " __DATE__;
 }

@@ -340,6 +340,27 @@ class SoftmaxUnit(ComputeUnit):
         return lossmat.sum(0).sum(1), lossmat.shape[1]
 
 
+class AccuracyUnit(ComputeUnit):
+    """net.py:436-487: top-1 accuracy of the scores against one-hot labels.  Non-lazy like the reference's (count_zero
+    blocks), so it only runs in the TEST phase or when asked (`getacc`)."""
+
+    def __init__(self, name, btm, label, top, top_k=1):
+        super().__init__(name, [btm, label], [top])
+        self.top_k, self.acc, self.batch_size = top_k, 0.0, 0
+
+    def forward(self, from_btm, to_top, phase):
+        self._scores, self._labels = from_btm[self.btm_names[0]], from_btm[self.btm_names[1]]
+        if phase == "TEST":
+            self.getacc()
+
+    def getacc(self):
+        predict = self._scores.max_index(0)
+        truth = self._labels.max_index(0)
+        self.batch_size = self._scores.shape[-1]
+        self.acc = (predict - truth).count_zero() * 1.0 / self.batch_size
+        return self.acc
+
+
 class DataUnit(ComputeUnit):
     """Synthetic data layer: the caller sets `.data` / `.label` (owl NArrays) before forward."""
 

@@ -189,3 +189,80 @@ def test_googlenet_graph_runs(gpu_owl):
     losses = [lu.getloss() for lu in net.get_loss_units()]
     assert len(losses) == 3 and all(np.isfinite(l) and np.log(1000) - 1.0 < l < np.log(1000) + 3.0 for l in losses), losses
     tr.step()
+
+
+def test_image_transform_matches_host_data_layer(gpu_owl):
+    """mnv_image_transform_u8 == the reference data layer's host computation (owl/owl/net/netio.py:300-311):
+    (uint8 image - mean image)[crop window][mirrored] as float32, bit for bit."""
+    import torch
+    from tests import gpu_util as g
+    rs = np.random.RandomState(4)
+    for (N, C, S, crop, scale, use_mean, use_off) in ((5, 3, 40, 33, 1.0, True, True), (3, 1, 28, 28, 1.0 / 255, False, False),
+                                                      (4, 3, 256, 227, 0.017, True, True), (2, 2, 9, 7, 1.0, True, False)):
+        img = rs.randint(0, 256, (N, C, S, S), dtype=np.uint8)
+        mean = (rs.uniform(90, 130, (C, S, S))).astype(np.float32)
+        off = np.stack([rs.randint(0, S - crop + 1, N), rs.randint(0, S - crop + 1, N), rs.randint(0, 2, N)], 1).astype(np.int32)
+        want = np.empty((N, C, crop, crop), np.float32)
+        for n in range(N):
+            oy, ox, mir = off[n] if use_off else (0, 0, 0)
+            im = img[n].astype(np.float32) - (mean if use_mean else np.float32(0))        # netio.py:300
+            w = im[:, oy:oy + crop, ox:ox + crop]
+            want[n] = (w[:, :, ::-1] if mir else w) * np.float32(scale)
+        dst = torch.full((N, C, crop, crop), float("nan"), device="cuda")
+        g.run("mnv_image_transform_u8", torch.from_numpy(img).cuda(), torch.from_numpy(mean).cuda() if use_mean else 0,
+              torch.from_numpy(off).cuda() if use_off else 0, dst, N, C, S, S, crop, crop, float(scale))
+        g.assert_bits_equal(dst.cpu().numpy(), want, "image transform %r" % ((N, C, S, crop),))
+
+
+def test_feed_data_unit_trains(gpu_owl):
+    """A net whose data unit is a HostFeed over a provider (uint8 stored images, random crop + mirror on the device,
+    double-buffered uploads on a copy stream): steps run, every step sees a freshly uploaded batch, the loss is finite."""
+    import torch
+    import minerva_b200.owl.net as onet
+    from minerva_b200.owl import _runtime as rt
+    from minerva_b200.owl.net.data import HostFeed, FeedDataUnit, SyntheticImageProvider
+    from tests.test_net_cpu import _tiny_net
+    from minerva_b200.owl.net.net import _default_backend
+    gpu_owl.set_seed(2)
+    net = _tiny_net(_default_backend())
+    prov = SyntheticImageProvider(8, 3, (21, 21), 5, seed=1, pool=3)
+    feed = HostFeed(gpu_owl, rt, provider=prov, mean=[100.0, 110.0, 120.0], scale=1.0 / 64, crop=(17, 17), mirror=True)
+    du = FeedDataUnit("data", ["data", "label"], feed)
+    du.B = net.B
+    net.units[0] = du
+    net.batch_size = 8
+    tr = onet.NetTrainer(net, None)
+    seen = []
+    for _ in range(5):
+        tr.step()
+        seen.append(du.data.to_numpy().copy())
+        assert du.data.shape == [17, 17, 3, 8] and np.isfinite(net.get_loss_units()[0].getloss())
+    du.close()
+    assert not np.array_equal(seen[0], seen[1])                      # a new minibatch every step
+    lo, hi = (0 - 120.0) / 64, (255 - 100.0) / 64
+    assert all(s.min() >= lo and s.max() <= hi for s in seen)
+
+
+def test_prototxt_alexnet_trains_from_the_feed(gpu_owl):
+    """models/bvlc_alexnet_nogroup_{solver,train_val}.prototxt through CaffeNetBuilder: the Data layer becomes a
+    FeedDataUnit (synthetic 256 x 256 uint8 images, random 227 crop + mirror + mean on the device), in-place ReLU / Dropout
+    layers, fused conv+ReLU planned over the in-place names; two trainer steps at batch 4."""
+    import os
+    import minerva_b200.owl.net as onet
+    from minerva_b200.owl.net import net as N
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gpu_owl.set_seed(9)
+    cb = onet.CaffeNetBuilder(os.path.join(root, "models", "bvlc_alexnet_nogroup_solver.prototxt"))
+    net = cb.build_net(N.Net(), num_gpu=64)                     # 256 / 64 = 4 images per replica
+    du = net.get_data_unit()
+    assert du.geometry["batch"] == 4 and du.geometry["crop"] == (227, 227) and du.geometry["mirror"]
+    du.attach(1000, seed=1)
+    net.batch_size = 4
+    tr = onet.NetTrainer(net, None)
+    tr.step()
+    tr.step()
+    assert sum(1 for u in net.units if isinstance(u, N.ConvConnection) and u.fuse_relu) == 5
+    assert du.data.shape == [227, 227, 3, 4]
+    loss = net.get_loss_units()[0].getloss()
+    assert np.isfinite(loss) and 5.0 < loss < 9.0, loss
+    du.close()
