@@ -162,8 +162,8 @@ def op_work(name, a):
     if name in ("mnv_matmult", "mnv_matmult_ex"):
         return "tensor", 2.0 * a[3] * a[4] * a[5]
     if name in ("mnv_conv_forward", "mnv_conv_forward_relu", "mnv_conv_backward_data", "mnv_conv_backward_filter",
-                "mnv_conv_backward_filter_bias"):
-        off = 4 if name.startswith("mnv_conv_forward") or name.endswith("_bias") else 3
+                "mnv_conv_backward_filter_bias", "mnv_conv_forward_tw", "mnv_conv_backward_data_tw", "mnv_conv_backward_filter_tw"):
+        off = 4 if name.startswith("mnv_conv_forward") or name.endswith("_bias") or name == "mnv_conv_backward_filter_tw" else 3
         N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = a[off:off + 11]
         Ho, Wo = (H + 2 * ph - fh) // sv + 1, (W + 2 * pw - fw) // sh + 1
         return "tensor", 2.0 * N * Ho * Wo * Co * Ci * fh * fw

@@ -315,6 +315,37 @@ int mnv_image_transform_u8(const unsigned char* src, const float* mean, const in
                            int num_images, int num_channels, int src_height, int src_width, int crop_height,
                            int crop_width, float scale, mnv_stream_t stream);
 
+/* ---- channels-last twins shared by the convolution calls of one training step -------------------------
+ * The im2col tensor maps that feed the tensor core read a channels-last copy of an NCHW activation.  One training step
+ * wants each copy several times: forward and backward-filter read the bottom, backward-data and backward-filter read
+ * top_diff.  A caller that keeps the arrays alive between those calls (owl.net does) may own the copy -- the "twin",
+ * mnv_conv_twin_bytes() bytes, 256-byte aligned -- and pass it with an in/out state word: *state == 0: the call fills the
+ * twin (instead of a workspace copy) and sets *state = 1 if it did; *state != 0: the twin is current, the pre-pass is
+ * skipped.  twin == NULL: exactly the reference-shaped entry (copy in the workspace, once per call).  Results are
+ * bit-identical either way.  mnv_conv_twin_wanted(): bit 0 = some direction of this convolution can use a bottom twin,
+ * bit 1 = a top_diff twin (0: do not allocate; no launch).  mnv_conv_backward_filter_tw: bias_diff may be NULL; when it
+ * is not, the bias sums ride on the pass that fills the top_diff twin (so ask for them in the call that fills it). */
+size_t mnv_conv_twin_bytes(int num_images, int num_channels, int height, int width);
+int mnv_conv_twin_wanted(int num_images, int bottom_num_channels, int top_num_channels, int bottom_height,
+                         int bottom_width, int pad_height, int pad_width, int stride_vertical, int stride_horizontal,
+                         int filter_height, int filter_width);
+int mnv_conv_forward_tw(const float* bottom, const float* filter, const float* bias, float* top, int num_images,
+                        int bottom_num_channels, int top_num_channels, int bottom_height, int bottom_width,
+                        int pad_height, int pad_width, int stride_vertical, int stride_horizontal, int filter_height,
+                        int filter_width, int relu, float* bottom_twin, int* bottom_twin_state, void* workspace,
+                        size_t workspace_bytes, mnv_stream_t stream);
+int mnv_conv_backward_data_tw(const float* top_diff, const float* filter, float* bottom_diff, int num_images,
+                              int bottom_num_channels, int top_num_channels, int bottom_height, int bottom_width,
+                              int pad_height, int pad_width, int stride_vertical, int stride_horizontal,
+                              int filter_height, int filter_width, float* top_diff_twin, int* top_diff_twin_state,
+                              void* workspace, size_t workspace_bytes, mnv_stream_t stream);
+int mnv_conv_backward_filter_tw(const float* bottom, const float* top_diff, float* filter_diff, float* bias_diff,
+                                int num_images, int bottom_num_channels, int top_num_channels, int bottom_height,
+                                int bottom_width, int pad_height, int pad_width, int stride_vertical,
+                                int stride_horizontal, int filter_height, int filter_width, float* bottom_twin,
+                                int* bottom_twin_state, float* top_diff_twin, int* top_diff_twin_state, void* workspace,
+                                size_t workspace_bytes, mnv_stream_t stream);
+
 /* ---- explicit in-place forms ------------------------------------------------------------------
  * The entries above never alias an output with an input.  Two callers need to: the data-parallel gradient merge
  * (owl/net/merge.py: shard += peer's shard; the reference's `wgrad[upd_gpu] += wgrad[gid]`, owl/owl/net/trainer.py:131-135)

@@ -913,8 +913,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             } else if (p.a_mode == TMA_A_TILED_K) {
 #pragma unroll
               for (int h = 0; h < kHalves; ++h) tma_load_2d(a_dst + h * kABytes, &tmap_a, bar, ks * BK, t.mt * kTileM + h * BM);
-            } else {   // k-stage = 32 output pixels of one image (p.spi stages per image)
-              const int img = ks / p.spi, pix = (ks - img * p.spi) * BK, oh = pix / p.Wo;
+            } else {   // k-stage = 32 output pixels: of one image (p.spi stages per image, top_diff padded per image), or
+                       // spi == 0: 32 consecutive pixels of the flat (image, pixel) axis -- the im2col walk wraps into the
+                       // next image exactly as the channels-last top_diff's rows do, so nothing is padded
+              int img, pix;
+              if (p.spi > 0) { img = ks / p.spi; pix = (ks - img * p.spi) * BK; }
+              else { const int hw = p.Ho * p.Wo, m0 = ks * BK; img = m0 / hw; pix = m0 - img * hw; }
+              const int oh = pix / p.Wo;
               const int h = oh * p.sv - p.ph, w = (pix - oh * p.Wo) * p.sh - p.pw;
 #pragma unroll
               for (int j = 0; j < kChunks; ++j) tma_load_im2col_4d(a_dst + j * 4096, &tmap_a, bar, a_c[j], w, h, img, a_kw[j], a_kh[j]);
@@ -1458,6 +1463,7 @@ MNV_OPT g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
 MNV_OPT g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
 MNV_OPT g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
 MNV_OPT g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
+MNV_OPT g_opt_no_nhwc_wgrad{0}; // 1: backward-filter keeps the re-pitched NCHW top_diff (K-major B) instead of the channels-last one (tuning)
 MNV_OPT g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1550,8 +1556,10 @@ static bool make_im2col_tmap(CUtensorMap* tm, const float* x, int Cp, int W, int
 // x[n][c][hw] -> y[n][hw][Cp]: channels-last copy for the im2col tensor maps, channels C..Cp-1 zero (rounding to
 // TF32 is done by the TFLOAT32-typed tensor map).  Tiles go through shared memory so both sides stay coalesced.
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cp, int HW,
-                                                           int tiles_c, int tiles_hw, long long total_tiles) {
-  // tile = 32 channels x 128 pixels: 16 independent 128-byte-per-warp loads per thread before the barrier
+                                                           int tiles_c, int tiles_hw, long long total_tiles, float* __restrict__ tilesum) {
+  // tile = 32 channels x 128 pixels: 16 independent 128-byte-per-warp loads per thread before the barrier.
+  // tilesum != null: the pass also leaves the sum of every (image, pixel tile, channel) in tilesum[(n * tiles_hw + th) * C + c]
+  // -- for a top_diff that is ConvBackwardBias's per-tile partial, folded over (n, th) by rowsum_fold_kernel in a fixed order.
   __shared__ float tile[32][129];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -1564,10 +1572,18 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = wid + 8 * i;
+      float acc = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int hw = lane + 32 * j;
-        tile[c][hw] = (c0 + c < C && h0 + hw < HW) ? __ldg(src + static_cast<size_t>(c) * HW + hw) : 0.f;
+        const float v = (c0 + c < C && h0 + hw < HW) ? __ldg(src + static_cast<size_t>(c) * HW + hw) : 0.f;
+        tile[c][hw] = v;
+        acc += v;
+      }
+      if (tilesum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && c0 + c < C) tilesum[(n * tiles_hw + th) * C + c0 + c] = acc;
       }
     }
     __syncthreads();
@@ -2017,13 +2033,24 @@ static int check_conv(int N, int Ci, int Co, int H, int W, int ph, int pw, int s
 static bool fits_int(long long v) { return v > 0 && v < 0x7fffffffLL; }
 
 static size_t round256(size_t v) { return (v + 255) / 256 * 256; }
-static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, cudaStream_t s) {
+static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, cudaStream_t s, float* tilesum = nullptr) {
   const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
   const long long total = static_cast<long long>(N) * tiles_c * tiles_hw;
   const long long cap = static_cast<long long>(kNumSMs) * 16;
-  nchw_to_nhwc_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(x, y, C, Cp, HW, tiles_c, tiles_hw, total);
+  nchw_to_nhwc_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum);
   return finish_launch();
 }
+
+// Channels-last "twin" of an NCHW activation, owned by the CALLER (mnv_conv_twin_bytes): several calls of one training
+// step want the same copy (forward and backward-filter read x, backward-data and backward-filter read top_diff), so the
+// *_tw entry points take (pointer, in/out state) and whichever call comes first fills it.  Without a twin the copy goes
+// to the workspace, once per call, as before.
+struct Twin {
+  float* ptr;        // null: none
+  int* state;        // *state != 0: already filled
+  bool usable() const { return ptr != nullptr && state != nullptr; }
+  bool valid() const { return usable() && *state != 0; }
+};
 
 // Cross-correlation of x[N][Ci][H][W] with `ff` taps as a GEMM whose two operands both arrive through TMA:
 //   A[m = (n,oh,ow)][k = (tap, c)]  channels-last copy of x through an im2col tensor map (no gather warps, padding
@@ -2034,7 +2061,7 @@ static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, c
 // the gather kernel.
 static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long long w_sc, int flip, const float* bias, int relu, float* out, int N,
                           int Ci, int Co, int H, int W, int Ho, int Wo, int ph, int pw, int sv, int sh, int fh, int fw, void* ws,
-                          size_t ws_bytes, cudaStream_t s, bool* done, const S2D* s2d = nullptr) {
+                          size_t ws_bytes, cudaStream_t s, bool* done, const S2D* s2d = nullptr, Twin twin = Twin{nullptr, nullptr}) {
   // s2d != null: x and w are the REAL strided convolution's operands (w strides w_sn / w_sc over its real taps) and the
   // geometry arguments describe its stride-1 space-to-depth view; only the two pre-passes differ.
   *done = false;
@@ -2046,10 +2073,11 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   const int Cp = (Ci + 3) / 4 * 4;
   const long long M = static_cast<long long>(N) * Ho * Wo, K = static_cast<long long>(ff) * cpt * BK;
   if (!fits_int(M) || !fits_int(K) || !fits_int(static_cast<long long>(N) * H * W * Cp)) return MNV_OK;
-  const size_t x_bytes = round256(static_cast<size_t>(N) * H * W * Cp * sizeof(float));
+  const bool use_twin = twin.usable() && !s2d;
+  const size_t x_bytes = use_twin ? 0 : round256(static_cast<size_t>(N) * H * W * Cp * sizeof(float));
   const size_t b_bytes = round256(static_cast<size_t>(Co) * K * sizeof(float));
   if (ws_bytes < x_bytes + b_bytes) return MNV_OK;
-  float* xh = static_cast<float*>(ws);
+  float* xh = use_twin ? twin.ptr : static_cast<float*>(ws);
   float* wb = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + x_bytes);
   void* ws2 = static_cast<uint8_t*>(ws) + x_bytes + b_bytes;
   const size_t ws2_bytes = ws_bytes - x_bytes - b_bytes;
@@ -2076,7 +2104,12 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   memset(&tm_b, 0, sizeof(tm_b));
   if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
   if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
-  int rc = s2d ? launch_s2d(x, xh, N, *s2d, Cp, s) : launch_nhwc(x, xh, N, Ci, Cp, H * W, s);
+  int rc = MNV_OK;
+  if (s2d) rc = launch_s2d(x, xh, N, *s2d, Cp, s);
+  else if (!(use_twin && twin.valid())) {
+    rc = launch_nhwc(x, xh, N, Ci, Cp, H * W, s);
+    if (!rc && use_twin) *twin.state = 1;
+  }
   if (rc) return rc;
   if (s2d) s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, *s2d, cpt, 0, 4, static_cast<int>(K), w_sn, w_sc, flip, prepass_round());
   else filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
@@ -2171,6 +2204,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "s2d_im2col") return g_opt_s2d_im2col.exchange(value);
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
+  if (k == "no_nhwc_wgrad") return g_opt_no_nhwc_wgrad.exchange(value);
   return -1;
 }
 #endif
@@ -2254,7 +2288,7 @@ int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k
 
 static int conv_forward_impl(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
                              int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
-                             size_t workspace_bytes, mnv_stream_t stream, int relu);
+                             size_t workspace_bytes, mnv_stream_t stream, int relu, Twin twin = Twin{nullptr, nullptr});
 int mnv_conv_forward(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
                      int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
                      size_t workspace_bytes, mnv_stream_t stream) {
@@ -2265,9 +2299,32 @@ int mnv_conv_forward_relu(const float* bottom, const float* filter, const float*
                           size_t workspace_bytes, mnv_stream_t stream) {
   return conv_forward_impl(bottom, filter, bias, top, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes, stream, 1);
 }
+int mnv_conv_forward_tw(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci, int Co, int H, int W,
+                        int ph, int pw, int sv, int sh, int fh, int fw, int relu, float* bottom_twin, int* bottom_twin_state,
+                        void* workspace, size_t workspace_bytes, mnv_stream_t stream) {
+  return conv_forward_impl(bottom, filter, bias, top, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes, stream, relu ? 1 : 0,
+                           Twin{bottom_twin, bottom_twin_state});
+}
+int mnv_conv_twin_wanted(int N, int Ci, int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw) {
+  if (check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw) || N == 0 || !get_im2col_fn() || !get_encode_fn()) return 0;
+  const int ff = fh * fw;
+  const bool lim = ph <= 127 && pw <= 127 && fh - 1 - ph <= 128 && fw - 1 - pw <= 128 && sv <= 8 && sh <= 8;
+  auto chan_ok = [](int c) { return ((c + BK - 1) / BK) * BK * 2 <= c * 3; };
+  S2D v;
+  const int Ho = (H + 2 * ph - fh) / sv + 1, Wo = (W + 2 * pw - fw) / sh + 1;
+  const bool shift = s2d_plan(&v, Ci, H, W, Ho, Wo, ph, pw, sv, sh, fh, fw);
+  const bool fwd = !shift && lim && chan_ok(Ci) && !(static_cast<long long>(Co) * ff < 3000 && Co > 128);
+  const bool dgrad = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && chan_ok(Co) && !(static_cast<long long>(Ci) * ff < 3000 && Ci > 128);
+  const bool wgrad = lim && chan_ok(Ci);
+  return ((fwd || wgrad) ? 1 : 0) | ((dgrad || wgrad) ? 2 : 0);
+}
+size_t mnv_conv_twin_bytes(int N, int C, int H, int W) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return round256(static_cast<size_t>(N) * H * W * ((C + 3) / 4 * 4) * sizeof(float));
+}
 static int conv_forward_impl(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
                              int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
-                             size_t workspace_bytes, mnv_stream_t stream, int relu) {
+                             size_t workspace_bytes, mnv_stream_t stream, int relu, Twin twin) {
   int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
   if (rc) return rc;
   if (N == 0) return MNV_OK;
@@ -2291,7 +2348,7 @@ static int conv_forward_impl(const float* bottom, const float* filter, const flo
     bool done = false;
     rc = conv_tma_fprop(bottom, filter, static_cast<long long>(Ci) * fh * fw, fh * fw, 1, bias, relu, top, N, Ci, Co, H, W,
                         (H + 2 * ph - fh) / sv + 1, (W + 2 * pw - fw) / sh + 1, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes,
-                        as_stream(stream), &done);
+                        as_stream(stream), &done, nullptr, twin);
     if (rc || done) return rc;
   }
   GemmParams p;
@@ -2307,9 +2364,24 @@ static int conv_forward_impl(const float* bottom, const float* filter, const flo
   return launch_gemm<A_IM2COL_FWD, B_KMAJOR>(p, workspace, workspace_bytes, as_stream(stream));
 }
 
+static int conv_backward_data_impl(const float* top_diff, const float* filter, float* bottom_diff, int N, int Ci, int Co,
+                                   int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                                   size_t workspace_bytes, mnv_stream_t stream, Twin twin);
 int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bottom_diff, int N, int Ci, int Co,
                            int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
                            size_t workspace_bytes, mnv_stream_t stream) {
+  return conv_backward_data_impl(top_diff, filter, bottom_diff, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes, stream,
+                                 Twin{nullptr, nullptr});
+}
+int mnv_conv_backward_data_tw(const float* top_diff, const float* filter, float* bottom_diff, int N, int Ci, int Co, int H, int W,
+                              int ph, int pw, int sv, int sh, int fh, int fw, float* top_diff_twin, int* top_diff_twin_state,
+                              void* workspace, size_t workspace_bytes, mnv_stream_t stream) {
+  return conv_backward_data_impl(top_diff, filter, bottom_diff, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes, stream,
+                                 Twin{top_diff_twin, top_diff_twin_state});
+}
+static int conv_backward_data_impl(const float* top_diff, const float* filter, float* bottom_diff, int N, int Ci, int Co,
+                                   int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
+                                   size_t workspace_bytes, mnv_stream_t stream, Twin twin) {
   int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
   if (rc) return rc;
   if (N == 0) return MNV_OK;
@@ -2345,7 +2417,7 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
     // operator) cancel
     bool done = false;
     rc = conv_tma_fprop(top_diff, filter, fh * fw, static_cast<long long>(Ci) * fh * fw, 0, nullptr, 0, bottom_diff, N, Co, Ci, Ho, Wo, H, W,
-                        fh - 1 - ph, fw - 1 - pw, 1, 1, fh, fw, workspace, workspace_bytes, as_stream(stream), &done);
+                        fh - 1 - ph, fw - 1 - pw, 1, 1, fh, fw, workspace, workspace_bytes, as_stream(stream), &done, nullptr, twin);
     if (rc || done) return rc;
   }
   filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(
@@ -2375,7 +2447,8 @@ int mnv_conv_backward_data(const float* top_diff, const float* filter, float* bo
 
 static int conv_backward_filter_impl(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
                                      int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
-                                     size_t workspace_bytes, mnv_stream_t stream, float* bias_diff, bool* bias_done);
+                                     size_t workspace_bytes, mnv_stream_t stream, float* bias_diff, bool* bias_done,
+                                     Twin xtw = Twin{nullptr, nullptr}, Twin dtw = Twin{nullptr, nullptr});
 int mnv_conv_backward_filter(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
                              int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
                              size_t workspace_bytes, mnv_stream_t stream) {
@@ -2401,9 +2474,26 @@ int mnv_conv_backward_filter_bias(const float* bottom, const float* top_diff, fl
   return mnv_conv_backward_bias(top_diff, bias_diff, N, Co, (H + 2 * ph - fh) / sv + 1, (W + 2 * pw - fw) / sh + 1, workspace,
                                 workspace_bytes, stream);
 }
+int mnv_conv_backward_filter_tw(const float* bottom, const float* top_diff, float* filter_diff, float* bias_diff, int N, int Ci, int Co,
+                                int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, float* bottom_twin, int* bottom_twin_state,
+                                float* top_diff_twin, int* top_diff_twin_state, void* workspace, size_t workspace_bytes,
+                                mnv_stream_t stream) {
+  int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
+  if (rc) return rc;
+  if (bias_diff && N == 0) {
+    rc = mnv_fill(bias_diff, static_cast<size_t>(Co), 0.f, stream);
+    if (rc) return rc;
+  }
+  bool bias_done = false;
+  rc = conv_backward_filter_impl(bottom, top_diff, filter_diff, N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw, workspace, workspace_bytes,
+                                 stream, bias_diff, &bias_done, Twin{bottom_twin, bottom_twin_state}, Twin{top_diff_twin, top_diff_twin_state});
+  if (rc || !bias_diff || bias_done || N == 0) return rc;
+  return mnv_conv_backward_bias(top_diff, bias_diff, N, Co, (H + 2 * ph - fh) / sv + 1, (W + 2 * pw - fw) / sh + 1, workspace,
+                                workspace_bytes, stream);
+}
 static int conv_backward_filter_impl(const float* bottom, const float* top_diff, float* filter_diff, int N, int Ci, int Co,
                                      int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
-                                     size_t workspace_bytes, mnv_stream_t stream, float* bias_diff, bool* bias_done) {
+                                     size_t workspace_bytes, mnv_stream_t stream, float* bias_diff, bool* bias_done, Twin xtw, Twin dtw) {
   *bias_done = false;
   int rc = check_conv(N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw);
   if (rc) return rc;
@@ -2423,6 +2513,60 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
   if (g_opt_simt.load() || g_opt_no_tma.load())
     return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, workspace, workspace_bytes, s);
 
+  {  // Both operands channels-last, both MN-major, k = the flat (image, pixel) axis: A = bottom through an im2col map
+     // (32 pixels x 4 boxes of 32 channels per tap), B = top_diff[(n, pixel)][co] as a plain 2-D tensor (boxes of 32 co x
+     // 32 pixels).  The im2col walk and the rows of B wrap from one image into the next identically, so nothing is padded
+     // per image, top_diff needs no re-pitch, and the two copies are the ones forward / backward-data use (twins).
+    const int cpt = (Ci + BK - 1) / BK, Cp = (Ci + 3) / 4 * 4, Cop = (Co + 3) / 4 * 4;
+    const int tiles_hw = (P + 127) / 128;
+    const bool geom_ok = cpt * BK * 2 <= Ci * 3 && ph <= 127 && pw <= 127 && fh - 1 - ph <= 128 && fw - 1 - pw <= 128 && sv <= 8 && sh <= 8 &&
+                         fits_int(static_cast<long long>(N) * H * W * Cp) && fits_int(static_cast<long long>(N) * P * Cop);
+    if (geom_ok && !(g_opt_no_tma_a.load() & 4) && !g_opt_no_nhwc_wgrad.load() && get_im2col_fn() && get_encode_fn()) {
+      uint8_t* ws = static_cast<uint8_t*>(workspace);
+      size_t ws_left = workspace ? workspace_bytes : 0;
+      const size_t x_bytes = xtw.usable() ? 0 : round256(static_cast<size_t>(N) * H * W * Cp * sizeof(float));
+      const size_t d_bytes = dtw.usable() ? 0 : round256(static_cast<size_t>(N) * P * Cop * sizeof(float));
+      const bool ride_bias = bias_diff != nullptr && !dtw.valid();
+      const size_t ts_bytes = ride_bias ? round256(static_cast<size_t>(N) * tiles_hw * Co * sizeof(float)) : 0;
+      if (ws_left >= x_bytes + d_bytes + ts_bytes) {
+        float* xh = xtw.usable() ? xtw.ptr : reinterpret_cast<float*>(ws);
+        float* dyh = dtw.usable() ? dtw.ptr : reinterpret_cast<float*>(ws + x_bytes);
+        float* tilesum = ride_bias ? reinterpret_cast<float*>(ws + x_bytes + d_bytes) : nullptr;
+        ws += x_bytes + d_bytes + ts_bytes; ws_left -= x_bytes + d_bytes + ts_bytes;
+        GemmParams q = p;
+        q.a = xh; q.b = dyh; q.M = fh * fw * cpt * BK; q.a_mode = TMA_A_IM2COL_MN; q.b_mn = 1; q.cpt = cpt; q.out_mode = 1; q.spi = 0;
+        q.P = q.M; q.col_stride = static_cast<long long>(Ci) * fh * fw; q.ldb = Cop; q.b_vec = 1;
+        plan_tiles(q, ws_left, false, true);
+        q.bn = (q.bn + 31) / 32 * 32;                  // MN-major B: boxes of 32 columns
+        if (q.bn > BN_MAX) q.bn = BN_MAX;
+        q.n_tiles = (q.N + q.bn - 1) / q.bn;
+        plan_splits(q, ws_left);
+        q.partial = q.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+        CUtensorMap tm_a, tm_b;
+        memset(&tm_a, 0, sizeof(tm_a));
+        memset(&tm_b, 0, sizeof(tm_b));
+        if (make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true) && make_a_mn_tmap(&tm_b, dyh, Co, q.K, Cop)) {
+          if (!xtw.valid()) {
+            rc = launch_nhwc(bottom, xh, N, Ci, Cp, H * W, s);
+            if (rc) return rc;
+            if (xtw.usable()) *xtw.state = 1;
+          }
+          if (!dtw.valid()) {
+            rc = launch_nhwc(top_diff, dyh, N, Co, Cop, P, s, tilesum);
+            if (rc) return rc;
+            if (dtw.usable()) *dtw.state = 1;
+            if (tilesum) {   // ConvBackwardBias rides on the pass: per-(image, pixel tile, channel) sums, folded in a fixed order
+              rowsum_fold_kernel<<<(Co + 31) / 32, 256, 0, s>>>(tilesum, bias_diff, N * tiles_hw, Co);
+              rc = finish_launch();
+              if (rc) return rc;
+              *bias_done = true;
+            }
+          }
+          return launch_umma_tma(q, tm_a, tm_b, s);
+        }
+      }
+    }
+  }
   // TMA-fed top_diff: rows must be 16-byte pitched.  When Ho*Wo % 4 != 0 the tensor is re-pitched
   // into the workspace first (one streaming pass, << the GEMM).  Each image's pixel range is padded to
   // a whole number of 32-pixel k-stages so a TMA box never straddles two images.

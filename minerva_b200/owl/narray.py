@@ -1,5 +1,6 @@
 """owl.NArray -- same operators and static methods as the reference binding
 (owl/owl/libowl.pyx:51-444 over minerva/narray/*.cpp); each maps to one C-ABI call."""
+import ctypes
 import weakref
 
 import numpy as np
@@ -74,11 +75,36 @@ class NArray:
     # to the tensor-core kernel (mnv_matmult_ex) and the reference's explicit transposes in FullyConnected.bp
     # (owl/owl/net/net.py:612-614) were pure HBM traffic.  `_views` lists pending transposes of this array so that
     # the one in-place op (sgd_update) can materialise them before it overwrites their source.
-    __slots__ = ("_buf", "_shape", "_dev", "_lazy_src", "_views", "__weakref__")
+    # `_twin` = (flat device buffer, ctypes.c_int state): the channels-last copy of a 4-D activation that the convolution
+    # calls of one training step share (include/mnv.h, mnv_conv_*_tw): forward fills the bottom's twin and backward-filter
+    # reuses it, backward-filter fills top_diff's and backward-data reuses it.  Arrays are immutable once produced (the only
+    # in-place op, sgd_update, touches parameters), so a filled twin stays current for the array's lifetime.
+    __slots__ = ("_buf", "_shape", "_dev", "_lazy_src", "_views", "_twin", "__weakref__")
+    use_twins = True     # Net.fuse_conv_twins: False = every convolution call makes its own workspace copy (the plain entries)
+    _twin_wanted = {}    # geometry -> mnv_conv_twin_wanted bitmask
 
     def __init__(self, tensor, shape, dev):
         self._buf, self._shape, self._dev = tensor, [int(s) for s in shape], dev
-        self._lazy_src, self._views = None, None
+        self._lazy_src, self._views, self._twin = None, None, None
+
+    @staticmethod
+    def _twins(geo, bottom, top_diff, dev):
+        """-> [bottom twin ptr, byref(state), top_diff twin ptr, byref(state)] for one convolution geometry
+        (None, None where a twin is not wanted / no array given); buffers are allocated on first use."""
+        want = NArray._twin_wanted.get(geo)
+        if want is None:
+            want = NArray._twin_wanted[geo] = _lib.load().mnv_conv_twin_wanted(*geo) if NArray.use_twins else 0
+        out = []
+        for bit, arr in ((1, bottom), (2, top_diff)):
+            if arr is None or not (want & bit) or not NArray.use_twins or arr._dev is not dev:
+                out += [None, None]
+                continue
+            if arr._twin is None:
+                W, H, C, N = arr._shape
+                nbytes = _lib.load().mnv_conv_twin_bytes(N, C, H, W)
+                arr._twin = (torch.empty(nbytes // 4, dtype=torch.float32, device=dev.device), ctypes.c_int(0))
+            out += [arr._twin[0].data_ptr(), ctypes.byref(arr._twin[1])]
+        return out
 
     @property
     def _t(self):
@@ -392,9 +418,10 @@ class NArray:
         Ho = (H + 2 * info.pad_height - fh) // info.stride_vertical + 1
         dev = _rt.current_device()
         out = NArray._new([Wo, Ho, Co, N], dev)
-        NArray._call("mnv_conv_forward_relu" if relu else "mnv_conv_forward", dev, src._on(dev).data_ptr(), filt._on(dev).data_ptr(), bias._on(dev).data_ptr(),
-                     out._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
-                     info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
+        geo = (N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal, fh, fw)
+        xt, xs, _, _ = NArray._twins(geo, src, None, dev)
+        NArray._call("mnv_conv_forward_tw", dev, src._on(dev).data_ptr(), filt._on(dev).data_ptr(), bias._on(dev).data_ptr(),
+                     out._t.data_ptr(), *geo, 1 if relu else 0, xt, xs, dev.ws_ptr, dev.ws_bytes)
         return out
 
     @staticmethod
@@ -404,9 +431,10 @@ class NArray:
         _check(diff._shape[2] == Co, "#output channels mismatch")
         dev = _rt.current_device()
         out = NArray._new(bottom._shape, dev)
-        NArray._call("mnv_conv_backward_data", dev, diff._on(dev).data_ptr(), filt._on(dev).data_ptr(), out._t.data_ptr(),
-                     N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal,
-                     fh, fw, dev.ws_ptr, dev.ws_bytes)
+        geo = (N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal, fh, fw)
+        _, _, dt, ds = NArray._twins(geo, None, diff, dev)
+        NArray._call("mnv_conv_backward_data_tw", dev, diff._on(dev).data_ptr(), filt._on(dev).data_ptr(), out._t.data_ptr(),
+                     *geo, dt, ds, dev.ws_ptr, dev.ws_bytes)
         return out
 
     @staticmethod
@@ -416,9 +444,9 @@ class NArray:
         _check(diff._shape[3] == N, "#images mismatch")
         dev = _rt.current_device()
         out = NArray._new(filt._shape, dev)
-        NArray._call("mnv_conv_backward_filter", dev, bottom._on(dev).data_ptr(), diff._on(dev).data_ptr(),
-                     out._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
-                     info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
+        geo = (N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal, fh, fw)
+        NArray._call("mnv_conv_backward_filter_tw", dev, bottom._on(dev).data_ptr(), diff._on(dev).data_ptr(), out._t.data_ptr(), None,
+                     *geo, *NArray._twins(geo, bottom, diff, dev), dev.ws_ptr, dev.ws_bytes)
         return out
 
     @staticmethod
@@ -429,9 +457,9 @@ class NArray:
         _check(diff._shape[3] == N, "#images mismatch")
         dev = _rt.current_device()
         dw, db = NArray._new(filt._shape, dev), NArray._new([Co], dev)
-        NArray._call("mnv_conv_backward_filter_bias", dev, bottom._on(dev).data_ptr(), diff._on(dev).data_ptr(),
-                     dw._t.data_ptr(), db._t.data_ptr(), N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical,
-                     info.stride_horizontal, fh, fw, dev.ws_ptr, dev.ws_bytes)
+        geo = (N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal, fh, fw)
+        NArray._call("mnv_conv_backward_filter_tw", dev, bottom._on(dev).data_ptr(), diff._on(dev).data_ptr(), dw._t.data_ptr(),
+                     db._t.data_ptr(), *geo, *NArray._twins(geo, bottom, diff, dev), dev.ws_ptr, dev.ws_bytes)
         return dw, db
 
     @staticmethod

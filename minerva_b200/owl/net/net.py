@@ -392,6 +392,7 @@ class Net(object):
         self.fuse_lrn_recompute = True   # False: LRN keeps the reference's (bottom, top, scale) three-array form
         self.fuse_pool_index = True      # False: max pooling backward recomputes the arg-max from the bottom
         self.fuse_conv_grads = True      # False: ConvBackwardFilter and ConvBackwardBias stay two ops
+        self.fuse_conv_twins = True      # False: every convolution call makes its own channels-last workspace copy
 
     def add_unit(self, unit):
         unit.B = self.B
@@ -414,6 +415,9 @@ class Net(object):
         the two-op sequence (owl/owl/net/net.py:281-296 after :621-716).  Only backends that advertise the fused
         entry point take part (the CPU twin used by the parity tests does not)."""
         self._fusion_planned = True
+        if hasattr(self.B.owl, "NArray") and hasattr(self.B.owl.NArray, "use_twins"):
+            self.B.owl.NArray.use_twins = bool(self.fuse_conv_twins)
+            self.B.owl.NArray._twin_wanted = {}
         for u in self.units:
             if isinstance(u, LRNUnit):
                 u.lite = bool(self.fuse_lrn_recompute)

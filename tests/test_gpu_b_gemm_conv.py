@@ -395,3 +395,72 @@ def test_conv_full_size_properties(g):
     y2 = g.empty(y.numel())
     g.run("mnv_conv_forward", 2 * x, w, b, y2, *geo, ws, ws.numel())
     assert torch.equal(y2, 2 * y)
+
+
+@pytest.mark.parametrize("case", [TMA_CASES[0], TMA_CASES[1], TMA_CASES[4], TMA_CASES[5], TMA_CASES[7], CONV_CASES[2], CONV_CASES[8]])
+def test_conv_twin_entries(g, case):
+    """mnv_conv_*_tw: a caller-owned channels-last twin, filled by whichever call comes first and reused by the next,
+    gives the bits of the plain entries (which make the same copy in the workspace per call); the bias sums that ride on
+    the top_diff twin's fill are within 1e-5 of sum |top_diff|; geometries that cannot use a twin leave the state at 0."""
+    import ctypes
+    import torch
+    from minerva_b200 import _lib
+    lib = _lib.load()
+    N, Ci, Co, H, W, ph, pw, sv, sh, fh, fw = case
+    Ho, Wo = orc.conv_out(H, ph, fh, sv), orc.conv_out(W, pw, fw, sh)
+    geo = tuple(case)
+    x = rng.normal(0, 1, N * Ci * H * W).astype(np.float32)
+    w = rng.normal(0, 1, Co * Ci * fh * fw).astype(np.float32)
+    b = rng.normal(0, 1, Co).astype(np.float32)
+    dy = rng.normal(0, 1, N * Co * Ho * Wo).astype(np.float32)
+    dx_, dw_, db_, dyd = g.dev(x), g.dev(w), g.dev(b), g.dev(dy)
+    ws = g.workspace()
+    want = lib.mnv_conv_twin_wanted(*geo)
+
+    def twin(n, c, h, wd):
+        t = torch.full((max(lib.mnv_conv_twin_bytes(n, c, h, wd) // 4, 1),), float("nan"), device="cuda")
+        return t, ctypes.c_int(0)
+    xt, xs = twin(N, Ci, H, W)
+    dt, ds = twin(N, Co, Ho, Wo)
+    st = g.stream()
+
+    def call(name, *a):
+        _lib.check(getattr(lib, name)(*[v.data_ptr() if isinstance(v, torch.Tensor) else v for v in a], st), name)
+        torch.cuda.synchronize()
+    # forward: plain vs twin (fills) vs twin (reuses)
+    y0, y1, y2 = (torch.full((N * Co * Ho * Wo,), float("nan"), device="cuda") for _ in range(3))
+    call("mnv_conv_forward_relu", dx_, dw_, db_, y0, *geo, ws, ws.numel())
+    call("mnv_conv_forward_tw", dx_, dw_, db_, y1, *geo, 1, xt, ctypes.byref(xs), ws, ws.numel())
+    filled_by_fwd = xs.value
+    call("mnv_conv_forward_tw", dx_, dw_, db_, y2, *geo, 1, xt, ctypes.byref(xs), ws, ws.numel())
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    assert g.norm_rel(g.host(y0), np.maximum(orc.conv_forward(x, w, b, *geo), 0)) < TOL
+    if not (want & 1):
+        assert xs.value == 0
+    # backward filter (+ bias riding on the top_diff twin's fill), then backward data reusing that twin
+    f0, f1 = (torch.full((w.size,), float("nan"), device="cuda") for _ in range(2))
+    b0, b1 = (torch.full((Co,), float("nan"), device="cuda") for _ in range(2))
+    call("mnv_conv_backward_filter_bias", dx_, dyd, f0, b0, *geo, ws, ws.numel())
+    call("mnv_conv_backward_filter_tw", dx_, dyd, f1, b1, *geo, xt, ctypes.byref(xs), dt, ctypes.byref(ds), ws, ws.numel())
+    assert torch.equal(f0, f1)
+    assert g.norm_rel(g.host(f1), orc.conv_backward_filter(x, dy, *geo)) < TOL
+    wb = orc.conv_backward_bias(dy, N, Co, Ho, Wo)
+    tol_b = 1e-5 * np.abs(dy).reshape(N, Co, -1).sum((0, 2)).max()
+    assert np.abs(g.host(b1) - wb).max() <= tol_b and np.abs(g.host(b0) - wb).max() <= tol_b
+    if want & 2:
+        assert ds.value == 1 and (xs.value == 1 or not (want & 1))
+        nhwc = g.host(dt)[:N * Ho * Wo * ((Co + 3) // 4 * 4)].reshape(N, Ho * Wo, -1)[:, :, :Co]
+        np.testing.assert_array_equal(nhwc, dy.reshape(N, Co, Ho * Wo).transpose(0, 2, 1))      # the twin IS the channels-last copy
+    # second call with both twins current: no pre-pass, same bits; bias now comes from the stand-alone reduction
+    f2, b2 = torch.full((w.size,), float("nan"), device="cuda"), torch.full((Co,), float("nan"), device="cuda")
+    call("mnv_conv_backward_filter_tw", dx_, dyd, f2, b2, *geo, xt, ctypes.byref(xs), dt, ctypes.byref(ds), ws, ws.numel())
+    assert torch.equal(f0, f2) and np.abs(g.host(b2) - wb).max() <= tol_b
+    d0, d1 = (torch.full((x.size,), float("nan"), device="cuda") for _ in range(2))
+    call("mnv_conv_backward_data", dyd, dw_, d0, *geo, ws, ws.numel())
+    call("mnv_conv_backward_data_tw", dyd, dw_, d1, *geo, dt, ctypes.byref(ds), ws, ws.numel())
+    assert torch.equal(d0, d1)
+    assert g.norm_rel(g.host(d1), orc.conv_backward_data(dy, w, *geo)) < TOL
+    # null twins == the plain entries
+    call("mnv_conv_backward_filter_tw", dx_, dyd, f2, 0, *geo, 0, 0, 0, 0, ws, ws.numel())
+    assert torch.equal(f0, f2)
+    assert filled_by_fwd in (0, 1)

@@ -125,7 +125,7 @@ def test_conv_relu_fusion_is_bit_identical(gpu_owl):
     for fuse in (True, False):
         gpu_owl.set_seed(5)
         net = _tiny_net(_default_backend())
-        net.fuse_conv_relu = net.fuse_relu_backward = net.fuse_lrn_recompute = net.fuse_pool_index = net.fuse_conv_grads = fuse
+        net.fuse_conv_relu = net.fuse_relu_backward = net.fuse_lrn_recompute = net.fuse_pool_index = net.fuse_conv_grads = net.fuse_conv_twins = fuse
         du = net.get_data_unit()
         du.data, du.label = _batch(net.B, 8)
         net.batch_size = 8
