@@ -223,6 +223,8 @@ def op_work(name, a):
         return "hbm", 4.0 * a[1]
     if name == "mnv_sgd_momentum_update":
         return "hbm", 20.0 * a[3]
+    if name == "mnv_sgd_momentum_update_multi":
+        return "hbm", 20.0 * a[3]          # the owl binding reports (.., .., .., total parameters) to the profiler
     if name == "mnv_image_transform_u8":
         return "hbm", 5.0 * a[4] * a[5] * a[8] * a[9]        # 1 B in + 4 B out per element (the mean image stays in L2)
     return None, 0.0

@@ -75,6 +75,12 @@ int mnv_elewise_exp(const float* in, float* out, size_t n, mnv_stream_t stream);
 int mnv_elewise_ln(const float* in, float* out, size_t n, mnv_stream_t stream);
 int mnv_elewise_negative(const float* in, float* out, size_t n, mnv_stream_t stream);
 
+/* Exact mode: the same three ops returning the CPU reference's bits -- glibc 2.39's expf / logf restated in
+ * double precision (minerva_b200/csrc/glibc_math.h, pinned against libm on all 2^32 inputs).  The default entries above
+ * use CUDA's expf / logf (<= 2 ulp from glibc, ~1.3x faster). */
+int mnv_elewise_exp_exact(const float* in, float* out, size_t n, mnv_stream_t stream);
+int mnv_elewise_ln_exact(const float* in, float* out, size_t n, mnv_stream_t stream);
+
 /* ---- a7 NormArithmetic on a column-major {m,n} matrix (cuda_perform.h:25-33) ---------------
  * "OnCol": vec has n entries, res[i + j*m] = matrix[i + j*m] o vec[j]   (dims_to_replicate {0})
  * "OnRow": vec has m entries, res[i + j*m] = matrix[i + j*m] o vec[i]   (dims_to_replicate {1}) */
@@ -191,6 +197,12 @@ int mnv_relu_forward(const float* bottom, float* top, int num_images, int num_ch
                      int height, int width, mnv_stream_t stream);
 int mnv_tanh_forward(const float* bottom, float* top, int num_images, int num_channels,
                      int height, int width, mnv_stream_t stream);
+/* Exact mode: sigmoid as (float)(1.0 / (1.0 + (double)expf(-x))) with glibc's expf (basic.cpp:416), tanh as glibc's tanhf
+ * (fdlibm over expm1f, basic.cpp:444) -- bit-identical to the reference's CPU ops; relu is exact in the default entry. */
+int mnv_sigmoid_forward_exact(const float* bottom, float* top, int num_images, int num_channels,
+                              int height, int width, mnv_stream_t stream);
+int mnv_tanh_forward_exact(const float* bottom, float* top, int num_images, int num_channels,
+                           int height, int width, mnv_stream_t stream);
 /* sigmoid: dx = dy*y*(1-y); relu: dx = x>0 ? dy : 0; tanh: dx = dy*(1-y*y) */
 int mnv_sigmoid_backward(const float* bottom, const float* top, const float* top_diff,
                          float* bottom_diff, int num_images, int num_channels, int height,
@@ -358,6 +370,18 @@ int mnv_relu_mask_inplace(float* dx, const float* x, size_t n, mnv_stream_t stre
  * reference's ten-op chain).  In place on w and delta. */
 int mnv_sgd_momentum_update(float* w, float* delta, const float* grad, size_t n, float momentum,
                             float lr_over_batch, float lr_times_wd, mnv_stream_t stream);
+
+/* The same update for `count` tensors in one launch (host array of descriptors, copied into the kernel's parameters):
+ * a net's many small parameter tensors make one launch per tensor launch-bound.  Bit-identical to `count` single calls. */
+typedef struct {
+  float* w;
+  float* delta;
+  const float* grad;
+  size_t n;
+  float lr_over_batch;
+  float lr_times_wd;
+} mnv_sgd_tensor_t;
+int mnv_sgd_momentum_update_multi(const mnv_sgd_tensor_t* tensors, int count, float momentum, mnv_stream_t stream);
 
 #ifdef __cplusplus
 }

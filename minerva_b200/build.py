@@ -40,7 +40,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]   # incl. glibc_math.h
     headers.append(os.path.join(ROOT, "include", "mnv.h"))
     objs = []
     for src, extra in SOURCES.items():
@@ -68,14 +68,17 @@ def build(force=False, verbose=False):
 
 
 HOST = os.path.join(CSRC, "host", "minerva")
-HOST_SRCS = [os.path.join(HOST, "op", "impl", "cuda.cpp"), os.path.join(HOST, "device", "gpu_device.cpp")]
+HOST_SRCS = [os.path.join(HOST, "op", "impl", "cuda.cpp"), os.path.join(HOST, "device", "gpu_device.cpp"),
+             os.path.join(HOST, "device", "stream_device.cpp")]
 HOST_TEST = os.path.join(OUT_DIR, "test_host_plugin")
+MNIST_APPS = os.path.join(OUT_DIR, "mnist_apps")      # apps/mnist_mlp + apps/mnist_cnn over ComputeFn::Execute on the StreamDevice
 
 
 def build_host(force=False):
     """The C++ host side above the C ABI (minerva/op plug-in surface + GpuDevice) -> libminerva_b200_host.so,
     and the C++ plug-in test binary (links the CPU oracle as its checker)."""
-    deps = HOST_SRCS + [os.path.join(HOST, "op", "hotpath.h"), os.path.join(HOST, "device", "gpu_device.h"), LIB]
+    deps = HOST_SRCS + [os.path.join(HOST, "op", "hotpath.h"), os.path.join(HOST, "device", "gpu_device.h"),
+                        os.path.join(HOST, "device", "stream_device.h"), os.path.join(HOST, "device", "task.h"), LIB]
     inc = ["-I" + HOST, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"]
     if force or _stale(HOST_LIB, deps):
         subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-o", HOST_LIB] + inc + HOST_SRCS +
@@ -89,6 +92,11 @@ def build_host(force=False):
         subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-o", HOST_TEST, test_src, oracle_o] + inc +
                               ["-L" + OUT_DIR, "-lminerva_b200_host", "-lmnv_b200", "-L/usr/local/cuda/lib64", "-lcudart",
                                "-fopenmp", "-lm", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    app_src = os.path.join(CSRC, "host", "apps", "mnist_apps.cpp")
+    if force or _stale(MNIST_APPS, [app_src, HOST_LIB]):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-o", MNIST_APPS, app_src] + inc +
+                              ["-L" + OUT_DIR, "-lminerva_b200_host", "-lmnv_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lpthread",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"])
     return HOST_LIB
 
 

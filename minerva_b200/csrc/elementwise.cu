@@ -10,6 +10,25 @@
 // glibc; the reference's own tests allow 4 ulp, tests/unittest_elewise.cpp:17).
 #include "common.cuh"
 
+// ---- exact mode: glibc's expf / logf / tanhf and the reference's sigmoid, bit for bit -------------------------
+// glibc_math.h is one text for host and device; here its arithmetic macros are the IEEE round-to-nearest intrinsics, which
+// nvcc neither contracts nor reassociates.  The host build of the same text is compared with libm on all 2^32 inputs by
+// tests/cpp/check_glibc_math.c (0 mismatches), so these kernels return what minerva/op/impl/basic.cpp:134,139,416,444 return.
+#define MNV_GM_FN __device__ __forceinline__
+#define MNV_GM_CONST __device__ const
+#define MNV_INFF __int_as_float(0x7f800000)
+#define MNV_NANF __int_as_float(0x7fffffff)
+#define MNV_MUL(a, b) __dmul_rn((a), (b))
+#define MNV_ADD(a, b) __dadd_rn((a), (b))
+#define MNV_SUB(a, b) __dsub_rn((a), (b))
+#define MNV_DIV(a, b) __ddiv_rn((a), (b))
+#define MNV_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define MNV_FMULF(a, b) __fmul_rn((a), (b))
+#define MNV_FADDF(a, b) __fadd_rn((a), (b))
+#define MNV_FSUBF(a, b) __fsub_rn((a), (b))
+#define MNV_FDIVF(a, b) __fdiv_rn((a), (b))
+#include "glibc_math.h"
+
 namespace mnv {
 
 std::atomic<uint64_t> g_launches{0};
@@ -109,6 +128,10 @@ struct SigmoidOp {
     return static_cast<float>(1.0 / (1.0 + static_cast<double>(expf(-x))));
   }
 };
+struct ExpExactOp { __device__ float operator()(float x, float, float) const { return mnv_glibc_expf(x); } };
+struct LnExactOp { __device__ float operator()(float x, float, float) const { return mnv_glibc_logf(x); } };
+struct TanhExactOp { __device__ float operator()(float x, float, float) const { return mnv_glibc_tanhf(x); } };
+struct SigmoidExactOp { __device__ float operator()(float x, float, float) const { return mnv_ref_sigmoidf(x); } };
 struct ReluOp { __device__ float operator()(float x, float, float) const { return x > 0.f ? x : 0.f; } };  // basic.cpp:430
 struct TanhOp { __device__ float operator()(float x, float, float) const { return tanhf(x); } };
 // backward functors take (dy, y, x)
@@ -301,6 +324,58 @@ __global__ void __launch_bounds__(kBlock) sgd_kernel(float* __restrict__ w, floa
   }
 }
 
+// The same update for up to kSgdMaxTensors tensors in ONE launch: a step's 16 (AlexNet) / 128 (GoogLeNet) parameter
+// tensors are mostly small (biases, 1x1 filters), so one launch per tensor is launch-bound (16 launches: 0.29 ms for
+// 1.25 GB = 65 % of the HBM peak; one launch streams at the rate of the large tensors).  Work is cut into chunks of
+// kSgdChunk elements; a CTA walks chunks grid-stride and finds each chunk's tensor in the (<= 64 entry) prefix table.
+constexpr int kSgdMaxTensors = 64;
+constexpr int kSgdChunk = 4096;
+struct SgdTable {
+  float* w[kSgdMaxTensors];
+  float* delta[kSgdMaxTensors];
+  const float* grad[kSgdMaxTensors];
+  unsigned long long n[kSgdMaxTensors];
+  unsigned int first_chunk[kSgdMaxTensors + 1];
+  float lrb[kSgdMaxTensors], lrwd[kSgdMaxTensors];
+  int count;
+};
+__global__ void __launch_bounds__(kBlock) sgd_multi_kernel(const __grid_constant__ SgdTable t, float mom) {
+  const unsigned total = t.first_chunk[t.count];
+  for (unsigned c = blockIdx.x; c < total; c += gridDim.x) {
+    int lo = 0, hi = t.count - 1;
+    while (lo < hi) {                       // last tensor whose first chunk is <= c
+      const int mid = (lo + hi + 1) >> 1;
+      if (t.first_chunk[mid] <= c) lo = mid; else hi = mid - 1;
+    }
+    float* w = t.w[lo];
+    float* d = t.delta[lo];
+    const float* g = t.grad[lo];
+    const float lrb = t.lrb[lo], lrwd = t.lrwd[lo];
+    const size_t begin = static_cast<size_t>(c - t.first_chunk[lo]) * kSgdChunk;
+    const size_t end = min(begin + static_cast<size_t>(kSgdChunk), static_cast<size_t>(t.n[lo]));
+    auto upd = [&](float& wv, float& dv, float gv) {
+      const float nd = __fsub_rn(__fsub_rn(__fmul_rn(mom, dv), __fmul_rn(lrb, gv)), __fmul_rn(lrwd, wv));
+      dv = nd;
+      wv = __fadd_rn(wv, nd);
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0;
+    if (vec) {                              // chunk starts are multiples of 4 elements
+      const size_t b4 = begin / 4, e4 = end / 4;
+      float4* w4 = reinterpret_cast<float4*>(w);
+      float4* d4 = reinterpret_cast<float4*>(d);
+      const float4* g4 = reinterpret_cast<const float4*>(g);
+      for (size_t i = b4 + threadIdx.x; i < e4; i += kBlock) {
+        float4 wv = w4[i], dv = d4[i], gv = __ldg(g4 + i);
+        upd(wv.x, dv.x, gv.x); upd(wv.y, dv.y, gv.y); upd(wv.z, dv.z, gv.z); upd(wv.w, dv.w, gv.w);
+        w4[i] = wv; d4[i] = dv;
+      }
+      for (size_t i = e4 * 4 + threadIdx.x; i < end; i += kBlock) { float wv = w[i], dv = d[i]; upd(wv, dv, g[i]); w[i] = wv; d[i] = dv; }
+    } else {
+      for (size_t i = begin + threadIdx.x; i < end; i += kBlock) { float wv = w[i], dv = d[i]; upd(wv, dv, g[i]); w[i] = wv; d[i] = dv; }
+    }
+  }
+}
+
 }  // namespace mnv
 
 using namespace mnv;
@@ -340,6 +415,12 @@ int mnv_elewise_exp(const float* in, float* out, size_t n, mnv_stream_t s) {
 int mnv_elewise_ln(const float* in, float* out, size_t n, mnv_stream_t s) {
   return launch_ew<1>(in, nullptr, nullptr, out, n, LnOp{}, as_stream(s));
 }
+int mnv_elewise_exp_exact(const float* in, float* out, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, ExpExactOp{}, as_stream(s));
+}
+int mnv_elewise_ln_exact(const float* in, float* out, size_t n, mnv_stream_t s) {
+  return launch_ew<1>(in, nullptr, nullptr, out, n, LnExactOp{}, as_stream(s));
+}
 int mnv_elewise_negative(const float* in, float* out, size_t n, mnv_stream_t s) {
   return launch_ew<1>(in, nullptr, nullptr, out, n, NegOp{}, as_stream(s));
 }
@@ -367,6 +448,14 @@ int mnv_relu_forward(const float* x, float* y, int N, int C, int H, int W, mnv_s
 int mnv_tanh_forward(const float* x, float* y, int N, int C, int H, int W, mnv_stream_t s) {
   if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
   return launch_ew<1>(x, nullptr, nullptr, y, prod4(N, C, H, W), TanhOp{}, as_stream(s));
+}
+int mnv_sigmoid_forward_exact(const float* x, float* y, int N, int C, int H, int W, mnv_stream_t s) {
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<1>(x, nullptr, nullptr, y, prod4(N, C, H, W), SigmoidExactOp{}, as_stream(s));
+}
+int mnv_tanh_forward_exact(const float* x, float* y, int N, int C, int H, int W, mnv_stream_t s) {
+  if (!MNV_DIMS_OK(N, C, H, W)) return MNV_EINVAL;
+  return launch_ew<1>(x, nullptr, nullptr, y, prod4(N, C, H, W), TanhExactOp{}, as_stream(s));
 }
 // Only the operands the formula needs are read (12 B/elem): sigmoid/tanh use (dy, y), relu (dy, x).
 int mnv_sigmoid_backward(const float* x, const float* y, const float* dy, float* dx, int N, int C, int H,
@@ -416,6 +505,31 @@ int mnv_sgd_momentum_update(float* w, float* delta, const float* grad, size_t n,
   return finish_launch();
 }
 
+int mnv_sgd_momentum_update_multi(const mnv_sgd_tensor_t* tensors, int count, float momentum, mnv_stream_t s) {
+  if (count < 0 || (count > 0 && !tensors)) return MNV_EINVAL;
+  for (int i = 0; i < count;) {
+    SgdTable t;
+    t.count = 0;
+    unsigned chunks = 0;
+    for (; i < count && t.count < kSgdMaxTensors; ++i) {
+      const mnv_sgd_tensor_t& e = tensors[i];
+      if (e.n == 0) continue;
+      if (!e.w || !e.delta || !e.grad) return MNV_EINVAL;
+      const size_t nch = (e.n + kSgdChunk - 1) / kSgdChunk;
+      if (nch > 0x7fffffffu - chunks) return MNV_EUNSUPPORTED;
+      const int k = t.count++;
+      t.w[k] = e.w; t.delta[k] = e.delta; t.grad[k] = e.grad; t.n[k] = e.n; t.lrb[k] = e.lr_over_batch; t.lrwd[k] = e.lr_times_wd;
+      t.first_chunk[k] = chunks;
+      chunks += static_cast<unsigned>(nch);
+    }
+    if (t.count == 0) continue;
+    t.first_chunk[t.count] = chunks;
+    sgd_multi_kernel<<<stream_grid(static_cast<size_t>(chunks) * kBlock), kBlock, 0, as_stream(s)>>>(t, momentum);
+    int rc = finish_launch();
+    if (rc) return rc;
+  }
+  return MNV_OK;
+}
 int mnv_accumulate(float* acc, const float* x, size_t n, mnv_stream_t s) {
   return launch_inplace(acc, x, n, AddOp{}, as_stream(s));
 }

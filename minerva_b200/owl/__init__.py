@@ -65,3 +65,9 @@ def set_seed(seed):
 def set_rank_salt(rank):
     """Mix the data-parallel rank into the dropout (randb) seeds; weights (randn) stay identical across ranks."""
     _rt.set_rank_salt(rank)
+
+
+def set_exact_math(flag):
+    """True: exp / ln / sigmoid / tanh use the exact-mode kernels (mnv_*_exact), bit-identical to the reference's CPU ops
+    (glibc's expf / logf / tanhf restated in the kernel); False (default): CUDA's fast functions, <= 4 ulp away."""
+    NArray.exact_math = bool(flag)

@@ -80,6 +80,7 @@ class NArray:
     # reuses it, backward-filter fills top_diff's and backward-data reuses it.  Arrays are immutable once produced (the only
     # in-place op, sgd_update, touches parameters), so a filled twin stays current for the array's lifetime.
     __slots__ = ("_buf", "_shape", "_dev", "_lazy_src", "_views", "_twin", "__weakref__")
+    exact_math = False   # owl.set_exact_math(True): exp / ln / sigmoid / tanh return the CPU reference's (glibc's) bits
     use_twins = True     # Net.fuse_conv_twins: False = every convolution call makes its own workspace copy (the plain entries)
     _twin_wanted = {}    # geometry -> mnv_conv_twin_wanted bitmask
 
@@ -167,10 +168,10 @@ class NArray:
         return self._t.to(dev.device, non_blocking=True)
 
     @staticmethod
-    def _call(name, dev, *args):
+    def _call(name, dev, *args, prof_args=None):
         prof = _rt.profiler
         if prof is not None:          # per-op device timing (the reference's ExecutionProfiler role)
-            tok = prof.begin(name, args, dev)
+            tok = prof.begin(name, prof_args if prof_args is not None else args, dev)
         rc = getattr(_lib.load(), name)(*args, dev.stream_ptr)
         if rc:
             _lib.check(rc, name)
@@ -194,6 +195,27 @@ class NArray:
         delta._flush_views()
         NArray._call("mnv_sgd_momentum_update", dev, w._t.data_ptr(), delta._t.data_ptr(), grad._on(dev).data_ptr(),
                      w.size, float(momentum), float(lr_over_batch), float(lr_times_wd))
+
+    class _SgdTensor(ctypes.Structure):      # mnv_sgd_tensor_t (include/mnv.h)
+        _fields_ = [("w", ctypes.c_void_p), ("delta", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("n", ctypes.c_size_t),
+                    ("lr_over_batch", ctypes.c_float), ("lr_times_wd", ctypes.c_float)]
+
+    @staticmethod
+    def sgd_update_multi(entries, momentum):
+        """entries: [(w, delta, grad, lr_over_batch, lr_times_wd)] -- every parameter tensor of a net updated by ONE launch
+        (mnv_sgd_momentum_update_multi); bit-identical to one sgd_update per tensor."""
+        dev = _rt.current_device()
+        arr = (NArray._SgdTensor * len(entries))()
+        keep = []
+        for i, (w, delta, grad, lrb, lrwd) in enumerate(entries):
+            _check(w._dev is dev and delta._dev is dev, "sgd_update is in place: w and delta must live on this device")
+            w._flush_views()
+            delta._flush_views()
+            g = grad._on(dev)
+            keep.append(g)
+            arr[i] = NArray._SgdTensor(w._t.data_ptr(), delta._t.data_ptr(), g.data_ptr(), w.size, float(lrb), float(lrwd))
+        NArray._call("mnv_sgd_momentum_update_multi", dev, ctypes.cast(arr, ctypes.c_void_p), len(entries), float(momentum),
+                     prof_args=(0, len(entries), float(momentum), sum(e[0].size for e in entries)))
 
     def start_eval(self):
         pass
@@ -270,11 +292,11 @@ class NArray:
 
     @staticmethod
     def exp(x):
-        return x._unary("mnv_elewise_exp")
+        return x._unary("mnv_elewise_exp_exact" if NArray.exact_math else "mnv_elewise_exp")
 
     @staticmethod
     def ln(x):
-        return x._unary("mnv_elewise_ln")
+        return x._unary("mnv_elewise_ln_exact" if NArray.exact_math else "mnv_elewise_ln")
 
     # ---- activations (narray_elewise.cpp:51-82; argument order (diff, top, bottom)) --------------
     def _act(self, fn):
@@ -294,7 +316,7 @@ class NArray:
 
     @staticmethod
     def sigm(x):
-        return x._act("mnv_sigmoid_forward")
+        return x._act("mnv_sigmoid_forward_exact" if NArray.exact_math else "mnv_sigmoid_forward")
 
     @staticmethod
     def relu(x):
@@ -302,7 +324,7 @@ class NArray:
 
     @staticmethod
     def tanh(x):
-        return x._act("mnv_tanh_forward")
+        return x._act("mnv_tanh_forward_exact" if NArray.exact_math else "mnv_tanh_forward")
 
     @staticmethod
     def sigm_back(diff, top, bottom):
@@ -318,7 +340,8 @@ class NArray:
 
     @staticmethod
     def activation_forward(src, algo):
-        return src._act("mnv_%s_forward" % algo.name)
+        exact = NArray.exact_math and algo.name in ("sigmoid", "tanh")
+        return src._act("mnv_%s_forward%s" % (algo.name, "_exact" if exact else ""))
 
     @staticmethod
     def activation_backward(diff, top, bottom, algo):

@@ -91,13 +91,18 @@ class NetTrainer(object):
             return
         NArray = net.B.owl.NArray
         lr, wd, mom, bs = net.current_lr, net.base_weight_decay, net.momentum, net.batch_size
+        entries = []
         for uid in net.get_weighted_unit_ids():
             u = net.units[uid]
-            NArray.sgd_update(u.weight, u.weightdelta, u.weightgrad, mom, lr * u.lr_mult_w / bs,
-                              lr * u.lr_mult_w * wd * u.decay_mult_w)
-            NArray.sgd_update(u.bias, u.biasdelta, u.biasgrad, mom, lr * u.lr_mult_b / bs,
-                              lr * u.lr_mult_b * wd * u.decay_mult_b)
-            u.weightgrad = u.biasgrad = None
+            entries.append((u.weight, u.weightdelta, u.weightgrad, lr * u.lr_mult_w / bs, lr * u.lr_mult_w * wd * u.decay_mult_w))
+            entries.append((u.bias, u.biasdelta, u.biasgrad, lr * u.lr_mult_b / bs, lr * u.lr_mult_b * wd * u.decay_mult_b))
+        if hasattr(NArray, "sgd_update_multi"):          # one launch for every parameter tensor of the net
+            NArray.sgd_update_multi(entries, mom)
+        else:
+            for e in entries:
+                NArray.sgd_update(e[0], e[1], e[2], mom, e[3], e[4])
+        for uid in net.get_weighted_unit_ids():
+            net.units[uid].weightgrad = net.units[uid].biasgrad = None
 
     def run(self, iters, sync_freq=1, log=None):
         """trainer.py:101-148: img/s = batch_size * sync_freq / wall time between wait_for_all() calls."""

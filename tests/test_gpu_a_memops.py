@@ -96,6 +96,35 @@ def test_elewise(g):
     assert g.ulp_diff(g.host(dy), orc.elewise_ln(xl)).max() <= 4
 
 
+def test_exact_mode_transcendentals_bit_exact(g):
+    """mnv_*_exact (exp, ln, sigmoid, tanh) return the CPU reference's bits: compared with the reference's own basic::
+    functions (oracle/_ref, which call this box's libm) where built, and with the oracle restatement, on (a) every 1021st
+    of all 2^32 float bit patterns (4.2 M values: all exponents, subnormals, both signs, inf / nan), (b) the reference
+    tests' input ranges (unittest_elewise.cpp:13,43, unittest_activation.cpp:15,45), (c) the edge vector."""
+    sweep = np.arange(0, 1 << 32, 1021, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    x = np.concatenate([sweep, rng.normal(0, 1, 200003).astype(np.float32), rng.normal(500, 1, 100003).astype(np.float32),
+                        rng.normal(0, 5, 100003).astype(np.float32), rng.uniform(-104, 89, 200003).astype(np.float32), _edge()])
+    n = x.size
+    dx, dy = g.dev(x), g.empty(n)
+    cases = [("mnv_elewise_exp_exact", (n,), orc.elewise_exp, lambda v: orc.Ref.elewise("exp", v)),
+             ("mnv_elewise_ln_exact", (n,), orc.elewise_ln, lambda v: orc.Ref.elewise("ln", v)),
+             ("mnv_sigmoid_forward_exact", (1, 1, 1, n), orc.sigmoid_forward, lambda v: orc.Ref.activation("sigmoid", v)),
+             ("mnv_tanh_forward_exact", (1, 1, 1, n), orc.tanh_forward, lambda v: orc.Ref.activation("tanh", v))]
+    with np.errstate(all="ignore"):
+        for name, dims, oracle_fn, ref_fn in cases:
+            dy.fill_(float("nan"))
+            g.run(name, dx, dy, *dims)
+            got = g.host(dy)
+            g.assert_bits_equal(got, oracle_fn(x), name + " vs oracle")
+            if orc.have_ref():
+                g.assert_bits_equal(got, ref_fn(x), name + " vs the compiled reference")
+    # the default (fast) entries stay within the reference tests' 4 ulp on the reference tests' ranges
+    xs = rng.normal(0, 1, 100003).astype(np.float32)
+    d2 = g.empty(xs.size)
+    g.run("mnv_sigmoid_forward", g.dev(xs), d2, 1, 1, 1, xs.size)
+    assert g.ulp_diff(g.host(d2), orc.sigmoid_forward(xs)).max() <= 4
+
+
 def test_activation(g):
     n = 50001
     x = np.concatenate([rng.normal(0, 1, n).astype(np.float32), _edge()])
@@ -347,6 +376,33 @@ def test_sgd_update_bit_exact(g):
         w2, d2 = orc.sgd_momentum_update(w, d, gr, 0.9, 0.01 / 256, 0.01 * 5e-4)
         g.assert_bits_equal(g.host(dd), d2, "delta")
         g.assert_bits_equal(g.host(dw), w2, "w")
+
+
+def test_sgd_update_multi_equals_single_calls(g):
+    """mnv_sgd_momentum_update_multi: one launch over many tensors (sizes from 1 element to several chunks, one of them
+    misaligned, one empty) == one mnv_sgd_momentum_update per tensor, bit for bit."""
+    import ctypes
+    import torch
+    from minerva_b200 import _lib
+    from minerva_b200.owl.narray import NArray
+    sizes = [1, 96, 0, 4096, 4097, 1000, 37748736 // 64, 12289, 5] * 9          # 81 tensors: more than one 64-entry table
+    ws, ds, gs = [], [], []
+    arr = (NArray._SgdTensor * len(sizes))()
+    for i, n in enumerate(sizes):
+        off = 1 if i == 4 else 0
+        w, d, gr = (torch.randn(n + off, device="cuda")[off:] for _ in range(3))
+        ws.append(w); ds.append(d); gs.append(gr)
+        arr[i] = NArray._SgdTensor(w.data_ptr(), d.data_ptr(), gr.data_ptr(), n, 0.01 / 256 * (1 + i % 3), 5e-6 * (i % 2))
+    w1, d1 = [w.clone() for w in ws], [d.clone() for d in ds]
+    lib = _lib.load()
+    for i, n in enumerate(sizes):
+        if n:
+            _lib.check(lib.mnv_sgd_momentum_update(w1[i].data_ptr(), d1[i].data_ptr(), gs[i].data_ptr(), n, 0.9, 0.01 / 256 * (1 + i % 3),
+                                                   5e-6 * (i % 2), g.stream()), "single")
+    _lib.check(lib.mnv_sgd_momentum_update_multi(ctypes.cast(arr, ctypes.c_void_p), len(sizes), 0.9, g.stream()), "multi")
+    torch.cuda.synchronize()
+    for i in range(len(sizes)):
+        assert torch.equal(ws[i], w1[i]) and torch.equal(ds[i], d1[i]), i
 
 
 def test_bad_arguments_fail_loudly(g):
