@@ -1458,7 +1458,8 @@ MNV_OPT g_opt_force_tma_a{0}; // 1: take the all-TMA conv path whenever it appli
 MNV_OPT g_opt_no_klane{0};   // 1: strided convs keep the lanes-along-pixels gathers (debug / tuning)
 MNV_OPT g_opt_no_deep{0};    // 1: keep the 4 x 48 KB ring for bn <= 128 on the all-TMA path (tuning)
 MNV_OPT g_opt_no_tall{0};    // 1: never use the 256-row tile (tuning)
-MNV_OPT g_opt_tall_min_stages{64};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (tuning)
+MNV_OPT g_opt_tall_min_stages{32};  // shortest per-tile mainloop (k-stages) the 256-row tile is used for (measured on AlexNet conv3-5:
+                                    // 32 beats 64 by 3-7 % on forward / backward-data, 16 and 8 are no better; FC GEMMs do not care)
 MNV_OPT g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
 MNV_OPT g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
 MNV_OPT g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)

@@ -318,7 +318,7 @@ def test_matmult_operand_paths(g, m, n, k):
         finally:
             for key, v in defaults.items():
                 _set(key, v)
-            _set("tall_min_stages", 64)
+            _set("tall_min_stages", 32)
         assert g.norm_rel(got, want) < TOL, name
 
 
