@@ -93,3 +93,16 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(_lib.MnvError):
         _lib.load()
+
+
+def test_reference_side_binding_compiles_against_the_reference_headers():
+    """the replacement bodies of minerva/op/impl/cuda.cpp's shims compile against the REFERENCE'S
+    own headers (DataList, closures, Context, the declarations in op/impl/cuda.h) and call the C ABI of include/mnv.h."""
+    ref = "/root/reference/minerva"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference tree is not present on this box")
+    cmd = ["/usr/bin/g++", "-std=c++11", "-fsyntax-only", "-DHAS_CUDA", "-I" + ref, "-I" + os.path.join(ROOT, "oracle", "shim"),
+           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", "-I/usr/include/x86_64-linux-gnu",
+           os.path.join(ROOT, "tests", "cpp", "reference_binding_stub.cpp")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
