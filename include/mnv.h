@@ -295,7 +295,8 @@ int mnv_max_pooling_backward_relu(const float* bottom, const float* top, const f
                                   int stride_horizontal, int window_height, int window_width,
                                   int pad_height, int pad_width, mnv_stream_t stream);
 
-/* Extension (remember instead of recompute): 3x3 / stride 2 / pad 0 max pooling (AlexNet, GoogLeNet) whose
+/* Extension (remember instead of recompute): 3x3 / stride 2 / pad 0 max pooling (AlexNet, GoogLeNet) and
+ * 3x3 / stride 1 / pad 1 max pooling (GoogLeNet's inception pools; mnv_max_pooling_idx_supported says which) whose
  * forward pass also writes one byte per pooled element -- the window position kh*3+kw of the first maximum in scan
  * order, 255 for a window of NaNs -- so that the backward pass reads (top_diff, idx) = 5 B per pooled element instead of
  * re-reading the whole bottom (4 B per INPUT element) and recomputing the arg-max.  bottom_diff is bit-identical to

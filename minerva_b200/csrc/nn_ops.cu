@@ -4,6 +4,7 @@
 // the stream per call (minerva/op/impl/cuda/cuda_perform.cu:339-615); here each op is one
 // enqueue-only launch (two for bias-grad with a workspace).
 #include <math_constants.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mnv {
@@ -535,7 +536,11 @@ __global__ void __launch_bounds__(kBlock) maxpool332_bwd_kernel(const float* __r
 // four outputs.  Traffic: 5 B per pooled element + 4 B per input element, against 4 + 8 for the recomputing kernel.
 // Same (i-major, j-minor) accumulation order, so the result is bit-identical.  mask != null: ReLU backward folded in --
 // an element passes only if its window's maximum (= the element itself, being the arg-max) is > 0.
-// (Assembling the planes in shared memory for 16-byte stores was measured slower: 0.29 vs 0.27 ms per AlexNet step.)
+// (Assembling the planes in shared memory for 16-byte stores was measured slower: 0.29 vs 0.27 ms per AlexNet step.  Round 2
+// tried two more organisations on the 55 -> 27 planes, 0.176 ms here: column strips that walk down the 2-row blocks with
+// the window row above kept in registers -- 0.191 ms, the stride-2 stores are the limit, not the index arithmetic -- and a
+// warp per plane with a thread per input element, whose stores are consecutive floats -- 0.371 ms, the 1-4 dependent
+// byte -> float loads per element serialise.)
 __global__ void __launch_bounds__(kBlock) maxpool332_bwd_idx_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx,
                                                                      const float* __restrict__ mask, float* __restrict__ dx, size_t planes,
                                                                      int G, PoolGeom g, FastDiv d_blk, FastDiv d_bw) {
@@ -586,6 +591,138 @@ __global__ void __launch_bounds__(kBlock) maxpool332_bwd_idx_kernel(const float*
         if (w + 1 < W) out[W + 1] = o11;
       }
     }
+  }
+}
+
+// ---- 3x3 / stride 1 / pad 1 max pooling (GoogLeNet's nine inception pools): column strips ---------------------------
+// The generic staged kernels spend ~80 instructions per output on index arithmetic and bounds tests (15 % of the HBM peak on
+// 28 x 28 planes).  Here a thread owns one COLUMN of one staged plane and walks down its rows: the column's two edge tests
+// are loop invariants, a row costs three shared-memory loads, and the (value, position) of the horizontal first-maximum of
+// the last three rows slides through registers.  Scan order is the oracle's (kh-major, kw-minor, strict >), so outputs and
+// arg-max bytes are bit-identical to the generic kernels.  idx == null: plain forward.
+__global__ void __launch_bounds__(kBlock) maxpool331_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W,
+                                                                 int G, FastDiv d_w, unsigned char* __restrict__ idx) {
+  extern __shared__ float sm[];
+  const int HW = H * W;
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    const float* xsrc = x + static_cast<size_t>(p0) * HW;
+    float* sx = sm + misalign4(xsrc);
+    stage_in(sx, xsrc, cnt * HW);
+    __syncthreads();
+    for (int c = threadIdx.x; c < cnt * W; c += blockDim.x) {
+      const int gq = fdiv(c, d_w), w = c - gq * W;
+      const bool hl = w > 0, hr = w + 1 < W;
+      const float* col = sx + gq * HW + w;
+      float* yp = y + (static_cast<size_t>(p0) + gq) * HW + w;
+      unsigned char* ip = idx ? idx + (static_cast<size_t>(p0) + gq) * HW + w : nullptr;
+      // (rv, ra): first maximum of input row r over kw = 0..2, ra = kw or 255 when nothing beat -inf
+      float v0 = -CUDART_INF_F, v1 = -CUDART_INF_F, v2;
+      int a0 = 255, a1 = 255, a2;
+      auto row_max = [&](int r, float& rv, int& ra) {
+        rv = -CUDART_INF_F; ra = 255;
+        if (r < H) {
+          const float* q = col + r * W;
+          if (hl) { const float t = q[-1]; if (t > rv) { rv = t; ra = 0; } }
+          { const float t = q[0]; if (t > rv) { rv = t; ra = 1; } }
+          if (hr) { const float t = q[1]; if (t > rv) { rv = t; ra = 2; } }
+        }
+      };
+      row_max(0, v1, a1);                       // window row kh = 1 of output row 0 (kh = 0 is padding)
+      for (int h = 0; h < H; ++h) {
+        row_max(h + 1, v2, a2);
+        float best = -CUDART_INF_F;
+        int arg = 255;
+        if (v0 > best) { best = v0; arg = a0; }
+        if (v1 > best) { best = v1; arg = 3 + a1; }
+        if (v2 > best) { best = v2; arg = 6 + a2; }
+        yp[h * W] = best;
+        if (ip) ip[h * W] = static_cast<unsigned char>(arg);
+        v0 = v1; a0 = a1; v1 = v2; a1 = a2;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Backward from the arg-max bytes: dx[h][w] = sum over the (up to nine) windows (i, j), i = h-1..h+1, j = w-1..w+1, in
+// (i-major, j-minor) order, of dy[i][j] where idx[i][j] names (h, w) -- position (h-i+1)*3 + (w-j+1).  Same column-strip walk:
+// three (dy, idx) pairs enter per row, the 3 x 3 neighbourhood slides through registers.  dy and idx are staged (idx as
+// bytes behind the floats).  Bit-identical to the generic backward kernel (same accumulation order, no float compares).
+__global__ void __launch_bounds__(kBlock) maxpool331_bwd_idx_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx,
+                                                                     const float* __restrict__ mask, float* __restrict__ dx, int planes, int H,
+                                                                     int W, int G, FastDiv d_w) {
+  extern __shared__ float sm[];
+  const int HW = H * W;
+  unsigned char* sidx_base = reinterpret_cast<unsigned char*>(sm + ((G * HW + 4 + 3) & ~3));
+  for (int p0 = blockIdx.x * G; p0 < planes; p0 += gridDim.x * G) {
+    const int cnt = min(G, planes - p0);
+    const float* dsrc = dy + static_cast<size_t>(p0) * HW;
+    const unsigned char* isrc = idx + static_cast<size_t>(p0) * HW;
+    float* sdy = sm + misalign4(dsrc);
+    stage_in(sdy, dsrc, cnt * HW);
+    {  // the byte plane: 16-byte vectors where source and destination agree mod 16, bytes at the ends
+      const int n = cnt * HW, mis = static_cast<int>(reinterpret_cast<uintptr_t>(isrc) & 15u);
+      unsigned char* sidx = sidx_base + mis;
+      int head = (16 - mis) & 15;
+      if (head > n) head = n;
+      if (static_cast<int>(threadIdx.x) < head) sidx[threadIdx.x] = __ldg(isrc + threadIdx.x);
+      const int n16 = (n - head) >> 4;
+      const uint4* s16 = reinterpret_cast<const uint4*>(isrc + head);
+      uint4* d16 = reinterpret_cast<uint4*>(sidx + head);
+      for (int i = threadIdx.x; i < n16; i += blockDim.x) d16[i] = __ldg(s16 + i);
+      const int done = head + (n16 << 4);
+      if (static_cast<int>(threadIdx.x) < n - done) sidx[done + threadIdx.x] = __ldg(isrc + done + threadIdx.x);
+    }
+    __syncthreads();
+    const unsigned char* sidx = sidx_base + static_cast<int>(reinterpret_cast<uintptr_t>(isrc) & 15u);
+    for (int c = threadIdx.x; c < cnt * W; c += blockDim.x) {
+      const int gq = fdiv(c, d_w), w = c - gq * W;
+      const bool hl = w > 0, hr = w + 1 < W;
+      const float* dcol = sdy + gq * HW + w;
+      const unsigned char* icol = sidx + gq * HW + w;
+      float* out = dx + (static_cast<size_t>(p0) + gq) * HW + w;
+      // mask != null (the pooled tensor is a ReLU output): window (i, j) passes only if its maximum top[i][j] is > 0
+      const float* mcol = mask ? mask + (static_cast<size_t>(p0) + gq) * HW + w : nullptr;
+      // window row i holds (d[j], a[j]) for j = w-1, w, w+1; arg 255 / out-of-range matches nothing
+      float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f}, d2[3];
+      int a0[3] = {255, 255, 255}, a1[3] = {255, 255, 255}, a2[3];
+      auto load_row = [&](int i, float (&d)[3], int (&a)[3]) {
+        d[0] = d[1] = d[2] = 0.f; a[0] = a[1] = a[2] = 255;
+        if (i < H) {
+          const float* q = dcol + i * W;
+          const unsigned char* b = icol + i * W;
+          if (hl) { d[0] = q[-1]; a[0] = b[-1]; }
+          d[1] = q[0]; a[1] = b[0];
+          if (hr) { d[2] = q[1]; a[2] = b[1]; }
+          if (mcol) {
+            const float* m = mcol + i * W;
+            if (hl && !(__ldg(m - 1) > 0.f)) a[0] = 255;
+            if (!(__ldg(m) > 0.f)) a[1] = 255;
+            if (hr && !(__ldg(m + 1) > 0.f)) a[2] = 255;
+          }
+        }
+      };
+      load_row(0, d1, a1);
+      for (int h = 0; h < H; ++h) {
+        load_row(h + 1, d2, a2);
+        // window (i, j) sees (h, w) at kh = h - i + 1, kw = w - j + 1: i = h-1 -> kh 2, j = w-1 -> kw 2
+        float acc = 0.f;
+        if (a0[0] == 8) acc = __fadd_rn(acc, d0[0]);
+        if (a0[1] == 7) acc = __fadd_rn(acc, d0[1]);
+        if (a0[2] == 6) acc = __fadd_rn(acc, d0[2]);
+        if (a1[0] == 5) acc = __fadd_rn(acc, d1[0]);
+        if (a1[1] == 4) acc = __fadd_rn(acc, d1[1]);
+        if (a1[2] == 3) acc = __fadd_rn(acc, d1[2]);
+        if (a2[0] == 2) acc = __fadd_rn(acc, d2[0]);
+        if (a2[1] == 1) acc = __fadd_rn(acc, d2[1]);
+        if (a2[2] == 0) acc = __fadd_rn(acc, d2[2]);
+        out[h * W] = acc;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { d0[j] = d1[j]; a0[j] = a1[j]; d1[j] = d2[j]; a1[j] = a2[j]; }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1133,6 +1270,11 @@ static int launch_pool_fwd(const float* x, float* y, size_t planes, const PoolGe
       }
       return finish_launch();
     }
+    if (IS_MAX && g.wh == 3 && g.ww == 3 && g.sv == 1 && g.sh == 1 && g.ph == 1 && g.pw == 1 && g.Ho == g.H && g.Wo == g.W &&
+        static_cast<size_t>(G) * g.W < (1u << 16)) {
+      maxpool331_fwd_kernel<<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g.H, g.W, G, make_fastdiv(g.W), idx);
+      return finish_launch();
+    }
     if (idx) return MNV_EUNSUPPORTED;
     pool_fwd_smem_kernel<IS_MAX><<<pool_grid(planes, G), kBlock, bytes, s>>>(x, y, static_cast<int>(planes), g, G,
                                                                             make_fastdiv(g.Ho * g.Wo), make_fastdiv(g.Wo));
@@ -1276,9 +1418,13 @@ int mnv_max_pooling_backward_relu(const float* x, const float* y, const float* d
 int mnv_max_pooling_idx_supported(int N, int C, int H, int W, int sv, int sh, int wh, int ww, int ph, int pw) {
   PoolGeom g;
   if (make_geom(&g, N, C, H, W, sv, sh, wh, ww, ph, pw)) return 0;
-  if (!(wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0)) return 0;
   const size_t planes = static_cast<size_t>(N) * C, per = static_cast<size_t>(H) * W;
   if (planes == 0 || planes >= 0x7fffffff) return 0;
+  if (wh == 3 && ww == 3 && sv == 1 && sh == 1 && ph == 1 && pw == 1) {   // inception pools: the column-strip pair
+    const int G1 = pool_group(per, planes, per);
+    return G1 > 0 && static_cast<size_t>(G1) * W < (1u << 16) ? 1 : 0;
+  }
+  if (!(wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0)) return 0;
   const int G = pool_group(per, planes, per);
   if (G <= 0 || 2 * ((per * G + 4 + 3) & ~static_cast<size_t>(3)) * sizeof(float) > static_cast<size_t>(kPoolSmemBig)) return 0;   // forward staging
   const size_t blk = static_cast<size_t>((H + 1) / 2) * ((W + 1) / 2);
@@ -1303,6 +1449,17 @@ int mnv_max_pooling_backward_idx(const float* dy, const unsigned char* idx, cons
   size_t planes = static_cast<size_t>(N) * C;
   if (planes == 0) return MNV_OK;
   if (!dy || !idx || !dx) return MNV_EINVAL;
+  if (wh == 3 && ww == 3 && sv == 1 && sh == 1 && ph == 1 && pw == 1) {
+    if (!mnv_max_pooling_idx_supported(N, C, H, W, sv, sh, wh, ww, ph, pw)) return MNV_EUNSUPPORTED;
+    const size_t per = static_cast<size_t>(H) * W;
+    const int G1 = pool_group(per, planes, per);
+    const size_t bytes = ((per * G1 + 4 + 3) & ~static_cast<size_t>(3)) * sizeof(float) + per * G1 + 32;
+    rc = pool_smem_attr(maxpool331_bwd_idx_kernel, bytes);
+    if (rc) return rc;
+    maxpool331_bwd_idx_kernel<<<pool_grid(planes, G1), kBlock, bytes, as_stream(s)>>>(dy, idx, relu_top, dx, static_cast<int>(planes), H, W,
+                                                                                       G1, make_fastdiv(W));
+    return finish_launch();
+  }
   if (!(wh == 3 && ww == 3 && sv == 2 && sh == 2 && ph == 0 && pw == 0)) return MNV_EUNSUPPORTED;
   const size_t blk = static_cast<size_t>((H + 1) / 2) * ((W + 1) / 2);
   size_t G = 2048 / blk;                  // ~2K input blocks (8 per thread) per CTA pass

@@ -241,6 +241,7 @@ POOL_CASES = [
     (4, 8, 55, 55, 2, 2, 3, 3, 0, 0), (4, 8, 27, 27, 2, 2, 3, 3, 0, 0), (4, 8, 13, 13, 2, 2, 3, 3, 0, 0),
     (4, 16, 24, 24, 2, 2, 2, 2, 0, 0), (4, 32, 12, 12, 3, 3, 3, 3, 0, 0), (2, 3, 14, 14, 2, 2, 3, 3, 0, 0),
     (2, 3, 7, 9, 1, 1, 3, 3, 1, 1), (2, 4, 14, 14, 3, 3, 5, 5, 0, 0), (2, 4, 7, 7, 1, 1, 7, 7, 0, 0),
+    (5, 37, 28, 28, 1, 1, 3, 3, 1, 1), (3, 11, 14, 14, 1, 1, 3, 3, 1, 1), (2, 300, 7, 7, 1, 1, 3, 3, 1, 1), (2, 2, 1, 5, 1, 1, 3, 3, 1, 1),   # inception pools (column-strip kernels)
     (3, 5, 8, 11, 2, 2, 3, 3, 0, 0), (2, 3, 3, 3, 2, 2, 3, 3, 0, 0), (300, 7, 6, 6, 2, 2, 3, 3, 0, 0),   # 3x3/2: overhanging windows, one window, many planes
     (1, 2, 70, 131, 2, 2, 3, 3, 0, 0), (2, 3, 9, 64, 2, 2, 3, 3, 0, 0), (2, 2, 5, 4, 2, 2, 3, 3, 0, 0),    # wider than 64 columns (thread-per-block kernel), exactly 64, tiny
 ]
@@ -278,7 +279,7 @@ def test_pooling_bit_exact(g, case, relu_input):
             dfus = g.empty(x.size)
             g.run("mnv_max_pooling_backward_relu", dx, g.dev(want), dyd, dfus, N, C, H, W, sv, sh, wh, ww, ph, pw)
             g.assert_bits_equal(g.host(dfus), np.where(x > 0, wb, np.float32(0)).astype(np.float32), "max bwd + relu bwd")
-        if kind == "max" and (sv, sh, wh, ww, ph, pw) == (2, 2, 3, 3, 0, 0):
+        if kind == "max" and (sv, sh, wh, ww, ph, pw) in ((2, 2, 3, 3, 0, 0), (1, 1, 3, 3, 1, 1)):
             # arg-max remembering pair: same top, same bottom_diff, with and without the folded ReLU mask
             import torch
             out2 = g.empty(N * C * Ho * Wo)
