@@ -92,9 +92,12 @@ struct GemmParams {
   int relu;             // 1: epilogue applies max(x, 0) after the bias (conv + ReLU units fused by owl.net)
   int b_mn;             // 1: B arrives as an MN-major tile (bn/32 boxes of 32 n x 32 k; MatMult with B^T), all-TMA path only
   int cpt;              // 32-channel chunks per filter tap (TMA_A_IM2COL_K: k-stage = tap * cpt + chunk)
-  int out_mode;         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
+  int out_mode;         // 3: transposed convolution output: m = co, n = flat (image, pixel); bias is per m
+                        // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
                         // 2: the same over a space-to-depth view (below): virtual (tap, channel) -> real filter element
   int r_ci, r_fh, r_fw, r_sv, r_sh;   // out_mode 2: the real convolution's channels, filter and strides
+  int b_im2col;         // 1 (all-TMA path): B is the im2col operand -- bn output pixels x 32 channels of one tap per k-stage -- and A the
+                        // packed filter (TMA_A_TILED_K): the TRANSPOSED orientation D[co][pixel] for narrow outputs (out_mode 3)
   int b_flip;           // B_FILTER_T: 1 = taps rotated by 180 degrees (stride-1 backward-data run as a forward convolution)
 };
 
@@ -309,7 +312,7 @@ __device__ __forceinline__ bool out_row_ok(const GemmParams& p, int m) {
     const int a = tap / p.fw, b = tap - a * p.fw, r = ch / p.r_sh;   // r = c * sv + dy
     return ch < p.Ci && a * p.r_sv + r % p.r_sv < p.r_fh && b * p.r_sh + (ch - r * p.r_sh) < p.r_fw;
   }
-  return p.out_mode == 0 || ((m >> 5) % p.cpt) * 32 + (m & 31) < p.Ci;   // padded channels of a tap carry no output
+  return p.out_mode == 0 || p.out_mode == 3 || ((m >> 5) % p.cpt) * 32 + (m & 31) < p.Ci;   // padded channels of a tap carry no output
 }
 __device__ __forceinline__ size_t out_index(const GemmParams& p, int m, int n) {
   if (p.out_mode == 1) {   // filter_diff[co = n][ci][r][s]; tap (kh,kw) of the correlation is filter element ff-1-tap
@@ -780,6 +783,43 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
         for (int c0 = 16 * slot; c0 < p.bn; c0 += 16 * kEpiSlots) {
           uint32_t r[16];
           tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc_stage * BN_MAX + half * BN_MAX + c0), r);
+          if (p.out_mode == 3) {   // lane = output channel m, columns = 16 consecutive flat pixels: contiguous along the pixel axis
+            if (row_ok) {          // of plane (image, m) until the image ends (never split-K: see conv_tma_fprop)
+              const float bv = add_bias ? __ldg(p.bias + m) : 0.f;
+              int n = n0 + c0, img = n / p.P, pix = n - img * p.P;
+              float* q = p.out + static_cast<size_t>(img) * p.img_stride + static_cast<size_t>(m) * p.P;
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float val = __uint_as_float(r[j]) + bv;
+                v[j] = (relu && !(val > 0.f)) ? 0.f : val;
+              }
+              if (pix + 16 <= p.P && n + 16 <= p.N) {
+                // the 16 pixels are one contiguous 64-byte run of plane (img, m): 16-byte stores from the first aligned
+                // float on (the run's alignment differs per lane: plane sizes are odd), scalars at both ends
+                float* d = q + pix;
+                const int head = static_cast<int>((4u - ((reinterpret_cast<uintptr_t>(d) >> 2) & 3u)) & 3u);
+#define MNV_RUN(H)                                                                                                         \
+                {                                                                                                          \
+                  _Pragma("unroll") for (int j = 0; j < H; ++j) d[j] = v[j];                                               \
+                  _Pragma("unroll") for (int j = H; j + 4 <= 16; j += 4)                                                   \
+                    *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);                   \
+                  _Pragma("unroll") for (int j = H + (16 - H) / 4 * 4; j < 16; ++j) d[j] = v[j];                           \
+                }
+                if (head == 0) MNV_RUN(0) else if (head == 1) MNV_RUN(1) else if (head == 2) MNV_RUN(2) else MNV_RUN(3)
+#undef MNV_RUN
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j, ++n) {
+                  if (n < p.N) {
+                    q[pix] = v[j];
+                    if (++pix == p.P) { pix = 0; q += p.img_stride; }
+                  }
+                }
+              }
+            }
+            continue;
+          }
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -889,7 +929,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
                 for (int h = 0; h < kHalves; ++h) tma_prefetch_2d(&tmap_a, kp * BK, t.mt * kTileM + h * BM);
               }
             }
-            if (!(AM == A_TMA && p.b_mn)) {
+            if (!(AM == A_TMA && (p.b_mn || p.b_im2col))) {
               const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;
               for (int h = 0; h < halves; ++h) {
                 const int n0 = t.nt * p.bn + h * rows;
@@ -927,6 +967,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           }
           const uint32_t dst = smem_base + stage * kSBytes + kATile;
           const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;   // a TMA box has at most 256 rows
+          if (AM == A_TMA && p.b_im2col) {   // transposed orientation: the n-tile's bn pixels x 32 channels of tap (kh, kw)
+            const int n_first = t.nt * p.bn, img = n_first / p.P, pix = n_first - img * p.P, oh = pix / p.Wo;
+            const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
+            tma_load_im2col_4d(dst, &tmap_b, full0 + 8 * stage, cc * BK, (pix - oh * p.Wo) * p.sh - p.pw, oh * p.sv - p.ph, img, tap - kh * p.fw, kh);
+          } else
           if (AM == A_TMA && p.b_mn) {   // MN-major B: one 32 n x 32 k box per 32 columns (bn % 32 == 0, never wide)
             for (int j = 0; j < p.bn / 32; ++j) tma_load_2d(dst + j * 4096, &tmap_b, full0 + 8 * stage, t.nt * p.bn + 32 * j, ks * BK);
           } else
@@ -1464,6 +1509,7 @@ MNV_OPT g_opt_no_ktab{0};    // 1: table-free forward gather (debug)
 MNV_OPT g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather kernel (debug / tuning)
 MNV_OPT g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
 MNV_OPT g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
+MNV_OPT g_opt_no_transposed{0};  // 1: narrow-output convolutions keep the D[pixel][co] orientation (tuning)
 MNV_OPT g_opt_no_nhwc_wgrad{0}; // 1: backward-filter keeps the re-pitched NCHW top_diff (K-major B) instead of the channels-last one (tuning)
 MNV_OPT g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
 
@@ -2022,7 +2068,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.b_im2col = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -2094,19 +2140,34 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   p.P = Ho * Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
   p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt; p.relu = relu;
   plan_tiles(p, ws2_bytes, true, true);
-  // Measured on AlexNet's layers (tools/tma_diag.py, profiles/r01_tma_diag_*.log): the all-TMA kernel is 10-35%
-  // faster than the gather kernel, but the channels-last pre-pass costs one pass over the input, so the path pays
-  // only when the GEMM does enough work per input element (Co * taps >= ~3000, i.e. ~1500 flop per input byte).
-  // Narrow outputs (bn <= 128) are the gather kernel's worst case (128 x 96 tile: 270 TF/s, against 402 TF/s for
-  // the 256 x 96 tile here): always taken.  "force_tma_a" overrides for experiments.
-  if (!s2d && !g_opt_force_tma_a.load() && static_cast<long long>(Co) * ff < 3000 && p.bn > 128) return MNV_OK;
+  // Round 1 took this path only when the GEMM did enough work per input element to pay for the channels-last pre-pass
+  // (Co * taps >= 3000, or a narrow output).  With the twins shared between the calls of a step (and between the branches
+  // of an inception module) the pre-pass is paid once per array, and the rule lost on both nets: always taken now
+  // (GoogLeNet b120 15.95 -> 14.56 ms per step, AlexNet b256 5.66 -> 5.63 ms).  "no_tma_a" still forces the gather kernel.
+  (void)g_opt_force_tma_a;
   p.partial = p.splits > 1 ? static_cast<float*>(ws2) : nullptr;
   plan_tail(p, ws2, ws2_bytes);
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
-  if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
-  if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
+  // Narrow outputs (80..128 filters: AlexNet conv2 backward-data, GoogLeNet's 96 / 112 / 128-filter layers): a 128 x 96 x 8
+  // UMMA costs ~95 cycles against 138 for 128 x 256 x 8, so D[pixel][co] runs the tensor pipe at ~0.43 of its rate however
+  // well it is fed.  Transposed, D[co][pixel], the filters are the 128-lane operand (TMA_A_TILED_K over the packed filter)
+  // and 256 pixels the N of every instruction (the im2col box becomes the B tile): ~0.75 for 96 filters.  The epilogue then
+  // owns 16 consecutive pixels of one output plane per thread.  Only when the pixel tiles fill the machine without split-K.
+  bool transposed = false;
+  GemmParams q = p;
+  if (!s2d && Co >= 80 && Co <= BM && !g_opt_no_transposed.load()) {
+    q.M = Co; q.N = static_cast<int>(M); q.a = wb; q.b = xh; q.lda = p.K; q.a_mode = TMA_A_TILED_K; q.b_im2col = 1; q.out_mode = 3;
+    q.tail_first = 0; q.tail_splits = 0; q.tail_stages = 0; q.partial = nullptr;
+    plan_tiles(q, 0, false, false);
+    transposed = q.splits == 1 && q.m_tiles == 1 && q.n_tiles >= sm_budget() / 2 &&
+                 make_b_tmap(&tm_a, wb, Co, p.K, p.K, BM) && make_im2col_tmap(&tm_b, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, q.bn, false);
+  }
+  if (!transposed) {
+    if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
+    if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
+  }
   int rc = MNV_OK;
   if (s2d) rc = launch_s2d(x, xh, N, *s2d, Cp, s);
   else if (!(use_twin && twin.valid())) {
@@ -2119,7 +2180,7 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   rc = finish_launch();
   if (rc) return rc;
   *done = true;
-  return launch_umma_tma(p, tm_a, tm_b, s);
+  return launch_umma_tma(transposed ? q : p, tm_a, tm_b, s);
 }
 
 // Strided few-channel convolution through its space-to-depth view on the shift-GEMM kernel (see conv_shift_fwd_kernel).
@@ -2208,6 +2269,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   if (k == "no_nhwc_wgrad") return g_opt_no_nhwc_wgrad.exchange(value);
+  if (k == "no_transposed") return g_opt_no_transposed.exchange(value);
   return -1;
 }
 #endif
@@ -2316,8 +2378,9 @@ int mnv_conv_twin_wanted(int N, int Ci, int Co, int H, int W, int ph, int pw, in
   S2D v;
   const int Ho = (H + 2 * ph - fh) / sv + 1, Wo = (W + 2 * pw - fw) / sh + 1;
   const bool shift = s2d_plan(&v, Ci, H, W, Ho, Wo, ph, pw, sv, sh, fh, fw);
-  const bool fwd = !shift && lim && chan_ok(Ci) && !(static_cast<long long>(Co) * ff < 3000 && Co > 128);
-  const bool dgrad = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && chan_ok(Co) && !(static_cast<long long>(Ci) * ff < 3000 && Ci > 128);
+  const bool fwd = !shift && lim && chan_ok(Ci);
+  const bool dgrad = sv == 1 && sh == 1 && fh - 1 - ph >= 0 && fw - 1 - pw >= 0 && chan_ok(Co);
+  (void)ff;
   const bool wgrad = lim && chan_ok(Ci);
   return ((fwd || wgrad) ? 1 : 0) | ((dgrad || wgrad) ? 2 : 0);
 }

@@ -150,6 +150,11 @@ TMA_CASES = [
     (2, 96, 64, 27, 27, 2, 2, 1, 1, 5, 5),      # AlexNet conv2 channels: 256-row tiles for backward-data (Co <= 128)
     (2, 384, 384, 13, 13, 1, 1, 1, 1, 3, 3),    # AlexNet conv4: 108 k-stages, wide (384-column) tile
     (5, 160, 300, 7, 7, 1, 1, 1, 1, 3, 3),
+    # 80..128 filters with enough pixel tiles: the transposed orientation D[co][pixel] (im2col operand as B)
+    (40, 64, 96, 28, 28, 1, 1, 1, 1, 3, 3),     # forward transposed (Co = 96); 31360 pixels = 123 tiles, image boundaries inside tiles
+    (33, 32, 128, 27, 25, 0, 0, 1, 1, 1, 1),    # 1x1, Co = 128, odd plane size
+    (30, 96, 64, 27, 27, 2, 2, 1, 1, 5, 5),     # backward-data transposed (Ci = 96 outputs), AlexNet conv2 geometry
+    (100, 112, 48, 14, 14, 1, 1, 1, 1, 3, 3),   # backward-data with 112 outputs; forward (Co = 48) stays put
 ]
 OPERAND_PATHS = [("gather", {"no_tma_a": 7}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tma+tall", {"force_tma_a": 1}),
                  ("tma, float32 maps", {"force_tma_a": 1, "tma_tf32": 0}), ("default", {})]
