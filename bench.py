@@ -352,6 +352,21 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
+    if args.workload == "mlp":
+        # configs[0] is the one config the reference can run on its own CPU stack: NArray -> DagScheduler ->
+        # CpuDevice -> basic::, compiled from /root/reference into oracle/_ref, ReluBackward supplied as a user ComputeFn
+        from oracle import pyoracle as orc
+        r = orc.run_reference_mlp(wl["batch"], max(args.steps, 1), max(args.warmup, 0))
+        if r is not None:
+            emit({"impl": "reference", "metric": "mlp train images/s", "value": r["images_per_s"], "unit": "images/s", "n_gpus": 0,
+                  "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                  "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"], "app": r["app"]},
+                  "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": 4, "kind": "reference",
+                                   "sample": "%d steps of batch %d through the reference's own stack (4 CpuDevice worker threads, one "
+                                             "thread per op); ReluBackward has no CPU implementation in the reference (bundle.h:32) and is "
+                                             "supplied as a user ComputeFn" % (r["steps"], r["mb"])},
+                  "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            return
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     rate1, dt1, used_ref = cpu_step_rate(wl, 1, 1, 0)           # calibration: one image
     budget = 150.0
@@ -691,6 +706,16 @@ def main():
             cpu_ops = cpu_reference_ops()
         except Exception as ex:
             cpu_ops = {"unavailable": repr(ex)}
+        try:       # configs[0] end to end through the reference's own CPU stack, next to our mlp_b256 line
+            from oracle import pyoracle as orc
+            r = orc.run_reference_mlp(256, 10, 2)
+            if r is not None:
+                cpu_ops["config0_mnist_mlp_reference_stack"] = {
+                    "images_per_s": r["images_per_s"], "ms_per_step": r["ms_per_step"], "kind": "reference", "cores": 4,
+                    "what": "apps/mnist_mlp b256 through NArray -> DagScheduler -> CpuDevice (4 worker threads) -> basic::, compiled from "
+                            "/root/reference (oracle/_ref); ReluBackward (no CPU impl in the reference) as a user ComputeFn"}
+        except Exception as ex:
+            cpu_ops["config0_mnist_mlp_reference_stack"] = {"unavailable": repr(ex)}
 
     if rank == 0:
         metric = "AlexNet train images/s" if args.workload == "alexnet" else args.workload + " train images/s"

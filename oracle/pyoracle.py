@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libmnv_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libminerva_ref.so")
+REF_MLP = os.path.join(_HERE, "_ref", "ref_mnist_mlp")     # configs[0] through the reference's own NArray / DagScheduler / CpuDevice stack
 
 F = C.POINTER(C.c_float)
 
@@ -25,7 +26,7 @@ def build(force=False):
     if force or not os.path.exists(_LIB) or (
             os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "mnv_oracle.c"))):
         subprocess.check_call(["make", "-s", "-C", _HERE, "_build/libmnv_oracle.so"])
-    if os.path.isdir("/root/reference/minerva") and (force or not os.path.exists(_REF)):
+    if os.path.isdir("/root/reference/minerva") and (force or not os.path.exists(_REF) or not os.path.exists(REF_MLP)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
 
 
@@ -47,6 +48,19 @@ def ref():
     if _ref is None and os.path.exists(_REF):
         _ref = C.CDLL(_REF)
     return _ref
+
+
+def run_reference_mlp(mb=256, steps=20, warmup=3, timeout=600):
+    """BASELINE configs[0] through the reference stack (oracle/ref_mnist_mlp.cpp): -> the program's JSON line as a dict,
+    or None when oracle/_ref was never built."""
+    import json
+    build()
+    if not os.path.exists(REF_MLP):
+        return None
+    out = subprocess.run([REF_MLP, str(mb), str(steps), str(warmup)], capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError("ref_mnist_mlp failed: " + out.stderr[-400:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
 
 
 def have_ref():

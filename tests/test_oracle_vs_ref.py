@@ -116,3 +116,12 @@ def test_exact_mode_math_is_glibc(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     for fn in ("expf", "logf", "tanhf", "sigmoid"):
         assert fn + ": 0 mismatches" in out.stdout, out.stdout
+
+
+def test_reference_stack_runs_config0():
+    """BASELINE configs[0] through the REFERENCE'S OWN stack (its 27 CPU sources compiled into oracle/_ref/libminerva_cpu.so,
+    driven by oracle/ref_mnist_mlp.cpp through NArray / DagScheduler / CpuDevice): trains, and its softmax is a softmax."""
+    r = orc.run_reference_mlp(mb=32, steps=3, warmup=1)
+    if r is None:
+        pytest.skip("oracle/_ref was never built (no /root/reference on this box)")
+    assert r["images_per_s"] > 0 and abs(r["softmax_column_sum"] - 1.0) < 1e-5 and r["cpu_worker_threads"] == 4
