@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the GoogLeNet / LeNet / MLP lines after the headline")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (NetTrainer(graph=True)); auto = on at 1 GPU")
     ap.add_argument("--merge", default="auto", choices=["auto", "peer", "nccl", "off"], help="N>1 gradient merge (owl/net/merge.py)")
     ap.add_argument("--nccl-ctas", type=int, default=0,
                     help="N>1: SMs left to NCCL (NCCL_MAX_CTAS) and kept out of the persistent tensor-core kernel's grid; 0 = do not manage")
@@ -457,9 +459,23 @@ def measure(C, args, wl_key, headline):
     x, onehot = host_batch(wl, net.input_shape, batch, 100 + rank)
     du = net.get_data_unit()
     du.data, du.label = owl.from_numpy(x), owl.from_numpy(onehot)
-    trainer = onet.NetTrainer(net, C.dist if world > 1 else None, fused_update=not args.unfused_update, merge=args.merge)
+    use_graph = world == 1 and not args.unfused_update and args.graph != "off"
+    trainer = onet.NetTrainer(net, C.dist if world > 1 else None, fused_update=not args.unfused_update, merge=args.merge, graph=use_graph)
     gdev = rt.current_device()
-    res = {"workload": wl["name"], "per_gpu_batch": batch, "global_batch": batch * world}
+    res = {"workload": wl["name"], "per_gpu_batch": batch, "global_batch": batch * world, "cuda_graph": use_graph}
+
+    def timed_steps(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0, r0 = lib.mnv_launch_count(), trainer.graph_replays
+        e0.record(gdev.stream)
+        t_host = time.perf_counter()
+        for _ in range(n):
+            trainer.step()
+        e1.record(gdev.stream)
+        t_host = time.perf_counter() - t_host      # host time to ENQUEUE the steps (no sync inside)
+        C.sync_all()
+        launches = lib.mnv_launch_count() - l0 + (trainer.graph_replays - r0) * trainer.graph_launches_per_step
+        return C.max_over_ranks(e0.elapsed_time(e1)), t_host, int(launches)
 
     for _ in range(max(3, args.warmup)):
         trainer.step()
@@ -472,20 +488,23 @@ def measure(C, args, wl_key, headline):
     sampler = ClockSampler(C.local) if headline else None
     if sampler:
         sampler.start()
-    launches0 = lib.mnv_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(gdev.stream)
-    for _ in range(args.steps):
-        trainer.step()
-    e1.record(gdev.stream)
-    C.sync_all()
-    launches = lib.mnv_launch_count() - launches0
+    ms_total, t_host, launches = timed_steps(args.steps)
     if sampler:
         sampler.stop_flag = True
         res["clocks"] = sampler.summary()
-    ms_total = C.max_over_ranks(e0.elapsed_time(e1))
+    if use_graph:
+        # the same steps launched one kernel at a time from Python (what every N > 1 run does): reported beside the headline
+        res["launches_per_graph_replay"] = trainer.graph_launches_per_step
+        trainer.graph = False
+        for _ in range(3):
+            trainer.step()
+        C.sync_all()
+        ms_e, t_e, _ = timed_steps(args.steps)
+        res["eager"] = {"value": batch * world * args.steps / (ms_e * 1e-3), "ms_per_step": ms_e / args.steps,
+                        "host_enqueue_ms_per_step": t_e * 1e3 / args.steps}
+        trainer.graph = True
     res.update(value=batch * world * args.steps / (ms_total * 1e-3), ms_per_step=ms_total / args.steps,
-               gpu_launches=int(launches), loss=float(net.get_loss_units()[-1].getloss()),
+               gpu_launches=int(launches), host_enqueue_ms_per_step=t_host * 1e3 / args.steps, loss=float(net.get_loss_units()[-1].getloss()),
                gradient_merge=trainer.merge_kind)
     if hasattr(trainer, "merge_note"):
         res["gradient_merge_note"] = trainer.merge_note
@@ -520,7 +539,7 @@ def run_e2e(C, args, net, trainer, du, x, onehot, batch):
             if not pipelined:
                 loss_val = lu.getloss()
                 continue
-            dsum, n = lu.getloss_device()
+            dsum, n = trainer.loss_device if trainer.graph else lu.getloss_device()     # graph: reduced inside the recording
             host_loss[cur].copy_(dsum.as_torch(), non_blocking=True)
             loss_ready[cur].record(gdev.stream)
             if pending is not None:
@@ -645,11 +664,13 @@ def main():
     # ---- per-call device times (every rank runs the two instrumented steps: they contain the gradient merge) ----------
     roofline, optable = None, None
     pk = peaks()
+    was_graph, trainer.graph = trainer.graph, False      # per-call events need the calls: two eager steps
     if rank == 0:
         rt.profiler = rt.EventProfiler()
     for _ in range(2):
         trainer.step()
     sync_all()
+    trainer.graph = was_graph
     if rank == 0:
         table = rt.profiler.table()
         rt.profiler = None
@@ -728,9 +749,13 @@ def main():
                        "parallelism": "dp%d" % world, "update": "chain" if args.unfused_update else "fused momentum-SGD kernel",
                        "l2": "working set per step (~2 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "gradient_merge": head["gradient_merge"],
+                       "launch": ("the whole step (forward, backward, loss reduction, update: %d kernel launches) recorded once into a CUDA "
+                                  "graph and replayed; `eager` = the same steps launched call by call" % head.get("launches_per_graph_replay", 0))
+                                 if head.get("cuda_graph") else "every C-ABI call launched from Python",
                        **({"gradient_merge_note": head["gradient_merge_note"]} if "gradient_merge_note" in head else {}),
                        **({"tuning": args.mnv_opt} if args.mnv_opt else {})},
-            "clocks": head.get("clocks"), "gpu_launches": head["gpu_launches"], "loss": head["loss"],
+            "clocks": head.get("clocks"), "gpu_launches": head["gpu_launches"], "host_enqueue_ms_per_step": head["host_enqueue_ms_per_step"], "loss": head["loss"],
+            "cuda_graph": head.get("cuda_graph", False), "eager": head.get("eager"),
             "e2e": head.get("e2e"), "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,
             "other_configs": others, "cpu_reference_ops": cpu_ops,
             "peaks": {k: pk.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},

@@ -246,6 +246,11 @@ int mnv_pooled_size(int x, int pad, int window, int stride);
  * (basic.cpp:275, cuda_perform.cu:621).  Runs on `stream` (the reference's ran off-stream). */
 int mnv_randn(float* dst, size_t n, unsigned int seed, float mean, float var, mnv_stream_t stream);
 int mnv_rand_bernoulli(float* dst, size_t n, unsigned int seed, float p, mnv_stream_t stream);
+/* The same Bernoulli stream with its key read on the device: seed = (*seed_base + seed_add) ^ seed_xor.  For callers that
+ * record a training step into a CUDA graph (owl.net.NetTrainer(graph=True)): the launch is frozen, the mask is not -- the
+ * caller stores the step's base word before every replay.  Bit-identical to mnv_rand_bernoulli with that seed. */
+int mnv_rand_bernoulli_ds(float* dst, size_t n, const unsigned int* seed_base, unsigned int seed_add,
+                          unsigned int seed_xor, float p, mnv_stream_t stream);
 int mnv_fill(float* dst, size_t n, float val, mnv_stream_t stream);
 
 /* ---- a22 LRN across channels (cuda_perform.h:72-73; cuda_kernel.h:223-331) ------------------
@@ -337,7 +342,9 @@ int mnv_image_transform_u8(const unsigned char* src, const float* mean, const in
  * skipped.  twin == NULL: exactly the reference-shaped entry (copy in the workspace, once per call).  Results are
  * bit-identical either way.  mnv_conv_twin_wanted(): bit 0 = some direction of this convolution can use a bottom twin,
  * bit 1 = a top_diff twin (0: do not allocate; no launch).  mnv_conv_backward_filter_tw: bias_diff may be NULL; when it
- * is not, the bias sums ride on the pass that fills the top_diff twin (so ask for them in the call that fills it). */
+ * is not, the bias sums ride on the pass that fills the top_diff twin (so ask for them in the call that fills it).
+ * State word: bit 0 = the copy is current; bit 1 = the buffer's tail also holds per-(image, 128-pixel tile, channel) sums
+ * of the array (left by mnv_relu_backward_tw), from which backward-filter folds bias_diff without reading top_diff. */
 size_t mnv_conv_twin_bytes(int num_images, int num_channels, int height, int width);
 int mnv_conv_twin_wanted(int num_images, int bottom_num_channels, int top_num_channels, int bottom_height,
                          int bottom_width, int pad_height, int pad_width, int stride_vertical, int stride_horizontal,
@@ -358,6 +365,13 @@ int mnv_conv_backward_filter_tw(const float* bottom, const float* top_diff, floa
                                 int stride_horizontal, int filter_height, int filter_width, float* bottom_twin,
                                 int* bottom_twin_state, float* top_diff_twin, int* top_diff_twin_state, void* workspace,
                                 size_t workspace_bytes, mnv_stream_t stream);
+
+/* ReLU backward (bottom_diff = top > 0 ? top_diff : 0, as mnv_relu_backward) that also fills the channels-last twin of
+ * bottom_diff -- the top_diff twin of the convolution whose output the ReLU rectified -- and the channel sums behind it
+ * (*twin_state = 3).  One pass of 16 B per element replaces ReLU backward (12 B) + the conversion (8 B).  twin == NULL:
+ * the plain op. */
+int mnv_relu_backward_tw(const float* top, const float* top_diff, float* bottom_diff, int num_images, int num_channels,
+                         int height, int width, float* twin, int* twin_state, mnv_stream_t stream);
 
 /* ---- explicit in-place forms ------------------------------------------------------------------
  * The entries above never alias an output with an input.  Two callers need to: the data-parallel gradient merge

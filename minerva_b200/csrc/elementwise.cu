@@ -187,7 +187,11 @@ __device__ __forceinline__ void store4_guarded(float* dst, size_t blk, size_t n,
   }
 }
 
-__global__ void __launch_bounds__(kBlock) bernoulli_kernel(float* __restrict__ dst, size_t n, uint32_t seed, float p) {
+// seed_base != null (mnv_rand_bernoulli_ds): the stream's key is (*seed_base + seed) ^ seed_xor, read on the device -- a launch
+// recorded in a CUDA graph draws a new mask on every replay once the caller has stored the step's base word.
+__global__ void __launch_bounds__(kBlock) bernoulli_kernel(float* __restrict__ dst, size_t n, uint32_t seed, float p,
+                                                           const uint32_t* __restrict__ seed_base, uint32_t seed_xor) {
+  if (seed_base) seed = (__ldg(seed_base) + seed) ^ seed_xor;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   size_t nblk = (n + 3) / 4;
   for (size_t blk = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; blk < nblk; blk += stride) {
@@ -486,7 +490,15 @@ int mnv_fill(float* dst, size_t n, float v, mnv_stream_t s) {
 int mnv_rand_bernoulli(float* dst, size_t n, unsigned int seed, float p, mnv_stream_t s) {
   if (n == 0) return MNV_OK;
   MNV_CHECK_PTR(dst);
-  bernoulli_kernel<<<stream_grid((n + 3) / 4), kBlock, 0, as_stream(s)>>>(dst, n, seed, p);
+  bernoulli_kernel<<<stream_grid((n + 3) / 4), kBlock, 0, as_stream(s)>>>(dst, n, seed, p, nullptr, 0u);
+  return finish_launch();
+}
+int mnv_rand_bernoulli_ds(float* dst, size_t n, const unsigned int* seed_base, unsigned int seed_add, unsigned int seed_xor, float p,
+                          mnv_stream_t s) {
+  if (n == 0) return MNV_OK;
+  MNV_CHECK_PTR(dst);
+  MNV_CHECK_PTR(seed_base);
+  bernoulli_kernel<<<stream_grid((n + 3) / 4), kBlock, 0, as_stream(s)>>>(dst, n, seed_add, p, seed_base, seed_xor);
   return finish_launch();
 }
 int mnv_randn(float* dst, size_t n, unsigned int seed, float mean, float var, mnv_stream_t s) {

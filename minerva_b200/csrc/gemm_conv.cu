@@ -1602,8 +1602,12 @@ static bool make_im2col_tmap(CUtensorMap* tm, const float* x, int Cp, int W, int
 
 // x[n][c][hw] -> y[n][hw][Cp]: channels-last copy for the im2col tensor maps, channels C..Cp-1 zero (rounding to
 // TF32 is done by the TFLOAT32-typed tensor map).  Tiles go through shared memory so both sides stay coalesced.
+// RELU: the source is ReLU backward's result computed on the fly, v = act > 0 ? x : 0, also written in NCHW to `dx` (the
+// reference op's output): one pass (8 B read + 8 B written per element) instead of ReLU backward (12 B) plus this copy (8 B).
+template <bool RELU>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cp, int HW,
-                                                           int tiles_c, int tiles_hw, long long total_tiles, float* __restrict__ tilesum) {
+                                                           int tiles_c, int tiles_hw, long long total_tiles, float* __restrict__ tilesum,
+                                                           const float* __restrict__ act = nullptr, float* __restrict__ dx = nullptr) {
   // tile = 32 channels x 128 pixels: 16 independent 128-byte-per-warp loads per thread before the barrier.
   // tilesum != null: the pass also leaves the sum of every (image, pixel tile, channel) in tilesum[(n * tiles_hw + th) * C + c]
   // -- for a top_diff that is ConvBackwardBias's per-tile partial, folded over (n, th) by rowsum_fold_kernel in a fixed order.
@@ -1623,7 +1627,16 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int hw = lane + 32 * j;
-        const float v = (c0 + c < C && h0 + hw < HW) ? __ldg(src + static_cast<size_t>(c) * HW + hw) : 0.f;
+        float v = 0.f;
+        if (c0 + c < C && h0 + hw < HW) {
+          const size_t o = static_cast<size_t>(c) * HW + hw;
+          v = __ldg(src + o);
+          if (RELU) {
+            const size_t g = (n * C + c0) * HW + h0 + o;
+            v = __ldg(act + g) > 0.f ? v : 0.f;
+            dx[g] = v;
+          }
+        }
         tile[c][hw] = v;
         acc += v;
       }
@@ -2086,7 +2099,7 @@ static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, c
   const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
   const long long total = static_cast<long long>(N) * tiles_c * tiles_hw;
   const long long cap = static_cast<long long>(kNumSMs) * 16;
-  nchw_to_nhwc_kernel<<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum);
+  nchw_to_nhwc_kernel<false><<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum);
   return finish_launch();
 }
 
@@ -2098,8 +2111,13 @@ struct Twin {
   float* ptr;        // null: none
   int* state;        // *state != 0: already filled
   bool usable() const { return ptr != nullptr && state != nullptr; }
-  bool valid() const { return usable() && *state != 0; }
+  bool valid() const { return usable() && (*state & 1) != 0; }
+  bool has_sums() const { return valid() && (*state & 2) != 0; }   // the per-tile channel sums behind the copy are filled too
 };
+// Layout of a twin buffer of mnv_conv_twin_bytes(): [n][hw][Cp] floats, then (256-byte aligned) the per-(image, pixel tile, channel)
+// sums a filling pass may leave for ConvBackwardBias: tilesum[(n * tiles_hw + th) * C + c], tiles of 128 pixels.
+static size_t twin_copy_bytes(int N, int C, int HW) { return round256(static_cast<size_t>(N) * HW * ((C + 3) / 4 * 4) * sizeof(float)); }
+static size_t twin_sums_bytes(int N, int C, int HW) { return round256(static_cast<size_t>(N) * ((HW + 127) / 128) * C * sizeof(float)); }
 
 // Cross-correlation of x[N][Ci][H][W] with `ff` taps as a GEMM whose two operands both arrive through TMA:
 //   A[m = (n,oh,ow)][k = (tap, c)]  channels-last copy of x through an im2col tensor map (no gather warps, padding
@@ -2384,9 +2402,27 @@ int mnv_conv_twin_wanted(int N, int Ci, int Co, int H, int W, int ph, int pw, in
   const bool wgrad = lim && chan_ok(Ci);
   return ((fwd || wgrad) ? 1 : 0) | ((dgrad || wgrad) ? 2 : 0);
 }
+int mnv_relu_backward_tw(const float* top, const float* top_diff, float* bottom_diff, int N, int C, int H, int W, float* twin,
+                         int* twin_state, mnv_stream_t stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0) return MNV_EINVAL;
+  const size_t n = static_cast<size_t>(N) * C * H * W;
+  if (n == 0) return MNV_OK;
+  if (!top || !top_diff || !bottom_diff) return MNV_EINVAL;
+  const int Cp = (C + 3) / 4 * 4, HW = H * W;
+  if (!twin || !twin_state || !fits_int(static_cast<long long>(N) * HW * Cp))    // no twin wanted: the plain op
+    return mnv_relu_backward(top, top, top_diff, bottom_diff, N, C, H, W, stream);
+  const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
+  const long long total = static_cast<long long>(N) * tiles_c * tiles_hw, cap = static_cast<long long>(kNumSMs) * 16;
+  float* tilesum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(twin) + twin_copy_bytes(N, C, HW));
+  nchw_to_nhwc_kernel<true><<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, as_stream(stream)>>>(
+      top_diff, twin, C, Cp, HW, tiles_c, tiles_hw, total, tilesum, top, bottom_diff);
+  int rc = finish_launch();
+  if (!rc) *twin_state = 3;     // copy + per-tile channel sums
+  return rc;
+}
 size_t mnv_conv_twin_bytes(int N, int C, int H, int W) {
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
-  return round256(static_cast<size_t>(N) * H * W * ((C + 3) / 4 * 4) * sizeof(float));
+  return twin_copy_bytes(N, C, H * W) + twin_sums_bytes(N, C, H * W);
 }
 static int conv_forward_impl(const float* bottom, const float* filter, const float* bias, float* top, int N, int Ci,
                              int Co, int H, int W, int ph, int pw, int sv, int sh, int fh, int fw, void* workspace,
@@ -2627,6 +2663,13 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
               if (rc) return rc;
               *bias_done = true;
             }
+          }
+          if (bias_diff && !*bias_done && dtw.has_sums()) {   // the twin's filler (mnv_relu_backward_tw) left the per-tile sums
+            const float* sums = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(dtw.ptr) + twin_copy_bytes(N, Co, P));
+            rowsum_fold_kernel<<<(Co + 31) / 32, 1024, 0, s>>>(sums, bias_diff, N * tiles_hw, Co);
+            rc = finish_launch();
+            if (rc) return rc;
+            *bias_done = true;
           }
           return launch_umma_tma(q, tm_a, tm_b, s);
         }

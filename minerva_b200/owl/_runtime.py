@@ -105,6 +105,28 @@ def set_rank_salt(rank):
     _seed[2] = int(rank) & 0xFFFF
 
 
+class GraphSeeds:
+    """Generator keys for a training step recorded into a CUDA graph: the k-th draw of the step uses
+    (*word + k * 0x85EBCA77) ^ salt on the device (mnv_rand_bernoulli_ds) -- the key next_seed() would have returned for
+    it -- and arm() stores the step's base word before every replay and advances the host counter by the step's draws."""
+
+    def __init__(self, dev):
+        self.word = torch.zeros(1, dtype=torch.int32, device=dev.device)
+        self.calls = 0
+
+    def next(self, salted=False):
+        self.calls += 1
+        return (self.calls * 0x85EBCA77) & 0xFFFFFFFF, ((_seed[2] * 0xC2B2AE35) & 0xFFFFFFFF) if salted else 0
+
+    def arm(self):
+        base = (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF
+        self.word.fill_(base - (1 << 32) if base >= (1 << 31) else base)      # enqueued on the device's stream, before the replay
+        _seed[1] += self.calls
+
+
+capture_seeds = None     # a GraphSeeds while NetTrainer records a step: generators take their key from the device word
+
+
 def next_seed(salted=False):
     _seed[1] += 1
     s = (_seed[0] * 0x9E3779B1 + _seed[1] * 0x85EBCA77) & 0xFFFFFFFF

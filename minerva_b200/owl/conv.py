@@ -48,6 +48,10 @@ class Convolver:
     def bp(self, y, x, w):
         return NArray.conv_backward_data(y, x, w, self.param)
 
+    def geo(self, x, w):
+        """The (N, Ci, Co, H, W, pads, strides, fh, fw) tuple the mnv_conv_* entries take for this layer (not in the reference API)."""
+        return NArray.conv_geo(x, w, self.param)
+
     def weight_grad(self, y, x, w):
         return NArray.conv_backward_filter(y, x, w, self.param)
 

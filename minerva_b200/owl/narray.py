@@ -335,6 +335,18 @@ class NArray:
         return NArray._act_back("mnv_relu_backward", diff, top, bottom)
 
     @staticmethod
+    def relu_back_tw(diff, top, conv_geo):
+        """ReLU backward for a 4-D activation that a convolution of geometry `conv_geo` produced: same result as relu_back,
+        and the result carries its channels-last twin (the top_diff twin that convolution's backward calls will ask for)."""
+        _check(diff._shape == top._shape and len(diff._shape) == 4, "inputs size mismatch")
+        dev = _rt.current_device()
+        out = NArray._new(diff._shape, dev)
+        W, H, C, N = diff._shape
+        _, _, tw, ts = NArray._twins(conv_geo, None, out, dev)
+        NArray._call("mnv_relu_backward_tw", dev, top._on(dev).data_ptr(), diff._on(dev).data_ptr(), out._t.data_ptr(), N, C, H, W, tw, ts)
+        return out
+
+    @staticmethod
     def tanh_back(diff, top, bottom):
         return NArray._act_back("mnv_tanh_backward", diff, top, bottom)
 
@@ -431,6 +443,12 @@ class NArray:
         return int((self._t == 0).sum().item())
 
     # ---- convolution family (narray/convolution.cpp) -----------------------------------------------
+    @staticmethod
+    def conv_geo(src, filt, info):
+        W, H, Ci, N = src._shape
+        fw, fh, _, Co = filt._shape
+        return (N, Ci, Co, H, W, info.pad_height, info.pad_width, info.stride_vertical, info.stride_horizontal, fh, fw)
+
     @staticmethod
     def conv_forward(src, filt, bias, info, relu=False):
         W, H, Ci, N = src._shape
@@ -649,7 +667,12 @@ class NArray:
     def randb(s, p):
         dev = _rt.current_device()
         out = NArray._new(s, dev)
-        NArray._call("mnv_rand_bernoulli", dev, out._t.data_ptr(), out.size, _rt.next_seed(salted=True), float(p))
+        cs = _rt.capture_seeds
+        if cs is not None:      # the step is being recorded into a CUDA graph: the key is read on the device at replay time
+            add, xor = cs.next(salted=True)
+            NArray._call("mnv_rand_bernoulli_ds", dev, out._t.data_ptr(), out.size, cs.word.data_ptr(), add, xor, float(p))
+        else:
+            NArray._call("mnv_rand_bernoulli", dev, out._t.data_ptr(), out.size, _rt.next_seed(salted=True), float(p))
         return out
 
     @staticmethod

@@ -111,8 +111,16 @@ class ReluUnit(ComputeUnitSimple):
         self.ff_y = x if self.fused else self.B.ele.relu(x)
         return self.ff_y
 
+    twin_for = None   # set by Net._plan_fusion: the ConvConnection whose output this unit alone reads
+
     def bp(self, y, phase):
-        return y if self.bp_fused else self.B.ele.relu_back(y, self.ff_y)
+        if self.bp_fused:
+            return y
+        geo = getattr(self.twin_for, "geo", None)
+        if geo is not None and len(y.shape) == 4:
+            # the result feeds that convolution's backward calls only: leave its channels-last twin with it
+            return self.B.owl.NArray.relu_back_tw(y, self.ff_y, geo)
+        return self.B.ele.relu_back(y, self.ff_y)
 
 
 class SigmoidUnit(ComputeUnitSimple):
@@ -290,10 +298,13 @@ class ConvConnection(WeightedComputeUnit):
             self.fan_in = self.kernel_size * self.kernel_size * ci
             self.wshape, self.bshape = [self.kernel_size, self.kernel_size, ci, self.num_output], [self.num_output]
             self.init_weights_with_filler()
+        if self.geo is None and hasattr(self.convolver, "geo"):
+            self.geo = self.convolver.geo(act, self.weight)
         if self.fuse_relu:
             return self.convolver.ff(act, self.weight, self.bias, relu=True)
         return self.convolver.ff(act, self.weight, self.bias)
 
+    geo = None           # the C-ABI geometry tuple of this layer (backends with channels-last twins only)
     fuse_grads = True    # Net.fuse_conv_grads: weight and bias gradient from one call (mnv_conv_backward_filter_bias)
 
     def bp(self, sen, phase):
@@ -440,6 +451,14 @@ class Net(object):
                     readers = readers_of(i, u.top_names[0])
                     if len(readers) == 1 and isinstance(readers[0], ReluUnit):
                         u.fuse_relu, readers[0].fused = True, True
+        # a ReluUnit that alone reads a convolution's output produces, in backward, exactly that convolution's top_diff:
+        # its kernel leaves the channels-last twin with the result (mnv_relu_backward_tw)
+        if self.fuse_conv_twins and hasattr(getattr(self.B.owl, "NArray", None), "relu_back_tw"):
+            for i, u in enumerate(self.units):
+                if isinstance(u, ConvConnection):
+                    readers = readers_of(i, u.top_names[0])
+                    if len(readers) == 1 and isinstance(readers[0], ReluUnit):
+                        readers[0].twin_for = u
         # backward: a ReluUnit read only by an LRN or max-pooling unit hands its mask to that unit's backward kernel
         # (mnv_lrn_backward_relu / mnv_max_pooling_backward_relu; both read the ReLU output anyway)
         if getattr(self.B.co, "FUSED_RELU_BACKWARD", False) and self.fuse_relu_backward:

@@ -12,8 +12,10 @@ import time
 
 
 class NetTrainer(object):
-    def __init__(self, net, dist=None, fused_update=True, merge="auto"):
+    def __init__(self, net, dist=None, fused_update=True, merge="auto", graph=False):
         """dist: an initialised torch.distributed module (or None for 1 GPU).
+        graph: record the whole step (forward, backward, loss reduction, update) into a CUDA graph once and replay it
+               (1 GPU, fused update): the step's ~100..750 launches cost one host call -- see _graph_step.
         fused_update: one mnv_sgd_momentum_update per tensor instead of the reference's op chain.
         merge: "peer" = reduce-scatter / all-gather over NVLink peer memory on the copy engines (merge.py),
                "nccl" = one NCCL all-reduce per gradient, "auto" = peer when the process group is NCCL on CUDA and the
@@ -25,6 +27,11 @@ class NetTrainer(object):
         self._pending = []
         self.peer = None
         self.merge_kind = "none (1 GPU)"
+        self.graph = bool(graph)
+        self._g = None                   # recorded step: dict(graph, key, seeds, data, label, launches, loss)
+        self.graph_replays = 0           # replays so far; launches they stand for = graph_launches_per_step each
+        self.graph_launches_per_step = 0
+        self.loss_device = None          # graph mode: (1-element NArray of sum(ln(y) o label), batch) of the last step
         if self.dist and hasattr(net.B.owl, "set_rank_salt"):
             net.B.owl.set_rank_salt(self.dist.get_rank())     # replicas draw different dropout masks, same weights
         if self.dist:
@@ -80,6 +87,95 @@ class NetTrainer(object):
 
     # -- one iteration ------------------------------------------------------------------------------
     def step(self):
+        if self.graph:
+            return self._graph_step()
+        return self._eager_step()
+
+    # -- the step as one CUDA graph -------------------------------------------------------------------
+    def _graph_step(self):
+        """The small configurations are bound by the host: LeNet / the MLP enqueue ~10..40 launches of a few microseconds
+        each, GoogLeNet ~750.  The step's launch sequence does not depend on data, so it is recorded once on the device's
+        stream (every buffer the ops allocate comes from the graph's private pool and keeps its address) and replayed.
+        What varies between steps stays outside the recording: the input batch is copied into the recorded input arrays,
+        the dropout keys are read from a device word stored before every replay (_runtime.GraphSeeds), and a change of the
+        learning rate / momentum / weight decay / batch size records a new graph.  Same kernels, same order, same bits as
+        the eager step."""
+        import torch
+        import minerva_b200.owl._runtime as rt
+        net = self.net
+        if self.dist is not None or not self.fused_update:
+            raise RuntimeError("NetTrainer(graph=True) records the 1-GPU step with the fused update")
+        du = net.get_data_unit()
+        dev = rt.current_device()
+        feed = getattr(du, "feed", None)
+        if feed is not None:             # FeedDataUnit: take the uploaded batch here, forward() is not run on a replay
+            if not du._started:
+                feed.start()
+                du._started = True
+            feed.done()
+            data, label = feed.next()
+        else:
+            data, label = du.data, du.label
+        key = (net.current_lr, net.base_weight_decay, net.momentum, net.batch_size, tuple(data.shape), tuple(label.shape), id(dev))
+        if self._g is None or self._g["key"] != key:
+            if any(net.units[uid].weight is None for uid in net.get_weighted_unit_ids()):
+                # the very first step runs eagerly: lazy initialisation (weight fillers, kernel attributes, driver entry
+                # points) is not recordable; the next call records
+                du.data, du.label = data, label
+                if feed is not None:
+                    du.feed = None
+                try:
+                    self._eager_step()
+                    lu = net.get_loss_units()
+                    self.loss_device = lu[-1].getloss_device() if lu and hasattr(lu[-1], "getloss_device") else None
+                finally:
+                    if feed is not None:
+                        du.feed = feed
+                return
+            self._record(key, data, label, dev)
+        g = self._g
+        if data is not g["data"]:
+            g["data"].as_torch().copy_(data.as_torch(), non_blocking=True)
+        if label is not g["label"]:
+            g["label"].as_torch().copy_(label.as_torch(), non_blocking=True)
+        g["seeds"].arm()
+        g["graph"].replay()
+        self.graph_replays += 1
+
+    def _record(self, key, data, label, dev):
+        import torch
+        import minerva_b200.owl._runtime as rt
+        from minerva_b200 import _lib
+        net = self.net
+        du = net.get_data_unit()
+        owl = net.B.owl
+        self._g = None                   # drop the previous recording (and its pool) first
+        static_data, static_label = owl.zeros(list(data.shape)), owl.zeros(list(label.shape))
+        seeds = rt.GraphSeeds(dev)
+        feed = getattr(du, "feed", None)
+        dev.stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        du.data, du.label = static_data, static_label
+        if feed is not None:
+            du.feed = None               # the recording reads the static arrays; the feed is driven by _graph_step
+        lib = _lib.load()
+        n0 = lib.mnv_launch_count()
+        rt.capture_seeds = seeds
+        try:
+            with torch.cuda.graph(graph, stream=dev.stream):
+                self._eager_step()
+                lu = net.get_loss_units()
+                loss = lu[-1].getloss_device() if lu and hasattr(lu[-1], "getloss_device") else None
+        finally:
+            rt.capture_seeds = None
+            if feed is not None:
+                du.feed = feed
+        rt.set_device(rt._devices.index(dev))      # torch.cuda.graph restores ITS entry stream; make the device's current again
+        self.graph_launches_per_step = int(lib.mnv_launch_count() - n0)
+        self.loss_device = loss
+        self._g = dict(graph=graph, key=key, seeds=seeds, data=static_data, label=static_label)
+
+    def _eager_step(self):
         net = self.net
         if self.peer is not None:
             self.peer.begin_step()

@@ -360,6 +360,12 @@ def test_generators_and_fill(g):
         g.assert_bits_equal(g.host(out)[:n], orc.rand_bernoulli(n, 42, 0.3), "bernoulli")
         g.run("mnv_randn", out, n, 7, 1.5, 0.5)
         np.testing.assert_allclose(g.host(out)[:n], orc.randn(n, 7, 1.5, 0.5), rtol=0, atol=2e-5)
+        # key read on the device (the form a recorded CUDA graph replays): (*base + add) ^ xor, 32-bit wrap-around
+        import torch
+        base = torch.tensor([0xFFFFFFF0 - (1 << 32)], dtype=torch.int32, device="cuda")
+        g.run("mnv_rand_bernoulli_ds", out, n, base, 0x35, 0x5A5A, 0.3)
+        seed = ((0xFFFFFFF0 + 0x35) & 0xFFFFFFFF) ^ 0x5A5A
+        g.assert_bits_equal(g.host(out)[:n], orc.rand_bernoulli(n, seed, 0.3), "bernoulli, device seed")
     n = 1 << 20
     out = g.empty(n)
     g.run("mnv_randn", out, n, 99, 0.0, 0.01)   # AlexNet gaussian filler

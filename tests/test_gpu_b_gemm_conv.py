@@ -469,3 +469,27 @@ def test_conv_twin_entries(g, case):
     call("mnv_conv_backward_filter_tw", dx_, dyd, f2, 0, *geo, 0, 0, 0, 0, ws, ws.numel())
     assert torch.equal(f0, f2)
     assert filled_by_fwd in (0, 1)
+    # mnv_relu_backward_tw: ReLU backward that leaves its result's twin and channel sums; the convolution's backward calls on that
+    # result then give the bits they give on the plain two-op sequence
+    act = rng.normal(0, 1, dy.size).astype(np.float32)
+    actd = g.dev(act)
+    r0, r1 = (torch.full((dy.size,), float("nan"), device="cuda") for _ in range(2))
+    rt, rs = twin(N, Co, Ho, Wo)
+    call("mnv_relu_backward", actd, actd, dyd, r0, N, Co, Ho, Wo)
+    call("mnv_relu_backward_tw", actd, dyd, r1, N, Co, Ho, Wo, rt, ctypes.byref(rs))
+    assert rs.value == 3
+    np.testing.assert_array_equal(g.host(r1), np.where(act > 0, dy, np.float32(0)))
+    assert torch.equal(r0, r1)
+    f3, f4, b3, b4 = (torch.full((k,), float("nan"), device="cuda") for k in (w.size, w.size, Co, Co))
+    call("mnv_conv_backward_filter_bias", dx_, r0, f3, b3, *geo, ws, ws.numel())
+    call("mnv_conv_backward_filter_tw", dx_, r1, f4, b4, *geo, xt, ctypes.byref(xs), rt, ctypes.byref(rs), ws, ws.numel())
+    assert torch.equal(f3, f4)
+    if want & 2:
+        assert torch.equal(b3, b4)         # the same per-tile sums folded in the same order
+    else:
+        assert np.abs(g.host(b4) - g.host(b3)).max() <= tol_b
+    call("mnv_conv_backward_data", r0, dw_, d0, *geo, ws, ws.numel())
+    call("mnv_conv_backward_data_tw", r1, dw_, d1, *geo, rt, ctypes.byref(rs), ws, ws.numel())
+    assert torch.equal(d0, d1)
+    call("mnv_relu_backward_tw", actd, dyd, r1, N, Co, Ho, Wo, 0, 0)      # no twin: the plain op
+    assert torch.equal(r0, r1)

@@ -141,6 +141,121 @@ def test_conv_relu_fusion_is_bit_identical(gpu_owl):
         np.testing.assert_array_equal(a, b)
 
 
+def test_graph_step_is_bit_identical(gpu_owl):
+    """NetTrainer(graph=True): the step recorded into a CUDA graph and replayed leaves, step after step, the bits of the eager
+    trainer -- weights, loss and the dropout masks (whose keys the replay reads from a device word) -- also when the
+    caller swaps the input arrays and changes the learning rate (a new recording)."""
+    from tests.test_net_cpu import _tiny_net, _batch
+    from minerva_b200.owl.net.net import _default_backend
+    from minerva_b200.owl.net.trainer import NetTrainer
+    out = []
+    for graph in (False, True):
+        gpu_owl.set_seed(21)
+        net = _tiny_net(_default_backend())
+        net.batch_size = 8
+        du = net.get_data_unit()
+        tr = NetTrainer(net, None, graph=graph)
+        losses, masks = [], []
+        for it in range(7):
+            if it == 4:
+                net.current_lr = net.current_lr * 0.5
+            du.data, du.label = _batch(net.B, 8, seed=it % 3)         # a fresh input array every step
+            tr.step()
+            if graph:
+                dsum, n = tr.loss_device
+                losses.append(-float(dsum.to_numpy().reshape(-1)[0]) / n)
+            else:
+                losses.append(net.get_loss_units()[0].getloss())
+            masks.append([u for u in net.units if u.name == "drop6"][0].dropmask.to_numpy().copy())
+        if graph:
+            assert tr.graph_replays == 6 and tr.graph_launches_per_step > 20      # the first step ran eagerly (lazy initialisation)
+        out.append((losses, masks, [net.units[uid].weight.to_numpy() for uid in net.get_weighted_unit_ids()]
+                    + [net.units[uid].biasdelta.to_numpy() for uid in net.get_weighted_unit_ids()]))
+    (l0, m0, w0), (l1, m1, w1) = out
+    assert l0 == l1
+    for a, b in zip(m0 + w0, m1 + w1):
+        np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(m0[0], m0[1])          # the masks do change from step to step
+    # an eager draw after the replays continues the same stream as after the eager steps (host counter kept in step)
+
+
+def test_graph_step_with_feed(gpu_owl):
+    """The recorded step driven by a FeedDataUnit (uint8 upload + device transform): same weights as the eager loop."""
+    from tests.test_net_cpu import _tiny_net
+    from minerva_b200.owl.net.net import _default_backend
+    from minerva_b200.owl.net.trainer import NetTrainer
+    from minerva_b200.owl.net.data import HostFeed, FeedDataUnit
+    import minerva_b200.owl._runtime as rt
+    res = []
+    for graph in (False, True):
+        gpu_owl.set_seed(3)
+        net = _tiny_net(_default_backend())
+        net.batch_size = 8
+        rs = np.random.RandomState(1)
+        stored = rs.randint(0, 256, (8, 3, 17, 17), dtype=np.uint8)
+        onehot = np.zeros((8, 5), np.float32)
+        onehot[np.arange(8), rs.randint(0, 5, 8)] = 1
+        feed = HostFeed(gpu_owl, rt, data_u8=stored, scale=1.0 / 255.0, label=onehot)
+        old = net.units[0]
+        fu = FeedDataUnit(old.name, old.top_names, feed)
+        fu.B = old.B
+        net.units[0] = fu
+        tr = NetTrainer(net, None, graph=graph)
+        for _ in range(4):
+            tr.step()
+        fu.close()
+        res.append([net.units[uid].weight.to_numpy() for uid in net.get_weighted_unit_ids()])
+    for a, b in zip(*res):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_relu_backward_twin_is_bit_identical(gpu_owl):
+    """conv -> relu -> conv chains (AlexNet conv3..5, every GoogLeNet reduce -> 3x3 / 5x5 pair): the ReluUnit's backward leaves
+    the channels-last twin and channel sums of its result (mnv_relu_backward_tw) for the convolution below; gradients are
+    the bits of the graph without twins."""
+    from minerva_b200.owl.net.net import (_default_backend, Net, DataUnit, ConvConnection, ReluUnit, FullyConnection, SoftmaxUnit)
+    res = []
+    for twins in (True, False):
+        gpu_owl.set_seed(9)
+        net = Net(_default_backend())
+        net.add_unit(DataUnit("data", ["data", "label"]))
+        net.add_unit(ConvConnection("c1", "data", "c1", 64, 3, 1, 1, weight_std=0.1))
+        net.add_unit(ReluUnit("r1", "c1", "c1"))                      # in place, the Caffe convention
+        net.add_unit(ConvConnection("c2", "c1", "c2", 96, 3, 1, 1, weight_std=0.05, bias_value=0.1))
+        net.add_unit(ReluUnit("r2", "c2", "c2r"))
+        net.add_unit(ConvConnection("c3", "c2r", "c3", 48, 1, 1, 0, weight_std=0.05))
+        net.add_unit(ReluUnit("r3", "c3", "c3"))
+        net.add_unit(FullyConnection("fc", "c3", "fc", 5, weight_std=0.05))
+        net.add_unit(SoftmaxUnit("loss", "fc", "label", "prob"))
+        net.fuse_conv_twins = twins
+        rs = np.random.RandomState(0)
+        x = rs.normal(0, 1, (8, 32, 14, 14)).astype(np.float32)
+        onehot = np.zeros((8, 5), np.float32)
+        onehot[np.arange(8), rs.randint(0, 5, 8)] = 1
+        du = net.get_data_unit()
+        du.data, du.label = gpu_owl.from_numpy(x), gpu_owl.from_numpy(onehot)
+        net.batch_size = 8
+        net.forward("TRAIN")
+        made = []
+        orig = gpu_owl.NArray.relu_back_tw
+
+        def spy(diff, top, geo):
+            out = orig(diff, top, geo)
+            made.append(out._twin[1].value if out._twin is not None else 0)
+            return out
+        gpu_owl.NArray.relu_back_tw = staticmethod(spy)
+        try:
+            net.backward("TRAIN")
+        finally:
+            gpu_owl.NArray.relu_back_tw = staticmethod(orig)
+        assert (len(made) == 3) == twins
+        if twins:
+            assert 3 in made          # at least one convolution here takes a top_diff twin (and its sums)
+        res.append([g for uid in net.get_weighted_unit_ids() for g in (net.units[uid].weightgrad.to_numpy(), net.units[uid].biasgrad.to_numpy())])
+    for a, b in zip(*res):
+        np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("builder,shape,batch", [("build_lenet", [28, 28, 1], 16), ("build_mnist_mlp", [784], 16)])
 def test_small_configs_train(gpu_owl, builder, shape, batch):
     """configs[0..1] of BASELINE.json at reduced batch: loss goes down on a fixed synthetic batch."""
