@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the GoogLeNet / LeNet / MLP lines after the headline")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (NetTrainer(graph=True)); auto = on at 1 GPU")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B: plain stream-ordered launches (mnv_set_dependent_launch(0))")
     ap.add_argument("--merge", default="auto", choices=["auto", "peer", "nccl", "off"], help="N>1 gradient merge (owl/net/merge.py)")
     ap.add_argument("--nccl-ctas", type=int, default=0,
                     help="N>1: SMs left to NCCL (NCCL_MAX_CTAS) and kept out of the persistent tensor-core kernel's grid; 0 = do not manage")
@@ -634,6 +635,8 @@ def main():
     for kv in args.mnv_opt:
         k, v = kv.split("=")
         lib.mnv_debug_set_option(k.encode(), int(v))
+    if args.no_pdl:
+        lib.mnv_set_dependent_launch(0)
     C.owl, C.onet, C.rt, C.lib = owl, onet, rt, lib
     owl.set_device(owl.create_gpu_device(local))
 

@@ -54,6 +54,10 @@ size_t mnv_workspace_bytes_hint(void);
 /* number of kernels this library has launched in this process (all threads); bench.py reads
  * it before/after the timed region to report "gpu_launches". */
 uint64_t mnv_launch_count(void);
+/* Programmatic dependent launch (on by default): the library's kernels let their successor in the stream start its
+ * prologue while they drain, and wait for their predecessor's completion before their first global access -- the
+ * stream order of results is unchanged.  0 = plain launches (for A/B timing).  -> the previous setting. */
+int mnv_set_dependent_launch(int enabled);
 
 /* ---- a1 Arithmetic: c = a o b  (cuda_perform.h:12-14,16; cuda_perform.cu:32-64) ------------ */
 int mnv_add(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);

@@ -33,6 +33,29 @@ inline int stream_grid(size_t work_items, int per_block = kBlock) {
   return static_cast<int>(blocks);
 }
 
+// Programmatic dependent launch: a kernel started through launch_pdl() may begin (its CTAs take the SM resources the
+// previous kernel in the stream frees, run their prologue: barrier init, TMEM allocation, index math) before that kernel
+// has finished; it must call pdl_wait() before its first global-memory access -- the wait returns once the previous
+// grid has completed and its writes are visible, so the ordering the stream promises is unchanged.  pdl_enter() =
+// "let MY successor start early too" + the wait.  A ~2 us launch gap per kernel boundary goes away (a step is
+// 100..750 dependent launches), inside a recorded CUDA graph as well (programmatic edges).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
+extern std::atomic<int> g_pdl;     // 0: plain stream-ordered launches (mnv_set_dependent_launch)
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float warp_sum(float v) {

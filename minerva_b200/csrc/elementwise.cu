@@ -32,6 +32,7 @@
 namespace mnv {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_pdl{1};
 
 constexpr int kUnroll = 4;
 
@@ -567,5 +568,6 @@ const char* mnv_build_info(void) {
 }
 size_t mnv_workspace_bytes_hint(void) { return static_cast<size_t>(768) << 20; }
 uint64_t mnv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int mnv_set_dependent_launch(int enabled) { return g_pdl.exchange(enabled ? 1 : 0, std::memory_order_relaxed); }
 
 }  // extern "C"

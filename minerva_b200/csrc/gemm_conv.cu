@@ -91,11 +91,14 @@ struct GemmParams {
   int a_mode;           // A_TMA sub-mode (TMA_A_*), 0 otherwise
   int relu;             // 1: epilogue applies max(x, 0) after the bias (conv + ReLU units fused by owl.net)
   int b_mn;             // 1: B arrives as an MN-major tile (bn/32 boxes of 32 n x 32 k; MatMult with B^T), all-TMA path only
+                        // 2: the same tile as ONE box of a (32 n, k, n / 32) view of the matrix (make_mn3_tmap): the producer
+                        //    thread issues one copy per k-stage instead of bn / 32
   int cpt;              // 32-channel chunks per filter tap (TMA_A_IM2COL_K: k-stage = tap * cpt + chunk)
   int out_mode;         // 3: transposed convolution output: m = co, n = flat (image, pixel); bias is per m
                         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
                         // 2: the same over a space-to-depth view (below): virtual (tap, channel) -> real filter element
   int r_ci, r_fh, r_fw, r_sv, r_sh;   // out_mode 2: the real convolution's channels, filter and strides
+  int a_g3;             // 1 (TMA_A_TILED_MN): the tile's 4 (tall: 8) slabs arrive as one box of a make_mn3_tmap view
   int b_im2col;         // 1 (all-TMA path): B is the im2col operand -- bn output pixels x 32 channels of one tap per k-stage -- and A the
                         // packed filter (TMA_A_TILED_K): the TRANSPOSED orientation D[co][pixel] for narrow outputs (out_mode 3)
   int b_flip;           // B_FILTER_T: 1 = taps rotated by 180 degrees (stride-1 backward-data run as a forward convolution)
@@ -698,6 +701,7 @@ template <int AM, int BMD, bool BTMA, int RING>
 __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p,
                                                                 const __grid_constant__ CUtensorMap tmap_b,
                                                                 const __grid_constant__ CUtensorMap tmap_a) {
+  pdl_trigger();
   // WIDE: one 128 x bn tile (256 < bn <= 384) as two UMMA halves sharing the A tile, single TMEM accumulator,
   // 3-deep ring of 64 KB slots; otherwise bn <= 256, two accumulators, 4-deep ring of 48 KB slots.
   // RING 2 (both operands through TMA, bn <= 128): 6-deep ring of 32 KB slots -- a 128 x 96 tile consumes a stage
@@ -752,6 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       st_shared_u32(ktab0 + 4 * k, e);
     }
   }
+  pdl_wait();          // everything above touched only shared memory / TMEM / kernel parameters
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -922,6 +927,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
 #pragma unroll
                 for (int h = 0; h < kHalves; ++h) tma_prefetch_im2col_4d(&tmap_a, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
               } else if (p.a_mode == TMA_A_TILED_MN) {
+                if (p.a_g3) tma_prefetch_3d(&tmap_a, 0, kp * BK, (t.mt * kTileM) >> 5);
+                else
 #pragma unroll
                 for (int j = 0; j < kChunks; ++j) tma_prefetch_2d(&tmap_a, t.mt * kTileM + 32 * j, kp * BK);
               } else if (p.a_mode == TMA_A_TILED_K) {
@@ -948,6 +955,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
               for (int h = 0; h < kHalves; ++h)
                 tma_load_im2col_4d(a_dst + h * kABytes, &tmap_a, bar, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
             } else if (p.a_mode == TMA_A_TILED_MN) {
+              if (p.a_g3) tma_load_3d(a_dst, &tmap_a, bar, 0, ks * BK, (t.mt * kTileM) >> 5);
+              else
 #pragma unroll
               for (int j = 0; j < kChunks; ++j) tma_load_2d(a_dst + j * 4096, &tmap_a, bar, t.mt * kTileM + 32 * j, ks * BK);
             } else if (p.a_mode == TMA_A_TILED_K) {
@@ -973,6 +982,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             tma_load_im2col_4d(dst, &tmap_b, full0 + 8 * stage, cc * BK, (pix - oh * p.Wo) * p.sh - p.pw, oh * p.sv - p.ph, img, tap - kh * p.fw, kh);
           } else
           if (AM == A_TMA && p.b_mn) {   // MN-major B: one 32 n x 32 k box per 32 columns (bn % 32 == 0, never wide)
+            if (p.b_mn == 2) tma_load_3d(dst, &tmap_b, full0 + 8 * stage, 0, ks * BK, (t.nt * p.bn) >> 5);
+            else
             for (int j = 0; j < p.bn / 32; ++j) tma_load_2d(dst + j * 4096, &tmap_b, full0 + 8 * stage, t.nt * p.bn + 32 * j, ks * BK);
           } else
           for (int h = 0; h < halves; ++h) {
@@ -1220,6 +1231,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
 
 // split-K: out[index(m,n)] = bias[n] + sum_s partial[s][n][m], splits folded in order
 __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams p) {
+  pdl_enter();
   size_t mn = static_cast<size_t>(p.M) * p.N;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < mn;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1235,6 +1247,7 @@ __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams 
 
 // tail split: the same fold for the K-split tiles of the last wave only (tile ids >= tail_first in raster order)
 __global__ void __launch_bounds__(kBlock) splitk_tail_reduce_kernel(const GemmParams p) {
+  pdl_enter();
   const int tile_m = p.tall ? 2 * BM : BM, per_tile = tile_m * p.bn;
   const int ntail = p.m_tiles * p.n_tiles - p.tail_first;
   const size_t mn = static_cast<size_t>(p.M) * p.N, total = static_cast<size_t>(ntail) * per_tile;
@@ -1256,6 +1269,7 @@ __global__ void __launch_bounds__(kBlock) splitk_tail_reduce_kernel(const GemmPa
 // flip = 1 additionally rotates the taps by 180 degrees (r' = fh-1-r, s' = fw-1-s), which turns a
 // stride-1 backward-data into a forward convolution of top_diff with pad' = f-1-pad.
 __global__ void __launch_bounds__(kBlock) filter_swap_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci, int ff, int flip, int round) {
+  pdl_enter();
   size_t total = static_cast<size_t>(Co) * Ci * ff;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1314,6 +1328,7 @@ constexpr int kShSmemFixed = kShPlanes * kShPlaneBytes + kShStagingBytes + 1024 
 __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __grid_constant__ ShiftParams p,
                                                                         const __grid_constant__ CUtensorMap tmap_x,
                                                                         const __grid_constant__ CUtensorMap tmap_w) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
@@ -1334,6 +1349,7 @@ __global__ void __launch_bounds__(kShThreads, 1) conv_shift_fwd_kernel(const __g
     fence_barrier_init();
   }
   if (warp == kShMmaWarp) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1510,6 +1526,7 @@ MNV_OPT g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather 
 MNV_OPT g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
 MNV_OPT g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
 MNV_OPT g_opt_no_transposed{0};  // 1: narrow-output convolutions keep the D[pixel][co] orientation (tuning)
+MNV_OPT g_opt_no_mn3{0};        // 1: MN-major operands as one 2-D box per 32 rows instead of one 3-D box per k-stage (tuning)
 MNV_OPT g_opt_no_nhwc_wgrad{0}; // 1: backward-filter keeps the re-pitched NCHW top_diff (K-major B) instead of the channels-last one (tuning)
 MNV_OPT g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
 
@@ -1561,6 +1578,22 @@ static bool make_a_mn_tmap(CUtensorMap* tm, const float* a, int M, int K, int ld
   return r == CUDA_SUCCESS;
 }
 
+// The same matrix as a (32 m, K, m / 32) 3-D tensor: one box of `groups` slabs = the `groups` consecutive 32 m x 32 k MN-major
+// slabs of a k-stage, laid out in shared memory exactly as `groups` boxes of make_a_mn_tmap at 4 KB steps -- one TMA
+// instruction instead of `groups` (the single producer thread's issue rate bounds the MN-major kernels).  A slab's 32
+// columns are read without a bound on m, so the caller guarantees round32(M) <= ld (rows past M are never stored).
+static bool make_mn3_tmap(CUtensorMap* tm, const float* a, int M, int K, int ld, int groups) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn || groups < 1 || groups > 8 || (M + 31) / 32 * 32 > ld) return false;
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(K), static_cast<cuuint64_t>((M + 31) / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, BK, static_cast<cuuint32_t>(groups)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, tmap_dtype(), 3, const_cast<float*>(a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1608,6 +1641,7 @@ template <bool RELU>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cp, int HW,
                                                            int tiles_c, int tiles_hw, long long total_tiles, float* __restrict__ tilesum,
                                                            const float* __restrict__ act = nullptr, float* __restrict__ dx = nullptr) {
+  pdl_enter();
   // tile = 32 channels x 128 pixels: 16 independent 128-byte-per-warp loads per thread before the barrier.
   // tilesum != null: the pass also leaves the sum of every (image, pixel tile, channel) in tilesum[(n * tiles_hw + th) * C + c]
   // -- for a top_diff that is ConvBackwardBias's per-tile partial, folded over (n, th) by rowsum_fold_kernel in a fixed order.
@@ -1662,6 +1696,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 //   = w[n*sn + c*sc + (flip ? ff-1-tap : tap)], TF32-rounded.
 __global__ void __launch_bounds__(kBlock) filter_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int C, int ff,
                                                              int Kc, long long sn, long long sc, int flip, int round) {
+  pdl_enter();
   size_t total = static_cast<size_t>(rows) * ff * Kc;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1703,6 +1738,7 @@ static bool s2d_plan(S2D* v, int Ci, int H, int W, int Ho, int Wo, int ph, int p
 __host__ __device__ inline int s2d_pitch(const S2D& v) { return (v.Wv * v.sh + 3) / 4 * 4 + 4; }
 template <bool VEC4>
 __global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const S2D v, int Cp, int R, int groups) {
+  pdl_enter();
   extern __shared__ float4 rows4[];
   float* rows = reinterpret_cast<float*>(rows4);
   const int L = v.Wv * v.sh, pitch = s2d_pitch(v), SR = v.Ci * v.sv;
@@ -1754,6 +1790,7 @@ __global__ void __launch_bounds__(256) s2d_nhwc_kernel(const float* __restrict__
 __global__ void __launch_bounds__(kBlock) s2d_filter_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, const S2D v,
                                                                  int cpt, int shift, int nk_last, int Kp, long long sn, long long sc, int flip,
                                                                  int round) {
+  pdl_enter();
   const int ffv = v.fhv * v.fwv, ff = v.fh * v.fw;
   size_t total = static_cast<size_t>(rows) * Kp;
   for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
@@ -1793,8 +1830,8 @@ static int launch_s2d(const float* x, float* y, int N, const S2D& v, int Cp, cud
   R = R > 4 ? 4 : R < 1 ? 1 : R;
   const int groups = (v.Hv + R - 1) / R;
   const unsigned grid = static_cast<unsigned>(N) * groups;
-  if (v.sh == 4 && v.Civ % 4 == 0 && aligned16(y)) s2d_nhwc_kernel<true><<<grid, 256, R * row_bytes, s>>>(x, y, v, Cp, R, groups);
-  else s2d_nhwc_kernel<false><<<grid, 256, R * row_bytes, s>>>(x, y, v, Cp, R, groups);
+  if (v.sh == 4 && v.Civ % 4 == 0 && aligned16(y)) launch_pdl((s2d_nhwc_kernel<true>), dim3(grid), dim3(256), R * row_bytes, s, x, y, v, Cp, R, groups);
+  else launch_pdl((s2d_nhwc_kernel<false>), dim3(grid), dim3(256), R * row_bytes, s, x, y, v, Cp, R, groups);
   return finish_launch();
 }
 
@@ -1819,6 +1856,7 @@ static bool make_dy_tmap(CUtensorMap* tm, const float* dy, int P, int pitch, int
 // element its own kernel would re-read are already in registers here).
 __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int inner, int pitch, size_t rows, int round,
                                                          float* __restrict__ rowsum) {
+  pdl_enter();
   // one warp per row keeps both sides coalesced without integer division
   size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
@@ -1840,6 +1878,7 @@ __global__ void __launch_bounds__(kBlock) repitch_kernel(const float* __restrict
 // 32 threads per channel take every 32nd row (independent loads, 128 B per warp), then the 32 partial sums are added in lane
 // order -- a fixed order, so the result is deterministic.
 __global__ void __launch_bounds__(1024) rowsum_fold_kernel(const float* __restrict__ rowsum, float* __restrict__ db, int N, int C) {
+  pdl_enter();
   // 32 channels x 32 row lanes per CTA; every lane keeps 4 independent loads in flight (the first version, 8 row lanes with
   // one CTA per 32 channels, was latency-bound: 16 us per call for 1536 rows)
   __shared__ float part[32][33];
@@ -1984,7 +2023,7 @@ static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_
   const long long total = q.total_units;
   const int sms = sm_budget();
   int grid = static_cast<int>(total < sms ? total : sms);
-  umma_gemm_kernel<AM, BMD, BTMA, RING><<<grid, kThreads, kSmemBytes, s>>>(q, tm, tm_a);
+  launch_pdl((umma_gemm_kernel<AM, BMD, BTMA, RING>), dim3(grid), dim3(kThreads), kSmemBytes, s, q, tm, tm_a);
   return finish_launch();
 }
 template <int AM, int BMD, bool BTMA>
@@ -2002,11 +2041,11 @@ static int launch_umma_tma(const GemmParams& p, const CUtensorMap& tm_a, const C
   if (rc) return rc;
   if (p.splits == 1 && p.tail_splits > 1 && p.partial) {
     const size_t items = static_cast<size_t>(p.m_tiles * p.n_tiles - p.tail_first) * (p.tall ? 2 * BM : BM) * p.bn;
-    splitk_tail_reduce_kernel<<<stream_grid(items), kBlock, 0, s>>>(p);
+    launch_pdl(splitk_tail_reduce_kernel, dim3(stream_grid(items)), dim3(kBlock), 0, s, p);
     return finish_launch();
   }
   if (p.splits == 1) return rc;
-  splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
+  launch_pdl(splitk_reduce_kernel, dim3(stream_grid(static_cast<size_t>(p.M) * p.N)), dim3(kBlock), 0, s, p);
   return finish_launch();
 }
 
@@ -2027,7 +2066,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
     size_t need = (static_cast<size_t>(p.N) * pitch * sizeof(float) + 255) / 256 * 256;
     if (ws_bytes >= need) {
       float* packed = static_cast<float*>(ws);
-      repitch_kernel<<<stream_grid(static_cast<size_t>(p.N) * 32), kBlock, 0, s>>>(p.b, packed, p.K, pitch, static_cast<size_t>(p.N), prepass_round(), nullptr);
+      launch_pdl(repitch_kernel, dim3(stream_grid(static_cast<size_t>(p.N) * 32)), dim3(kBlock), 0, s, p.b, packed, p.K, pitch, static_cast<size_t>(p.N), prepass_round(), nullptr);
       int rc0 = finish_launch();
       if (rc0) return rc0;
       p.b = packed; p.ldb = pitch; p.b_vec = 1;
@@ -2057,6 +2096,10 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   if (tma_a_ok && tma) {
     CUtensorMap tm_a;
     memset(&tm_a, 0, sizeof(tm_a));
+    if (!g_opt_no_mn3.load() && make_mn3_tmap(&tm_a, p.a, p.M, p.K, p.lda, p.tall ? 8 : 4)) {
+      p.a_mode = TMA_A_TILED_MN; p.a_g3 = 1;
+      return launch_umma_tma(p, tm_a, tm, s);
+    }
     if (make_a_mn_tmap(&tm_a, p.a, p.M, p.K, p.lda)) {
       p.a_mode = TMA_A_TILED_MN;
       return launch_umma_tma(p, tm_a, tm, s);
@@ -2074,14 +2117,14 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   } else if (BMD == B_KMAJOR && tma) rc = launch_umma<AM, B_KMAJOR, true>(p, tm, s);
   else rc = launch_umma<AM, BMD, false>(p, tm, s);
   if (rc || p.splits == 1) return rc;
-  splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
+  launch_pdl(splitk_reduce_kernel, dim3(stream_grid(static_cast<size_t>(p.M) * p.N)), dim3(kBlock), 0, s, p);
   return finish_launch();
 }
 
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.b_im2col = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.b_im2col = 0; p.a_g3 = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -2099,7 +2142,7 @@ static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, c
   const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
   const long long total = static_cast<long long>(N) * tiles_c * tiles_hw;
   const long long cap = static_cast<long long>(kNumSMs) * 16;
-  nchw_to_nhwc_kernel<false><<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, s>>>(x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum);
+  launch_pdl((nchw_to_nhwc_kernel<false>), dim3(static_cast<unsigned>(total < cap ? total : cap)), dim3(256), 0, s, x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum, nullptr, nullptr);
   return finish_launch();
 }
 
@@ -2193,8 +2236,8 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
     if (!rc && use_twin) *twin.state = 1;
   }
   if (rc) return rc;
-  if (s2d) s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, *s2d, cpt, 0, 4, static_cast<int>(K), w_sn, w_sc, flip, prepass_round());
-  else filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
+  if (s2d) launch_pdl(s2d_filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, *s2d, cpt, 0, 4, static_cast<int>(K), w_sn, w_sc, flip, prepass_round());
+  else launch_pdl(filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
   rc = finish_launch();
   if (rc) return rc;
   *done = true;
@@ -2243,12 +2286,12 @@ static int conv_shift_fprop(const float* x, const float* w, long long w_sn, long
   }
   int rc = launch_s2d(x, xv, N, v, Cp, s);
   if (rc) return rc;
-  s2d_filter_pack_kernel<<<stream_grid(static_cast<size_t>(Co) * K), kBlock, 0, s>>>(w, wb, Co, v, cpt, 1, nk_last, K, w_sn, w_sc, flip, prepass_round());
+  launch_pdl(s2d_filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, v, cpt, 1, nk_last, K, w_sn, w_sc, flip, prepass_round());
   rc = finish_launch();
   if (rc) return rc;
   *done = true;
   const int sms = sm_budget();
-  conv_shift_fwd_kernel<<<p.m_tiles < sms ? p.m_tiles : sms, kShThreads, smem_bytes, s>>>(p, tm_x, tm_w);
+  launch_pdl(conv_shift_fwd_kernel, dim3(p.m_tiles < sms ? p.m_tiles : sms), dim3(kShThreads), smem_bytes, s, p, tm_x, tm_w);
   return finish_launch();
 }
 
@@ -2287,6 +2330,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "tall_min_stages") return g_opt_tall_min_stages.exchange(value);
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   if (k == "no_nhwc_wgrad") return g_opt_no_nhwc_wgrad.exchange(value);
+  if (k == "no_mn3") return g_opt_no_mn3.exchange(value);
   if (k == "no_transposed") return g_opt_no_transposed.exchange(value);
   return -1;
 }
@@ -2363,8 +2407,14 @@ int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k
   CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
-  const bool ok_a = trans_a ? make_b_tmap(&tm_a, a, m, k, k, BM) : make_a_mn_tmap(&tm_a, a, m, k, m);
-  const bool ok_b = trans_b ? make_a_mn_tmap(&tm_b, b, n, k, n) : make_b_tmap(&tm_b, b, n, k, k, p.wide ? p.bn / 2 : p.bn);
+  bool ok_a, ok_b;
+  const bool mn3 = !g_opt_no_mn3.load();
+  if (trans_a) ok_a = make_b_tmap(&tm_a, a, m, k, k, BM);
+  else if (mn3 && make_mn3_tmap(&tm_a, a, m, k, m, p.tall ? 8 : 4)) { ok_a = true; p.a_g3 = 1; }
+  else ok_a = make_a_mn_tmap(&tm_a, a, m, k, m);
+  if (!trans_b) ok_b = make_b_tmap(&tm_b, b, n, k, k, p.wide ? p.bn / 2 : p.bn);
+  else if (mn3 && make_mn3_tmap(&tm_b, b, n, k, n, p.bn / 32)) { ok_b = true; p.b_mn = 2; }
+  else ok_b = make_a_mn_tmap(&tm_b, b, n, k, n);
   if (!ok_a || !ok_b) return MNV_EINVAL;
   return launch_umma_tma(p, tm_a, tm_b, s);
 }
@@ -2414,7 +2464,7 @@ int mnv_relu_backward_tw(const float* top, const float* top_diff, float* bottom_
   const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
   const long long total = static_cast<long long>(N) * tiles_c * tiles_hw, cap = static_cast<long long>(kNumSMs) * 16;
   float* tilesum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(twin) + twin_copy_bytes(N, C, HW));
-  nchw_to_nhwc_kernel<true><<<static_cast<unsigned>(total < cap ? total : cap), 256, 0, as_stream(stream)>>>(
+  launch_pdl((nchw_to_nhwc_kernel<true>), dim3(static_cast<unsigned>(total < cap ? total : cap)), dim3(256), 0, as_stream(stream), 
       top_diff, twin, C, Cp, HW, tiles_c, tiles_hw, total, tilesum, top, bottom_diff);
   int rc = finish_launch();
   if (!rc) *twin_state = 3;     // copy + per-tile channel sums
@@ -2522,7 +2572,7 @@ static int conv_backward_data_impl(const float* top_diff, const float* filter, f
                         fh - 1 - ph, fw - 1 - pw, 1, 1, fh, fw, workspace, workspace_bytes, as_stream(stream), &done, nullptr, twin);
     if (rc || done) return rc;
   }
-  filter_swap_kernel<<<stream_grid(static_cast<size_t>(Co) * Ci * fh * fw), kBlock, 0, as_stream(stream)>>>(
+  launch_pdl(filter_swap_kernel, dim3(stream_grid(static_cast<size_t>(Co) * Ci * fh * fw)), dim3(kBlock), 0, as_stream(stream), 
       filter, wt, Co, Ci, fh * fw, as_forward ? 1 : 0, prepass_round());
   rc = finish_launch();
   if (rc) return rc;
@@ -2647,7 +2697,10 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
         CUtensorMap tm_a, tm_b;
         memset(&tm_a, 0, sizeof(tm_a));
         memset(&tm_b, 0, sizeof(tm_b));
-        if (make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true) && make_a_mn_tmap(&tm_b, dyh, Co, q.K, Cop)) {
+        bool ok_b = !g_opt_no_mn3.load() && make_mn3_tmap(&tm_b, dyh, Co, q.K, Cop, q.bn / 32);
+        if (ok_b) q.b_mn = 2;
+        else ok_b = make_a_mn_tmap(&tm_b, dyh, Co, q.K, Cop);
+        if (ok_b && make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true)) {
           if (!xtw.valid()) {
             rc = launch_nhwc(bottom, xh, N, Ci, Cp, H * W, s);
             if (rc) return rc;
@@ -2658,7 +2711,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
             if (rc) return rc;
             if (dtw.usable()) *dtw.state = 1;
             if (tilesum) {   // ConvBackwardBias rides on the pass: per-(image, pixel tile, channel) sums, folded in a fixed order
-              rowsum_fold_kernel<<<(Co + 31) / 32, 1024, 0, s>>>(tilesum, bias_diff, N * tiles_hw, Co);
+              launch_pdl(rowsum_fold_kernel, dim3((Co + 31) / 32), dim3(1024), 0, s, tilesum, bias_diff, N * tiles_hw, Co);
               rc = finish_launch();
               if (rc) return rc;
               *bias_done = true;
@@ -2666,7 +2719,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
           }
           if (bias_diff && !*bias_done && dtw.has_sums()) {   // the twin's filler (mnv_relu_backward_tw) left the per-tile sums
             const float* sums = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(dtw.ptr) + twin_copy_bytes(N, Co, P));
-            rowsum_fold_kernel<<<(Co + 31) / 32, 1024, 0, s>>>(sums, bias_diff, N * tiles_hw, Co);
+            launch_pdl(rowsum_fold_kernel, dim3((Co + 31) / 32), dim3(1024), 0, s, sums, bias_diff, N * tiles_hw, Co);
             rc = finish_launch();
             if (rc) return rc;
             *bias_done = true;
@@ -2693,11 +2746,11 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
     float* rowsum = nullptr;
     const size_t rs_bytes = round256(rows * sizeof(float));
     if (bias_diff && ws_left >= rs_bytes) { rowsum = reinterpret_cast<float*>(ws); ws += rs_bytes; ws_left -= rs_bytes; }
-    repitch_kernel<<<stream_grid(rows * 32), kBlock, 0, s>>>(top_diff, packed, P, pitch, rows, prepass_round(), rowsum);
+    launch_pdl(repitch_kernel, dim3(stream_grid(rows * 32)), dim3(kBlock), 0, s, top_diff, packed, P, pitch, rows, prepass_round(), rowsum);
     rc = finish_launch();
     if (rc) return rc;
     if (rowsum) {
-      rowsum_fold_kernel<<<(Co + 31) / 32, 1024, 0, s>>>(rowsum, bias_diff, N, Co);
+      launch_pdl(rowsum_fold_kernel, dim3((Co + 31) / 32), dim3(1024), 0, s, rowsum, bias_diff, N, Co);
       rc = finish_launch();
       if (rc) return rc;
       *bias_done = true;
@@ -2767,7 +2820,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
   if ((sv > 1 || sh > 1) && !g_opt_no_klane.load() && !p.wide) rc = launch_umma<A_IM2COL_WGRAD_M, B_KMAJOR, true>(p, tm, s);
   else rc = launch_umma<A_IM2COL_WGRAD, B_KMAJOR, true>(p, tm, s);
   if (rc || p.splits == 1) return rc;
-  splitk_reduce_kernel<<<stream_grid(static_cast<size_t>(p.M) * p.N), kBlock, 0, s>>>(p);
+  launch_pdl(splitk_reduce_kernel, dim3(stream_grid(static_cast<size_t>(p.M) * p.N)), dim3(kBlock), 0, s, p);
   return finish_launch();
 }
 

@@ -161,6 +161,8 @@ class NetTrainer(object):
         lib = _lib.load()
         n0 = lib.mnv_launch_count()
         rt.capture_seeds = seeds
+        # graph nodes already follow each other without a launch gap; programmatic edges measured 1 % slower than plain ones
+        pdl = lib.mnv_set_dependent_launch(0)
         try:
             with torch.cuda.graph(graph, stream=dev.stream):
                 self._eager_step()
@@ -168,6 +170,7 @@ class NetTrainer(object):
                 loss = lu[-1].getloss_device() if lu and hasattr(lu[-1], "getloss_device") else None
         finally:
             rt.capture_seeds = None
+            lib.mnv_set_dependent_launch(pdl)
             if feed is not None:
                 du.feed = feed
         rt.set_device(rt._devices.index(dev))      # torch.cuda.graph restores ITS entry stream; make the device's current again
