@@ -98,6 +98,7 @@ struct GemmParams {
                         // 1: backward-filter through TMA: m = (tap * cpt + chunk) * 32 + channel-in-chunk
                         // 2: the same over a space-to-depth view (below): virtual (tap, channel) -> real filter element
   int r_ci, r_fh, r_fw, r_sv, r_sh;   // out_mode 2: the real convolution's channels, filter and strides
+  int pair_remote;      // CTA pair, tuning: 1 = the peer's copies count their bytes on the leader's barrier (cta_group::2 copy forms)
   int a_g3;             // 1 (TMA_A_TILED_MN): the tile's 4 (tall: 8) slabs arrive as one box of a make_mn3_tmap view
   int b_im2col;         // 1 (all-TMA path): B is the im2col operand -- bn output pixels x 32 channels of one tap per k-stage -- and A the
                         // packed filter (TMA_A_TILED_K): the TRANSPOSED orientation D[co][pixel] for narrow outputs (out_mode 3)
@@ -162,6 +163,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
     else if (now - t0 > 4000000000ull) asm volatile("trap;");  // 4 s: a protocol bug traps instead of hanging
   }
 }
+// the same wait with cluster-scope acquire: the phase is completed by an arrive from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, uint32_t hint = 0x989680u) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(hint)
+        : "memory");
+    if (done) return;
+    uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) asm volatile("trap;");
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -175,6 +194,54 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC run ONE UMMA of 256 rows -- each holds its 128 rows of A and
+// HALF of the B tile in its own shared memory and its 128 x N accumulator rows in its own TMEM; the leader (cluster rank 0)
+// issues the instruction for both.  Per SM and flop the B bytes halve (the bound of the 128-row kernel), the ring stays
+// 6 stages deep and both accumulator buffers remain, unlike the 256-row single-CTA tile.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the address, in the cluster's shared window, of the same shared-memory offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Fire-and-forget form: a release at cluster scope holds the thread for ~700 cycles per arrive.  Used where what the
+// arrive publishes is already complete in hardware terms: bytes a TMA copy has landed in shared memory (observed through
+// the local barrier) or TMEM loads retired by tcgen05.wait::ld.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -242,9 +309,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2,
 // B=TF32 [10,13)=2, both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major = false, bool b_mn_major = false) {
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn_major = false, bool b_mn_major = false, int m = BM) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major ? 1u << 15 : 0u) | (b_mn_major ? 1u << 16 : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(BM >> 4) << 24);
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 // MN-major tf32 operand.  32-bit MN-major operands exist in one shared-memory layout only, SWIZZLE_128B_BASE32B
 // (32-byte chunks swizzled inside the 128 B span by row & 3; TMA writes it as CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
@@ -634,6 +701,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// CTA-pair forms: the copy lands in the executing CTA's shared memory, its bytes are counted on the LEADER's barrier
+// (`bar` = that barrier's address in the cluster window, mapa_u32(bar, 0)).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c, int w, int h,
+                                                       int n, int kw, int kh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(static_cast<uint16_t>(kw)), "h"(static_cast<uint16_t>(kh))
+      : "memory");
+}
+
 // L2 prefetch of a box a few k-stages ahead: the smem ring covers ~1.5 us of TMA latency, less than an HBM round trip
 // under load, so operands that stream from HBM (FC weights, channels-last activation copies) are pulled into L2 early.
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int c0, int c1) {
@@ -709,11 +799,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   // RING 3 (both operands through TMA): a 256 x bn tile as two UMMA halves of 128 rows sharing the B tile, one
   // accumulator per half (all 512 TMEM columns), 3-deep ring of 64 KB slots.  The kernel is bound by L2 -> SM
   // operand traffic (48 KB per 128x256x32 stage = 44 flop/B); the tall tile moves 64 KB for twice the math.
-  constexpr bool WIDE = RING == 1, DEEP = RING == 2, TALL = RING == 3;
-  constexpr int kTileM = TALL ? 2 * BM : BM;
+  // RING 4 (both operands through TMA): the CTA PAIR -- a 256 x bn tile computed by two CTAs of a cluster with
+  // tcgen05.mma.cta_group::2: this CTA stages its 128 rows of A and bn / 2 rows of B (32 KB per stage, 6-deep ring) and
+  // drains its own 128 accumulator rows; rank 0 issues the MMAs for both and owns the full / tmem_empty barriers.
+  constexpr bool WIDE = RING == 1, DEEP = RING == 2, TALL = RING == 3, PAIR = RING == 4;
+  static_assert(!PAIR || AM == A_TMA, "the CTA pair exists on the all-TMA path only");
+  constexpr int kTileM = (TALL || PAIR) ? 2 * BM : BM;
   constexpr int kATile = TALL ? 2 * kABytes : kABytes;
-  constexpr int kNStages = (WIDE || TALL) ? 3 : DEEP ? 6 : kStages;
-  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : DEEP ? kABytes + 128 * BK * 4 : TALL ? 2 * kABytes + kBBytes : kStageBytes;
+  constexpr int kNStages = (WIDE || TALL) ? 3 : (DEEP || PAIR) ? 6 : kStages;
+  constexpr int kSBytes = WIDE ? kABytes + 384 * BK * 4 : (DEEP || PAIR) ? kABytes + 128 * BK * 4 : TALL ? 2 * kABytes + kBBytes : kStageBytes;
   constexpr int kNAcc = (WIDE || TALL) ? 1 : 2;
   constexpr int kMaxStages = 6;
   // With both operands on TMA the 16 gather warps have no mainloop work: they join the epilogue, five warps per
@@ -728,20 +822,29 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t tfull0 = smem_u32(bars + 2 * kMaxStages), tempty0 = smem_u32(bars + 2 * kMaxStages + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  const uint32_t pfull0 = smem_u32(bars + 2 * kMaxStages + 6);   // CTA pair, leader: "the peer's half of stage s has landed"
   const uint32_t ktab0 = smem_u32(smem + kStages * kStageBytes + 256);   // uint32 ktab[kKtabMax]
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.total_units;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                 // 0: the pair's leader
+  // (expressions, not variables: the single-CTA instantiations keep reading blockIdx / gridDim / p.bn in place)
+#define tile_first (PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x))
+#define tile_step (PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x))
+#define bn_cta (PAIR ? p.bn >> 1 : p.bn)                               /* B rows staged by this CTA */
+  const int m_rank = PAIR ? static_cast<int>(rank) * BM : 0;           // this CTA's rows inside the pair's tile
+  const int n_rank = PAIR ? static_cast<int>(rank) * bn_cta : 0;
 
   if (threadIdx.x == 0) {
     // full: TMA-fed B: the 4 warps of the slot's producer group + the TMA thread's arrive.expect_tx;
     //       gathered B: all 16 producer warps
     for (int s = 0; s < kNStages; ++s) { mbar_init(full0 + 8 * s, AM == A_TMA ? 1 : BTMA ? 4 + 1 : kProducerThreads / 32); mbar_init(empty0 + 8 * s, 1); }   // kNStages of them are used
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, PAIR ? 2 * kEpiWarps : kEpiWarps); }
+    if (PAIR) for (int s = 0; s < kNStages; ++s) mbar_init(pfull0 + 8 * s, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 4) { if (PAIR) tmem_alloc_2sm(smem_u32(tmem_slot), kTmemCols); else tmem_alloc(smem_u32(tmem_slot), kTmemCols); }
   if ((AM == A_IM2COL_FWD || AM == A_IM2COL_FWD_K) && p.use_ktab) {
     const int ff = p.fh * p.fw, HW = p.H * p.W;
     for (int k = threadIdx.x; k < p.k_stages * BK; k += blockDim.x) {
@@ -758,14 +861,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   }
   pdl_wait();          // everything above touched only shared memory / TMEM / kernel parameters
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   // ===================== epilogue (run by warps 0-3, and by the idle producer warps on the all-TMA path) ==========
   auto epilogue = [&](const int quarter, const int slot) {
     int acc_stage = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       TileCoord t = decode_tile(p, tile);
       mbar_wait(tfull0 + 8 * acc_stage, acc_phase, p.wait_hint);
       tc_fence_after();
@@ -774,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       const bool relu = p.relu != 0 && !t.partial;
 #pragma unroll
       for (int half = 0; half < (TALL ? 2 : 1); ++half) {
-        const int m = t.mt * kTileM + half * BM + quarter * 32 + lane;
+        const int m = t.mt * kTileM + m_rank + half * BM + quarter * 32 + lane;
         const bool row_ok = out_row_ok(p, m);
         float* dst;
         long long cstride;
@@ -841,7 +944,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc_stage);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster_relaxed(mapa_u32(tempty0 + 8 * acc_stage, 0));    // the leader's MMA thread waits for both CTAs' drains
+        else mbar_arrive(tempty0 + 8 * acc_stage);
+      }
       if (++acc_stage == kNAcc) { acc_stage = 0; acc_phase ^= 1; }
     }
   };
@@ -854,16 +960,17 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     const int bnh = WIDE ? p.bn / 2 : p.bn;           // columns per UMMA instruction
     const bool a_mn = AM == A_TMA && (p.a_mode == TMA_A_TILED_MN || p.a_mode == TMA_A_IM2COL_MN);
     const bool b_mn = AM == A_TMA && p.b_mn != 0;
-    const uint32_t idesc = make_idesc(bnh, a_mn, b_mn);
+    const uint32_t idesc = make_idesc(bnh, a_mn, b_mn, PAIR ? 2 * BM : BM);
     int stage = 0; uint32_t phase = 0;
     int acc_stage = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; (!PAIR || rank == 0) && tile < total_tiles; tile += tile_step) {
       TileCoord t = decode_tile(p, tile);
       mbar_wait(tempty0 + 8 * acc_stage, acc_phase ^ 1, p.wait_hint);  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc_stage * BN_MAX);
       for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
         mbar_wait(full0 + 8 * stage, phase, p.wait_hint);
+        if (PAIR && !p.pair_remote) mbar_wait_cluster(pfull0 + 8 * stage, phase, p.wait_hint);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_base + stage * kSBytes;
@@ -873,28 +980,56 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             const uint32_t acc = (ks > t.ks_begin || kk > 0) ? 1u : 0u;
             const uint64_t adesc = a_mn ? make_sw128_desc_mn(a_addr + kk * 1024) : make_sw128_desc(a_addr + kk * 32);
             const uint64_t bdesc = b_mn ? make_sw128_desc_mn(b_addr + kk * 1024) : make_sw128_desc(b_addr + kk * 32);
-            umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
+            if (PAIR) umma_tf32_2sm(tmem_d, adesc, bdesc, idesc, acc);
+            else umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
             if (WIDE)   // second half of the columns: same A tile, B rows bnh.., TMEM columns bnh..
               umma_tf32(tmem_d + bnh, adesc, make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
             if (TALL)   // rows 128..255: second A half, same B tile, second accumulator
               umma_tf32(tmem_d + BN_MAX, a_mn ? make_sw128_desc_mn(a_addr + kABytes + kk * 1024) : make_sw128_desc(a_addr + kABytes + kk * 32),
                         bdesc, idesc, acc);
           }
+          if (PAIR) {
+            umma_commit_2sm(empty0 + 8 * stage);                              // both CTAs' slots, both CTAs' accumulators
+            if (ks + 1 == t.ks_end) umma_commit_2sm(tfull0 + 8 * acc_stage);
+          } else {
           umma_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs have read it
           if (ks + 1 == t.ks_end) umma_commit(tfull0 + 8 * acc_stage);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == kNStages) { stage = 0; phase ^= 1; }
       }
       if (++acc_stage == kNAcc) { acc_stage = 0; acc_phase ^= 1; }
     }
+    if (PAIR && rank != 0 && lane == 0 && !p.pair_remote) {
+      // The peer's half of the pipeline hand-over: every copy counts its bytes on the barrier of the CTA it lands in
+      // (copies that signal a barrier in the other CTA measured ~4x the per-copy cost); this thread forwards "stage
+      // landed" to the leader, whose MMA thread waits for both halves.
+      const uint32_t pfull_ld0 = mapa_u32(pfull0, 0);
+      int st = 0; uint32_t ph = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        TileCoord t = decode_tile(p, tile);
+        for (int ks = t.ks_begin; ks < t.ks_end; ++ks) {
+          mbar_wait(full0 + 8 * st, ph, p.wait_hint);
+          mbar_arrive_cluster_relaxed(pfull_ld0 + 8 * st);
+          if (++st == kNStages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 5) {
     // ===================== TMA producer for B =====================
     if (BTMA && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       // the whole box(es), OOB rows/cols arrive as zeros
-      const uint32_t bytes = static_cast<uint32_t>(p.bn) * BK * 4 + (AM == A_TMA ? kATile : 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t bytes = static_cast<uint32_t>(bn_cta) * BK * 4 + (AM == A_TMA ? kATile : 0);
+      // CTA pair: where this CTA's copies count their bytes -- the leader's barrier (cta_group::2 copy forms) or its own
+      const bool remote_bar = PAIR && p.pair_remote;
+      const uint32_t full_ld0 = remote_bar ? mapa_u32(full0, 0) : full0;
+#define MNV_LD2(...) do { if constexpr (PAIR) { if (remote_bar) tma_load_2d_2sm(__VA_ARGS__); else tma_load_2d(__VA_ARGS__); } else tma_load_2d(__VA_ARGS__); } while (0)
+#define MNV_LD3(...) do { if constexpr (PAIR) { if (remote_bar) tma_load_3d_2sm(__VA_ARGS__); else tma_load_3d(__VA_ARGS__); } else tma_load_3d(__VA_ARGS__); } while (0)
+#define MNV_LDI(...) do { if constexpr (PAIR) { if (remote_bar) tma_load_im2col_4d_2sm(__VA_ARGS__); else tma_load_im2col_4d(__VA_ARGS__); } else tma_load_im2col_4d(__VA_ARGS__); } while (0)
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         TileCoord t = decode_tile(p, tile);
         // A_TMA: position of the tile's first row
         constexpr int kHalves = TALL ? 2 : 1, kChunks = 4 * kHalves;
@@ -904,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           if (p.a_mode == TMA_A_IM2COL_K) {
 #pragma unroll
             for (int h = 0; h < kHalves; ++h) {   // rows past M land in image >= N: zero-filled
-              const int m0 = t.mt * kTileM + h * BM;
+              const int m0 = t.mt * kTileM + m_rank + h * BM;
               a_n[h] = m0 / p.P;
               const int pix = m0 - a_n[h] * p.P, oh = pix / p.Wo;
               a_h[h] = oh * p.sv - p.ph; a_w[h] = (pix - oh * p.Wo) * p.sh - p.pw;
@@ -913,7 +1048,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             const int last = p.fh * p.fw * p.cpt - 1;   // rows past M still receive a (masked) box
 #pragma unroll
             for (int j = 0; j < kChunks; ++j) {
-              const int chunk = min(t.mt * kChunks + j, last), tap = chunk / p.cpt;
+              const int chunk = min(t.mt * (PAIR ? 2 * kChunks : kChunks) + (m_rank >> 5) + j, last), tap = chunk / p.cpt;
               a_c[j] = (chunk - tap * p.cpt) * 32; a_kh[j] = tap / p.fw; a_kw[j] = tap - a_kh[j] * p.fw;
             }
           }
@@ -927,41 +1062,43 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
 #pragma unroll
                 for (int h = 0; h < kHalves; ++h) tma_prefetch_im2col_4d(&tmap_a, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
               } else if (p.a_mode == TMA_A_TILED_MN) {
-                if (p.a_g3) tma_prefetch_3d(&tmap_a, 0, kp * BK, (t.mt * kTileM) >> 5);
+                if (p.a_g3) tma_prefetch_3d(&tmap_a, 0, kp * BK, (t.mt * kTileM + m_rank) >> 5);
                 else
 #pragma unroll
-                for (int j = 0; j < kChunks; ++j) tma_prefetch_2d(&tmap_a, t.mt * kTileM + 32 * j, kp * BK);
+                for (int j = 0; j < kChunks; ++j) tma_prefetch_2d(&tmap_a, t.mt * kTileM + m_rank + 32 * j, kp * BK);
               } else if (p.a_mode == TMA_A_TILED_K) {
 #pragma unroll
-                for (int h = 0; h < kHalves; ++h) tma_prefetch_2d(&tmap_a, kp * BK, t.mt * kTileM + h * BM);
+                for (int h = 0; h < kHalves; ++h) tma_prefetch_2d(&tmap_a, kp * BK, t.mt * kTileM + m_rank + h * BM);
               }
             }
             if (!(AM == A_TMA && (p.b_mn || p.b_im2col))) {
               const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;
               for (int h = 0; h < halves; ++h) {
-                const int n0 = t.nt * p.bn + h * rows;
+                const int n0 = t.nt * p.bn + n_rank + h * rows;
                 if (p.spi > 0) { const int img = kp / p.spi; tma_prefetch_3d(&tmap_b, (kp - img * p.spi) * BK, n0, img); }
                 else tma_prefetch_2d(&tmap_b, kp * BK, n0);
               }
             }
           }
           mbar_wait(empty0 + 8 * stage, phase ^ 1, p.wait_hint);
-          mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
+          if (!remote_bar) mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
+          else if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * bytes);      // both CTAs' copies land on the leader's barrier
+          const uint32_t fbar = full_ld0 + 8 * stage;
           if (AM == A_TMA) {
-            const uint32_t a_dst = smem_base + stage * kSBytes, bar = full0 + 8 * stage;
+            const uint32_t a_dst = smem_base + stage * kSBytes, bar = fbar;
             if (p.a_mode == TMA_A_IM2COL_K) {
               const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
 #pragma unroll
               for (int h = 0; h < kHalves; ++h)
-                tma_load_im2col_4d(a_dst + h * kABytes, &tmap_a, bar, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
+                MNV_LDI(a_dst + h * kABytes, &tmap_a, bar, cc * BK, a_w[h], a_h[h], a_n[h], tap - kh * p.fw, kh);
             } else if (p.a_mode == TMA_A_TILED_MN) {
-              if (p.a_g3) tma_load_3d(a_dst, &tmap_a, bar, 0, ks * BK, (t.mt * kTileM) >> 5);
+              if (p.a_g3) MNV_LD3(a_dst, &tmap_a, bar, 0, ks * BK, (t.mt * kTileM + m_rank) >> 5);
               else
 #pragma unroll
-              for (int j = 0; j < kChunks; ++j) tma_load_2d(a_dst + j * 4096, &tmap_a, bar, t.mt * kTileM + 32 * j, ks * BK);
+              for (int j = 0; j < kChunks; ++j) MNV_LD2(a_dst + j * 4096, &tmap_a, bar, t.mt * kTileM + m_rank + 32 * j, ks * BK);
             } else if (p.a_mode == TMA_A_TILED_K) {
 #pragma unroll
-              for (int h = 0; h < kHalves; ++h) tma_load_2d(a_dst + h * kABytes, &tmap_a, bar, ks * BK, t.mt * kTileM + h * BM);
+              for (int h = 0; h < kHalves; ++h) MNV_LD2(a_dst + h * kABytes, &tmap_a, bar, ks * BK, t.mt * kTileM + m_rank + h * BM);
             } else {   // k-stage = 32 output pixels: of one image (p.spi stages per image, top_diff padded per image), or
                        // spi == 0: 32 consecutive pixels of the flat (image, pixel) axis -- the im2col walk wraps into the
                        // next image exactly as the channels-last top_diff's rows do, so nothing is padded
@@ -971,7 +1108,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
               const int oh = pix / p.Wo;
               const int h = oh * p.sv - p.ph, w = (pix - oh * p.Wo) * p.sh - p.pw;
 #pragma unroll
-              for (int j = 0; j < kChunks; ++j) tma_load_im2col_4d(a_dst + j * 4096, &tmap_a, bar, a_c[j], w, h, img, a_kw[j], a_kh[j]);
+              for (int j = 0; j < kChunks; ++j) MNV_LDI(a_dst + j * 4096, &tmap_a, bar, a_c[j], w, h, img, a_kw[j], a_kh[j]);
             }
           }
           const uint32_t dst = smem_base + stage * kSBytes + kATile;
@@ -979,21 +1116,21 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           if (AM == A_TMA && p.b_im2col) {   // transposed orientation: the n-tile's bn pixels x 32 channels of tap (kh, kw)
             const int n_first = t.nt * p.bn, img = n_first / p.P, pix = n_first - img * p.P, oh = pix / p.Wo;
             const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
-            tma_load_im2col_4d(dst, &tmap_b, full0 + 8 * stage, cc * BK, (pix - oh * p.Wo) * p.sh - p.pw, oh * p.sv - p.ph, img, tap - kh * p.fw, kh);
+            tma_load_im2col_4d(dst, &tmap_b, full0 + 8 * stage, cc * BK, (pix - oh * p.Wo) * p.sh - p.pw, oh * p.sv - p.ph, img, tap - kh * p.fw, kh);   // never paired
           } else
           if (AM == A_TMA && p.b_mn) {   // MN-major B: one 32 n x 32 k box per 32 columns (bn % 32 == 0, never wide)
-            if (p.b_mn == 2) tma_load_3d(dst, &tmap_b, full0 + 8 * stage, 0, ks * BK, (t.nt * p.bn) >> 5);
+            if (p.b_mn == 2) MNV_LD3(dst, &tmap_b, fbar, 0, ks * BK, (t.nt * p.bn + n_rank) >> 5);
             else
-            for (int j = 0; j < p.bn / 32; ++j) tma_load_2d(dst + j * 4096, &tmap_b, full0 + 8 * stage, t.nt * p.bn + 32 * j, ks * BK);
+            for (int j = 0; j < bn_cta / 32; ++j) MNV_LD2(dst + j * 4096, &tmap_b, fbar, t.nt * p.bn + n_rank + 32 * j, ks * BK);
           } else
           for (int h = 0; h < halves; ++h) {
             const uint32_t d2 = dst + h * rows * 128;
-            const int n0 = t.nt * p.bn + h * rows;
+            const int n0 = t.nt * p.bn + n_rank + h * rows;
             if (p.spi > 0) {   // top_diff as (pixel, channel, image): one image's 32-pixel slab per stage
               int img = ks / p.spi;
-              tma_load_3d(d2, &tmap_b, full0 + 8 * stage, (ks - img * p.spi) * BK, n0, img);
+              MNV_LD3(d2, &tmap_b, fbar, (ks - img * p.spi) * BK, n0, img);
             } else {
-              tma_load_2d(d2, &tmap_b, full0 + 8 * stage, ks * BK, n0);
+              MNV_LD2(d2, &tmap_b, fbar, ks * BK, n0);
             }
           }
           if (++stage == kNStages) { stage = 0; phase ^= 1; }
@@ -1002,6 +1139,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     }
     __syncwarp();
   } else {
+#undef MNV_LD2
+#undef MNV_LD3
+#undef MNV_LDI
     // ===================== gather producers =====================
     if constexpr (AM == A_TMA) {
       // both operands come through TMA: no gather to do, help drain the accumulators
@@ -1032,7 +1172,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
         //            128-byte row of the tile: eight conflict-free STS.128.
         const int wq = pw & 3;
         const int HW = p.H * p.W;
-        for (int tile = blockIdx.x; grp < ngrp && tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; grp < ngrp && tile < total_tiles; tile += tile_step) {
           TileCoord t = decode_tile(p, tile);
           const int nks = t.ks_end - t.ks_begin;
           int ks = t.ks_begin + (grp + ngrp - static_cast<int>(cnt % static_cast<uint32_t>(ngrp))) % ngrp;
@@ -1106,7 +1246,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           }
         }
       } else
-      for (int tile = blockIdx.x; grp < ngrp && tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; grp < ngrp && tile < total_tiles; tile += tile_step) {
         TileCoord t = decode_tile(p, tile);
         const int nks = t.ks_end - t.ks_begin;
         int ks = t.ks_begin + (grp + ngrp - static_cast<int>(cnt % static_cast<uint32_t>(ngrp))) % ngrp;   // this group's first stage in the tile
@@ -1158,7 +1298,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     int stage = 0; uint32_t phase = 0;
     float va[LOOK][8];
     float4 vb[BTMA ? 1 : LOOK][4];
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       TileCoord t = decode_tile(p, tile);
       ARow arow = {};
       AWgrad<2> awg;
@@ -1225,9 +1365,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // neither CTA frees TMEM the pair's last MMAs may still write
+  if (warp == 4) { if (PAIR) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols); }
 }
+
+#undef tile_first
+#undef tile_step
+#undef bn_cta
 
 // split-K: out[index(m,n)] = bias[n] + sum_s partial[s][n][m], splits folded in order
 __global__ void __launch_bounds__(kBlock) splitk_reduce_kernel(const GemmParams p) {
@@ -1526,6 +1670,14 @@ MNV_OPT g_opt_no_s2d{0};     // 1: strided few-channel convs stay on the gather 
 MNV_OPT g_opt_shift_dbg{0};  // shift-GEMM kernel experiments (see ShiftParams::dbg)
 MNV_OPT g_opt_no_shift{0};   // 1: no shift-GEMM kernel (debug / tuning)
 MNV_OPT g_opt_no_transposed{0};  // 1: narrow-output convolutions keep the D[pixel][co] orientation (tuning)
+// The CTA pair (RING 4, tcgen05.mma.cta_group::2) is built, bit-identical to the other tiles and OFF: measured on B200 it is
+// slower than the 256-row single-CTA tile it would replace -- MatMult 8192^3 845 TF/s (tall) vs 744 (pair, the peer's copies
+// signalling the leader's barrier, the CUTLASS protocol) vs 686 (local barriers + a forwarded arrive); conv4 forward 0.233 ms vs
+// 0.314; conv4 backward-filter 0.315 vs 0.534.  With tf32 an instruction covers K = 8 (32 bytes), so a k-stage is four paired
+// instructions plus per-copy / per-stage cross-SM signalling; the halved B bytes do not buy that back.  DESIGN.md 5.1d.
+MNV_OPT g_opt_pair_remote{1};   // CTA pair: 1 = the peer's copies count their bytes on the leader's barrier (cta_group::2 copy forms),
+                                // 0 = every copy signals its own CTA's barrier and the peer forwards one arrive per stage
+MNV_OPT g_opt_pair{0};          // 1: 256-row tiles run on a CTA pair (RING 4) instead of one CTA (RING 3) (tuning)
 MNV_OPT g_opt_no_mn3{0};        // 1: MN-major operands as one 2-D box per 32 rows instead of one 3-D box per k-stage (tuning)
 MNV_OPT g_opt_no_nhwc_wgrad{0}; // 1: backward-filter keeps the re-pitched NCHW top_diff (K-major B) instead of the channels-last one (tuning)
 MNV_OPT g_opt_s2d_im2col{0}; // 1: space-to-depth views may also run on the im2col-fed kernel (experiments; slower than the gathers)
@@ -1917,7 +2069,7 @@ static int sm_budget() {
 static void plan_splits(GemmParams& p, size_t ws_bytes_for_partials) {
   long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   int splits = 1;
-  const int sms = sm_budget();
+  const int sms = p.tall == 2 ? sm_budget() / 2 : sm_budget();   // CTA pairs: one tile per two SMs
   if (tiles * 4 < sms * 3) {  // fewer than 3/4 of a wave: split K
     splits = static_cast<int>(sms / tiles);
     int max_by_k = p.k_stages / 4;  // at least 4 stages per split
@@ -1935,7 +2087,7 @@ static void plan_splits(GemmParams& p, size_t ws_bytes_for_partials) {
 // fraction of the machine's CTA slots the tile grid keeps busy over its whole run
 static double wave_fill(const GemmParams& p) {
   long long ctas = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
-  const int sms = sm_budget();
+  const int sms = p.tall == 2 ? sm_budget() / 2 : sm_budget();
   long long waves = (ctas + sms - 1) / sms;
   return static_cast<double>(ctas) / static_cast<double>(waves * sms);
 }
@@ -1977,7 +2129,20 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
     if (q.bn < 16) q.bn = 16;
     q.n_tiles = (p.N + q.bn - 1) / q.bn;
     plan_splits(q, ws_bytes_for_partials);
-    if (q.stages_per_split >= g_opt_tall_min_stages.load() && (wave_fill(q) >= 0.85 || wave_fill(q) >= wave_fill(p))) p = q;
+    if (q.stages_per_split >= g_opt_tall_min_stages.load() && (wave_fill(q) >= 0.85 || wave_fill(q) >= wave_fill(p))) {
+      p = q;
+      // the same 256-row tile on a CTA pair (cta_group::2): each CTA stages half of B, so bn is a multiple of 32
+      if (g_opt_pair.load() && sm_budget() % 2 == 0) {
+        GemmParams r = q;
+        r.bn = (q.bn + 31) / 32 * 32;
+        if (r.bn <= BN_MAX) {
+          r.n_tiles = (r.N + r.bn - 1) / r.bn;
+          r.tall = 2; r.stages = 6; r.stage_bytes = kABytes + 128 * BK * 4;
+          plan_splits(r, ws_bytes_for_partials);
+          p = r;
+        }
+      }
+    }
   }
 }
 
@@ -1988,7 +2153,7 @@ MNV_OPT g_opt_no_tail{0};    // 1: no tail split (tuning)
 static void plan_tail(GemmParams& p, void* ws, size_t ws_bytes) {
   p.tail_splits = 0;
   if (g_opt_no_tail.load() || p.splits != 1 || !ws) return;
-  const int sms = sm_budget(), tiles = p.m_tiles * p.n_tiles;
+  const int sms = p.tall == 2 ? sm_budget() / 2 : sm_budget(), tiles = p.m_tiles * p.n_tiles;
   const int rem = tiles % sms;
   if (tiles < sms || rem == 0 || rem * 2 > sms) return;
   int S = sms / rem;
@@ -2022,6 +2187,11 @@ static int launch_umma_w(const GemmParams& p, const CUtensorMap& tm, cudaStream_
   }
   const long long total = q.total_units;
   const int sms = sm_budget();
+  if (RING == 4) {   // CTA pairs: one cluster of 2 per tile in flight
+    const int pairs = static_cast<int>(total < sms / 2 ? total : sms / 2);
+    launch_pdl_cluster((umma_gemm_kernel<AM, BMD, BTMA, RING>), dim3(2 * pairs), dim3(kThreads), kSmemBytes, s, 2, q, tm, tm_a);
+    return finish_launch();
+  }
   int grid = static_cast<int>(total < sms ? total : sms);
   launch_pdl((umma_gemm_kernel<AM, BMD, BTMA, RING>), dim3(grid), dim3(kThreads), kSmemBytes, s, q, tm, tm_a);
   return finish_launch();
@@ -2034,7 +2204,8 @@ static int launch_umma(const GemmParams& p, const CUtensorMap& tm, cudaStream_t 
 
 // both operands through TMA
 static int launch_umma_tma(const GemmParams& p, const CUtensorMap& tm_a, const CUtensorMap& tm_b, cudaStream_t s) {
-  int rc = p.tall      ? launch_umma_w<A_TMA, B_KMAJOR, true, 3>(p, tm_b, s, tm_a)
+  int rc = p.tall == 2 ? launch_umma_w<A_TMA, B_KMAJOR, true, 4>(p, tm_b, s, tm_a)
+           : p.tall    ? launch_umma_w<A_TMA, B_KMAJOR, true, 3>(p, tm_b, s, tm_a)
            : p.wide    ? launch_umma_w<A_TMA, B_KMAJOR, true, 1>(p, tm_b, s, tm_a)
            : (p.bn <= 128 && !g_opt_no_deep.load()) ? launch_umma_w<A_TMA, B_KMAJOR, true, 2>(p, tm_b, s, tm_a)
                           : launch_umma_w<A_TMA, B_KMAJOR, true, 0>(p, tm_b, s, tm_a);
@@ -2088,7 +2259,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   memset(&tm, 0, sizeof(tm));
   bool tma = false;
   if (tma_ok) {
-    tma = make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.wide ? p.bn / 2 : p.bn);
+    tma = make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn);
     if (!tma && (p.wide || p.tall)) plan_tiles(p, ws ? ws_bytes : 0, false);   // the wide / tall tiles need the TMA-fed path
   }
   p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
@@ -2096,7 +2267,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   if (tma_a_ok && tma) {
     CUtensorMap tm_a;
     memset(&tm_a, 0, sizeof(tm_a));
-    if (!g_opt_no_mn3.load() && make_mn3_tmap(&tm_a, p.a, p.M, p.K, p.lda, p.tall ? 8 : 4)) {
+    if (!g_opt_no_mn3.load() && make_mn3_tmap(&tm_a, p.a, p.M, p.K, p.lda, p.tall == 1 ? 8 : 4)) {
       p.a_mode = TMA_A_TILED_MN; p.a_g3 = 1;
       return launch_umma_tma(p, tm_a, tm, s);
     }
@@ -2108,7 +2279,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
   if (p.tall) {   // planned for the all-TMA path, which did not materialise
     plan_tiles(p, ws ? ws_bytes : 0, tma);
     p.partial = p.splits > 1 ? static_cast<float*>(ws) : nullptr;
-    if (tma && !make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, p.wide ? p.bn / 2 : p.bn)) return MNV_EINVAL;
+    if (tma && !make_b_tmap(&tm, p.b, p.N, p.K, p.ldb, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn)) return MNV_EINVAL;
   }
   if (AM == A_IM2COL_FWD && BMD == B_KMAJOR && tma && (p.sv > 1 || p.sh > 1) && !g_opt_no_klane.load() &&
       p.k_stages * BK <= kKtabMax && static_cast<long long>(p.Ci) * p.H * p.W < (1ll << 22) && !p.wide) {
@@ -2124,7 +2295,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, cudaStream_t s)
 static void zero_conv(GemmParams& p) {
   p.Ci = p.Co = p.H = p.W = p.Ho = p.Wo = p.fh = p.fw = 1;
   p.ph = p.pw = 0; p.sv = p.sh = 1;
-  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.b_im2col = 0; p.a_g3 = 0; p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
+  p.lda = p.ldb = 0; p.b_vec = 0; p.use_ktab = 0; p.spi = 0; p.a_mode = 0; p.b_mn = 0; p.cpt = 1; p.out_mode = 0; p.relu = 0; p.pf_dist = g_opt_pf_dist.load(); p.tail_first = 0; p.tail_splits = 0; p.tail_stages = 0; p.total_units = 0; p.r_ci = p.r_fh = p.r_fw = p.r_sv = p.r_sh = 1; p.b_flip = 0; p.b_im2col = 0; p.a_g3 = 0; p.pair_remote = g_opt_pair_remote.load(); p.wait_hint = static_cast<unsigned>(g_opt_wait_hint.load());
   p.bias = nullptr; p.partial = nullptr;
 }
 
@@ -2227,7 +2398,7 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   }
   if (!transposed) {
     if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
-    if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, p.wide ? p.bn / 2 : p.bn)) return MNV_OK;
+    if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn)) return MNV_OK;
   }
   int rc = MNV_OK;
   if (s2d) rc = launch_s2d(x, xh, N, *s2d, Cp, s);
@@ -2331,6 +2502,8 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "force_tma_a") return g_opt_force_tma_a.exchange(value);
   if (k == "no_nhwc_wgrad") return g_opt_no_nhwc_wgrad.exchange(value);
   if (k == "no_mn3") return g_opt_no_mn3.exchange(value);
+  if (k == "pair") return g_opt_pair.exchange(value);
+  if (k == "pair_remote") return g_opt_pair_remote.exchange(value);
   if (k == "no_transposed") return g_opt_no_transposed.exchange(value);
   return -1;
 }
@@ -2398,7 +2571,7 @@ int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k
   p.b_mn = trans_b ? 1 : 0;
   plan_tiles(p, ws_left, !trans_b, true);   // MN-major B: boxes of 32 columns, no wide tile
   if (trans_b) {
-    p.bn = (p.bn + 31) / 32 * 32;
+    p.bn = p.tall == 2 ? (p.bn + 63) / 64 * 64 : (p.bn + 31) / 32 * 32;   // a CTA of a pair stages bn / 2 columns
     if (p.bn > BN_MAX) p.bn = BN_MAX;
     p.n_tiles = (p.N + p.bn - 1) / p.bn;
     plan_splits(p, ws_left);
@@ -2410,10 +2583,10 @@ int mnv_matmult_ex(const float* a, const float* b, float* c, int m, int n, int k
   bool ok_a, ok_b;
   const bool mn3 = !g_opt_no_mn3.load();
   if (trans_a) ok_a = make_b_tmap(&tm_a, a, m, k, k, BM);
-  else if (mn3 && make_mn3_tmap(&tm_a, a, m, k, m, p.tall ? 8 : 4)) { ok_a = true; p.a_g3 = 1; }
+  else if (mn3 && make_mn3_tmap(&tm_a, a, m, k, m, p.tall == 1 ? 8 : 4)) { ok_a = true; p.a_g3 = 1; }
   else ok_a = make_a_mn_tmap(&tm_a, a, m, k, m);
-  if (!trans_b) ok_b = make_b_tmap(&tm_b, b, n, k, k, p.wide ? p.bn / 2 : p.bn);
-  else if (mn3 && make_mn3_tmap(&tm_b, b, n, k, n, p.bn / 32)) { ok_b = true; p.b_mn = 2; }
+  if (!trans_b) ok_b = make_b_tmap(&tm_b, b, n, k, k, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn);
+  else if (mn3 && make_mn3_tmap(&tm_b, b, n, k, n, p.tall == 2 ? p.bn / 64 : p.bn / 32)) { ok_b = true; p.b_mn = 2; }
   else ok_b = make_a_mn_tmap(&tm_b, b, n, k, n);
   if (!ok_a || !ok_b) return MNV_EINVAL;
   return launch_umma_tma(p, tm_a, tm_b, s);
@@ -2689,7 +2862,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
         q.a = xh; q.b = dyh; q.M = fh * fw * cpt * BK; q.a_mode = TMA_A_IM2COL_MN; q.b_mn = 1; q.cpt = cpt; q.out_mode = 1; q.spi = 0;
         q.P = q.M; q.col_stride = static_cast<long long>(Ci) * fh * fw; q.ldb = Cop; q.b_vec = 1;
         plan_tiles(q, ws_left, false, true);
-        q.bn = (q.bn + 31) / 32 * 32;                  // MN-major B: boxes of 32 columns
+        q.bn = q.tall == 2 ? (q.bn + 63) / 64 * 64 : (q.bn + 31) / 32 * 32;   // MN-major B: boxes of 32 columns (per CTA of a pair)
         if (q.bn > BN_MAX) q.bn = BN_MAX;
         q.n_tiles = (q.N + q.bn - 1) / q.bn;
         plan_splits(q, ws_left);
@@ -2697,7 +2870,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
         CUtensorMap tm_a, tm_b;
         memset(&tm_a, 0, sizeof(tm_a));
         memset(&tm_b, 0, sizeof(tm_b));
-        bool ok_b = !g_opt_no_mn3.load() && make_mn3_tmap(&tm_b, dyh, Co, q.K, Cop, q.bn / 32);
+        bool ok_b = !g_opt_no_mn3.load() && make_mn3_tmap(&tm_b, dyh, Co, q.K, Cop, q.tall == 2 ? q.bn / 64 : q.bn / 32);
         if (ok_b) q.b_mn = 2;
         else ok_b = make_a_mn_tmap(&tm_b, dyh, Co, q.K, Cop);
         if (ok_b && make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true)) {
@@ -2779,7 +2952,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
         memset(&tm_a, 0, sizeof(tm_a));
         memset(&tm_b, 0, sizeof(tm_b));
         if (make_im2col_tmap(&tm_a, xh, Cp, v.Wv, v.Hv, N, 0, 0, v.fwv, v.fhv, 1, 1, BK, true) &&
-            make_dy_tmap(&tm_b, dy_tma, P, pitch, Co, N, q.wide ? q.bn / 2 : q.bn)) {
+            make_dy_tmap(&tm_b, dy_tma, P, pitch, Co, N, (q.wide || q.tall == 2) ? q.bn / 2 : q.bn)) {
           rc = launch_s2d(bottom, xh, N, v, Cp, s);
           if (rc) return rc;
           return launch_umma_tma(q, tm_a, tm_b, s);
@@ -2802,7 +2975,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
       memset(&tm_a, 0, sizeof(tm_a));
       memset(&tm_b, 0, sizeof(tm_b));
       if (make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true) &&
-          make_dy_tmap(&tm_b, dy_tma, P, pitch, Co, N, q.wide ? q.bn / 2 : q.bn)) {
+          make_dy_tmap(&tm_b, dy_tma, P, pitch, Co, N, (q.wide || q.tall == 2) ? q.bn / 2 : q.bn)) {
         rc = launch_nhwc(bottom, xh, N, Ci, Cp, H * W, s);
         if (rc) return rc;
         return launch_umma_tma(q, tm_a, tm_b, s);
@@ -2813,7 +2986,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
   p.partial = p.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  if (!make_dy_tmap(&tm, dy_tma, P, pitch, Co, N, p.wide ? p.bn / 2 : p.bn)) {
+  if (!make_dy_tmap(&tm, dy_tma, P, pitch, Co, N, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn)) {
     p.spi = 0; p.K = static_cast<int>(K);
     return launch_gemm<A_IM2COL_WGRAD, B_DY_WGRAD>(p, ws, ws_left, s);
   }

@@ -157,7 +157,11 @@ TMA_CASES = [
     (100, 112, 48, 14, 14, 1, 1, 1, 1, 3, 3),   # backward-data with 112 outputs; forward (Co = 48) stays put
 ]
 OPERAND_PATHS = [("gather", {"no_tma_a": 7}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tma+tall", {"force_tma_a": 1}),
-                 ("tma, float32 maps", {"force_tma_a": 1, "tma_tf32": 0}), ("default", {})]
+                 ("tma, float32 maps", {"force_tma_a": 1, "tma_tf32": 0}),
+                 # the CTA pair (tcgen05.mma.cta_group::2; built, measured slower, off by default), both hand-over protocols
+                 ("tma+pair", {"force_tma_a": 1, "pair": 1, "tall_min_stages": 4}),
+                 ("tma+pair, forwarded arrive", {"force_tma_a": 1, "pair": 1, "pair_remote": 0, "tall_min_stages": 4}),
+                 ("default", {})]
 
 
 @pytest.mark.parametrize("case", TMA_CASES)
@@ -173,7 +177,7 @@ def test_conv_operand_paths(g, case):
     wy = orc.conv_forward(x, w, b, *geo)
     wdx = orc.conv_backward_data(dy, w, *geo)
     wdw = orc.conv_backward_filter(x, dy, *geo)
-    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1}
+    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1, "pair": 0, "pair_remote": 1, "tall_min_stages": 32}
     for name, opts in OPERAND_PATHS:
         try:
             for k, v in {**defaults, **opts}.items():
@@ -314,8 +318,9 @@ def test_matmult_operand_paths(g, m, n, k):
     a = rng.normal(0, 1, m * k).astype(np.float32)
     b = rng.normal(0, 1, k * n).astype(np.float32)
     want = (b.reshape(n, k).astype(np.float64) @ a.reshape(k, m).astype(np.float64)).ravel()
-    defaults = {"no_tma_a": 0, "no_tall": 0, "tma_tf32": 1}
-    for name, opts in (("gather", {"no_tma_a": 2}), ("tma", {"no_tall": 1}), ("tma+tall", {"tall_min_stages": 1}), ("float32 maps", {"tma_tf32": 0})):
+    defaults = {"no_tma_a": 0, "no_tall": 0, "tma_tf32": 1, "pair": 0, "pair_remote": 1}
+    for name, opts in (("gather", {"no_tma_a": 2}), ("tma", {"no_tall": 1}), ("tma+tall", {"tall_min_stages": 1}), ("float32 maps", {"tma_tf32": 0}),
+                       ("tma+pair", {"tall_min_stages": 1, "pair": 1}), ("tma+pair, forwarded arrive", {"tall_min_stages": 1, "pair": 1, "pair_remote": 0})):
         try:
             for key, v in {**defaults, **opts}.items():
                 _set(key, v)
