@@ -1675,6 +1675,7 @@ MNV_OPT g_opt_no_transposed{0};  // 1: narrow-output convolutions keep the D[pix
 // signalling the leader's barrier, the CUTLASS protocol) vs 686 (local barriers + a forwarded arrive); conv4 forward 0.233 ms vs
 // 0.314; conv4 backward-filter 0.315 vs 0.534.  With tf32 an instruction covers K = 8 (32 bytes), so a k-stage is four paired
 // instructions plus per-copy / per-stage cross-SM signalling; the halved B bytes do not buy that back.  DESIGN.md 5.1d.
+MNV_OPT g_opt_no_pointwise{0};  // 1: 1x1 convolutions through the im2col map and the packed filter like every other geometry (tuning)
 MNV_OPT g_opt_pair_remote{1};   // CTA pair: 1 = the peer's copies count their bytes on the leader's barrier (cta_group::2 copy forms),
                                 // 0 = every copy signals its own CTA's barrier and the peer forwards one arrive per stage
 MNV_OPT g_opt_pair{0};          // 1: 256-row tiles run on a CTA pair (RING 4) instead of one CTA (RING 3) (tuning)
@@ -2371,7 +2372,23 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
   p.ldb = p.K; p.b_vec = 1;
   p.P = Ho * Wo; p.img_stride = static_cast<long long>(Co) * p.P; p.col_stride = p.P;
   p.a_mode = TMA_A_IM2COL_K; p.cpt = cpt; p.relu = relu;
-  plan_tiles(p, ws2_bytes, true, true);
+  // 1x1 / stride 1 / no padding (two thirds of GoogLeNet's convolutions): the channels-last copy IS the K-major A matrix
+  // [pixel][Cp] -- a tiled map instead of the im2col one -- and the filter as stored is already a TMA-able B operand:
+  // forward reads w[co][c] as K-major rows (Ci % 4 == 0), backward-data reads the same array as the MN-major B[k = co][n = ci]
+  // (one 3-D box per k-stage, make_mn3_tmap; Ci % 32 == 0).  No filter pre-pass, no launch for it.
+  const bool pointwise = !s2d && ff == 1 && sv == 1 && sh == 1 && ph == 0 && pw == 0 && !g_opt_no_pointwise.load();
+  int b_direct = 0;
+  if (pointwise && aligned16(w) && prepass_round() == 0) {     // (the TFLOAT32-typed maps round the operands as they copy)
+    if (w_sc == 1 && w_sn == Ci && Ci % 4 == 0) b_direct = 1;
+    else if (w_sn == 1 && w_sc == Co && Co % 32 == 0 && !g_opt_no_mn3.load()) b_direct = 2;
+  }
+  plan_tiles(p, ws2_bytes, b_direct != 2, true);
+  if (b_direct == 2) {      // MN-major B: boxes of 32 columns per CTA
+    p.bn = (p.bn + 31) / 32 * 32;
+    if (p.bn > BN_MAX) p.bn = BN_MAX;
+    p.n_tiles = (p.N + p.bn - 1) / p.bn;
+    plan_splits(p, ws2_bytes);
+  }
   // Round 1 took this path only when the GEMM did enough work per input element to pay for the channels-last pre-pass
   // (Co * taps >= 3000, or a narrow output).  With the twins shared between the calls of a step (and between the branches
   // of an inception module) the pre-pass is paid once per array, and the rule lost on both nets: always taken now
@@ -2396,9 +2413,14 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
     transposed = q.splits == 1 && q.m_tiles == 1 && q.n_tiles >= sm_budget() / 2 &&
                  make_b_tmap(&tm_a, wb, Co, p.K, p.K, BM) && make_im2col_tmap(&tm_b, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, q.bn, false);
   }
+  bool pack_filter = true;
   if (!transposed) {
-    if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
-    if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn)) return MNV_OK;
+    if (pointwise && make_b_tmap(&tm_a, xh, p.M, Cp, Cp, BM)) p.a_mode = TMA_A_TILED_K;
+    else if (!make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BM, false)) return MNV_OK;
+    if (b_direct == 1 && make_b_tmap(&tm_b, w, Co, Ci, Ci, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn)) pack_filter = false;
+    else if (b_direct == 2 && make_mn3_tmap(&tm_b, w, Co, Ci, Co, p.tall == 2 ? p.bn / 64 : p.bn / 32)) { pack_filter = false; p.b_mn = 2; }
+    else if (b_direct == 2) return MNV_OK;     // planned for 32-column boxes: let the caller take its generic route
+    else if (!make_b_tmap(&tm_b, wb, Co, p.K, p.K, (p.wide || p.tall == 2) ? p.bn / 2 : p.bn)) return MNV_OK;
   }
   int rc = MNV_OK;
   if (s2d) rc = launch_s2d(x, xh, N, *s2d, Cp, s);
@@ -2407,10 +2429,12 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
     if (!rc && use_twin) *twin.state = 1;
   }
   if (rc) return rc;
-  if (s2d) launch_pdl(s2d_filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, *s2d, cpt, 0, 4, static_cast<int>(K), w_sn, w_sc, flip, prepass_round());
-  else launch_pdl(filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
-  rc = finish_launch();
-  if (rc) return rc;
+  if (pack_filter) {
+    if (s2d) launch_pdl(s2d_filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, *s2d, cpt, 0, 4, static_cast<int>(K), w_sn, w_sc, flip, prepass_round());
+    else launch_pdl(filter_pack_kernel, dim3(stream_grid(static_cast<size_t>(Co) * K)), dim3(kBlock), 0, s, w, wb, Co, Ci, ff, cpt * BK, w_sn, w_sc, flip, prepass_round());
+    rc = finish_launch();
+    if (rc) return rc;
+  }
   *done = true;
   return launch_umma_tma(transposed ? q : p, tm_a, tm_b, s);
 }
@@ -2503,6 +2527,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_nhwc_wgrad") return g_opt_no_nhwc_wgrad.exchange(value);
   if (k == "no_mn3") return g_opt_no_mn3.exchange(value);
   if (k == "pair") return g_opt_pair.exchange(value);
+  if (k == "no_pointwise") return g_opt_no_pointwise.exchange(value);
   if (k == "pair_remote") return g_opt_pair_remote.exchange(value);
   if (k == "no_transposed") return g_opt_no_transposed.exchange(value);
   return -1;
@@ -2873,7 +2898,15 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
         bool ok_b = !g_opt_no_mn3.load() && make_mn3_tmap(&tm_b, dyh, Co, q.K, Cop, q.tall == 2 ? q.bn / 64 : q.bn / 32);
         if (ok_b) q.b_mn = 2;
         else ok_b = make_a_mn_tmap(&tm_b, dyh, Co, q.K, Cop);
-        if (ok_b && make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true)) {
+        // 1x1 / stride 1 / no padding: the channels-last bottom is the MN-major A matrix [pixel][Cp] itself -- one 3-D box per
+        // k-stage instead of four (tall: eight) im2col boxes
+        bool ok_a = false;
+        if (ok_b && fh == 1 && fw == 1 && sv == 1 && sh == 1 && ph == 0 && pw == 0 && !g_opt_no_pointwise.load() && !g_opt_no_mn3.load() &&
+            make_mn3_tmap(&tm_a, xh, Ci, q.K, Cp, q.tall == 1 ? 8 : 4)) {
+          ok_a = true; q.a_mode = TMA_A_TILED_MN; q.a_g3 = 1;
+        }
+        if (!ok_a) ok_a = ok_b && make_im2col_tmap(&tm_a, xh, Cp, W, H, N, pw, ph, fw, fh, sh, sv, BK, true);
+        if (ok_a) {
           if (!xtw.valid()) {
             rc = launch_nhwc(bottom, xh, N, Ci, Cp, H * W, s);
             if (rc) return rc;

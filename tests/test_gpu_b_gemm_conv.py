@@ -155,9 +155,15 @@ TMA_CASES = [
     (33, 32, 128, 27, 25, 0, 0, 1, 1, 1, 1),    # 1x1, Co = 128, odd plane size
     (30, 96, 64, 27, 27, 2, 2, 1, 1, 5, 5),     # backward-data transposed (Ci = 96 outputs), AlexNet conv2 geometry
     (100, 112, 48, 14, 14, 1, 1, 1, 1, 3, 3),   # backward-data with 112 outputs; forward (Co = 48) stays put
+    # 1x1 / stride 1 / pad 0 (GoogLeNet's reduce / projection layers): tiled maps over the channels-last copy, the filter read
+    # in place (K-major forward, MN-major backward-data), one 3-D box for backward-filter's A
+    (20, 480, 192, 14, 14, 0, 0, 1, 1, 1, 1),   # inception 4a 1x1: every direct path applies (Ci % 32 == 0, Co % 32 == 0)
+    (12, 192, 16, 28, 28, 0, 0, 1, 1, 1, 1),    # 3a 5x5_reduce: 16 filters
+    (9, 528, 160, 14, 13, 0, 0, 1, 1, 1, 1),    # Ci % 32 != 0: backward-data / backward-filter keep the packed / im2col forms
+    (7, 36, 24, 9, 9, 0, 0, 1, 1, 1, 1),        # Ci % 32 != 0, Co % 32 != 0, split-K
 ]
 OPERAND_PATHS = [("gather", {"no_tma_a": 7}), ("tma", {"force_tma_a": 1, "no_tall": 1}), ("tma+tall", {"force_tma_a": 1}),
-                 ("tma, float32 maps", {"force_tma_a": 1, "tma_tf32": 0}),
+                 ("tma, float32 maps", {"force_tma_a": 1, "tma_tf32": 0}), ("tma, no pointwise forms", {"force_tma_a": 1, "no_pointwise": 1}),
                  # the CTA pair (tcgen05.mma.cta_group::2; built, measured slower, off by default), both hand-over protocols
                  ("tma+pair", {"force_tma_a": 1, "pair": 1, "tall_min_stages": 4}),
                  ("tma+pair, forwarded arrive", {"force_tma_a": 1, "pair": 1, "pair_remote": 0, "tall_min_stages": 4}),
@@ -177,7 +183,7 @@ def test_conv_operand_paths(g, case):
     wy = orc.conv_forward(x, w, b, *geo)
     wdx = orc.conv_backward_data(dy, w, *geo)
     wdw = orc.conv_backward_filter(x, dy, *geo)
-    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1, "pair": 0, "pair_remote": 1, "tall_min_stages": 32}
+    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1, "pair": 0, "pair_remote": 1, "tall_min_stages": 32, "no_pointwise": 0}
     for name, opts in OPERAND_PATHS:
         try:
             for k, v in {**defaults, **opts}.items():
