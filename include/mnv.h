@@ -62,6 +62,9 @@ int mnv_set_dependent_launch(int enabled);
 /* ---- a1 Arithmetic: c = a o b  (cuda_perform.h:12-14,16; cuda_perform.cu:32-64) ------------ */
 int mnv_add(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
 int mnv_sub(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
+/* dst = ((srcs[0] + srcs[1]) + srcs[2]) + ... : the bits of count - 1 chained mnv_add calls, in one pass.  `srcs` is a HOST
+ * array of 1..8 device pointers.  owl.net sums the sensitivities of a blob with several consumers with it (net.py:1102-1114). */
+int mnv_add_n(const float* const* srcs, int count, float* dst, size_t n, mnv_stream_t stream);
 int mnv_dot_mult(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
 int mnv_dot_div(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
 

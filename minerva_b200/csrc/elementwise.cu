@@ -109,6 +109,37 @@ int launch_ew(const float* a, const float* b, const float* c, float* out, size_t
   return MNV_OK;
 }
 
+// dst = ((src0 + src1) + src2) + ...: the left-to-right chain of mnv_add calls in one pass (count + 1 streams instead of
+// 3 * (count - 1)).  owl.net sums the sensitivities a blob receives from its consumers with it (an inception input has four).
+struct AddNArgs { const float* src[8]; int count; };
+template <bool VEC>
+__global__ void __launch_bounds__(kBlock) add_n_kernel(const AddNArgs a, float* __restrict__ out, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (VEC) {
+    const size_t n4 = n / 4;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 acc = __ldg(reinterpret_cast<const float4*>(a.src[0]) + i);
+#pragma unroll 8
+      for (int j = 1; j < a.count; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[j]) + i);
+        acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+      }
+      reinterpret_cast<float4*>(out)[i] = acc;
+    }
+    for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float acc = a.src[0][i];
+      for (int j = 1; j < a.count; ++j) acc = __fadd_rn(acc, a.src[j][i]);
+      out[i] = acc;
+    }
+  } else {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float acc = a.src[0][i];
+      for (int j = 1; j < a.count; ++j) acc = __fadd_rn(acc, a.src[j][i]);
+      out[i] = acc;
+    }
+  }
+}
+
 // ---- functors (x, y, z) -> result; unused operands are ignored ------------------------------
 struct AddOp { __device__ float operator()(float x, float y, float) const { return __fadd_rn(x, y); } };
 struct SubOp { __device__ float operator()(float x, float y, float) const { return __fsub_rn(x, y); } };
@@ -389,6 +420,23 @@ extern "C" {
 
 int mnv_add(const float* a, const float* b, float* c, size_t n, mnv_stream_t s) {
   return launch_ew<2>(a, b, nullptr, c, n, AddOp{}, as_stream(s));
+}
+int mnv_add_n(const float* const* srcs, int count, float* dst, size_t n, mnv_stream_t s) {
+  if (count < 1 || count > 8) return MNV_EINVAL;
+  if (n == 0) return MNV_OK;
+  if (!srcs || !dst) return MNV_EINVAL;
+  AddNArgs a;
+  bool vec = aligned16(dst);
+  for (int j = 0; j < 8; ++j) a.src[j] = nullptr;
+  for (int j = 0; j < count; ++j) {
+    if (!srcs[j]) return MNV_EINVAL;
+    a.src[j] = srcs[j];
+    vec = vec && aligned16(srcs[j]);
+  }
+  a.count = count;
+  if (vec) add_n_kernel<true><<<stream_grid(n / 4 + 1), kBlock, 0, as_stream(s)>>>(a, dst, n);
+  else add_n_kernel<false><<<stream_grid(n), kBlock, 0, as_stream(s)>>>(a, dst, n);
+  return finish_launch();
 }
 int mnv_sub(const float* a, const float* b, float* c, size_t n, mnv_stream_t s) {
   return launch_ew<2>(a, b, nullptr, c, n, SubOp{}, as_stream(s));

@@ -335,6 +335,25 @@ class NArray:
         return NArray._act_back("mnv_relu_backward", diff, top, bottom)
 
     @staticmethod
+    def add_n(arrays):
+        """((a0 + a1) + a2) + ... in one pass (mnv_add_n): the bits of the chained `+`."""
+        arrays = list(arrays)
+        _check(len(arrays) >= 1 and all(a._shape == arrays[0]._shape for a in arrays), "inputs size mismatch")
+        if len(arrays) == 1:
+            return arrays[0]
+        dev = _rt.current_device()
+        out = NArray._new(arrays[0]._shape, dev)
+        done = 0
+        acc = None
+        while done < len(arrays):          # at most 8 sources per launch
+            chunk = ([acc] if acc is not None else []) + arrays[done:done + (7 if acc is not None else 8)]
+            done += len(chunk) - (1 if acc is not None else 0)
+            ptrs = (ctypes.c_void_p * len(chunk))(*[a._on(dev).data_ptr() for a in chunk])
+            NArray._call("mnv_add_n", dev, ptrs, len(chunk), out._t.data_ptr(), out.size, prof_args=(len(chunk), out.size))
+            acc = out
+        return out
+
+    @staticmethod
     def relu_back_tw(diff, top, conv_geo):
         """ReLU backward for a 4-D activation that a convolution of geometry `conv_geo` produced: same result as relu_back,
         and the result carries its channels-last twin (the top_diff twin that convolution's backward calls will ask for)."""

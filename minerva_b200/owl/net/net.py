@@ -483,11 +483,25 @@ class Net(object):
         # convention for relu / dropout) replaces the entry instead of adding to it, and only contributions of
         # different consumers of one blob version are summed -- what the reference's per-unit dicts do
         # (owl/owl/net/net.py:1102-1114).
-        sens = {}
+        sens = {}        # blob name -> list of contributions, summed left to right when the producer takes them
+        add_n = getattr(getattr(self.B.owl, "NArray", None), "add_n", None)
+
+        def take(name):
+            parts = sens.pop(name, None)
+            if not parts:
+                return None
+            if len(parts) == 1:
+                return parts[0]
+            if add_n is not None:          # one pass, the bits of the chained `+` (mnv_add_n)
+                return add_n(parts)
+            total = parts[0]
+            for v in parts[1:]:
+                total = total + v
+            return total
         for u in reversed(self.units):
             if isinstance(u, DataUnit):
                 continue
-            top_sens = {t: sens.pop(t, None) for t in u.top_names}
+            top_sens = {t: take(t) for t in u.top_names}
             if not isinstance(u, SoftmaxUnit) and any(v is None for v in top_sens.values()):
                 continue
             out = {}
@@ -495,7 +509,7 @@ class Net(object):
             for k, v in out.items():
                 if v is None:
                     continue
-                sens[k] = sens[k] + v if sens.get(k) is not None else v
+                sens.setdefault(k, []).append(v)
             if self.on_weight_grad is not None and isinstance(u, WeightedComputeUnit):
                 self.on_weight_grad(u)
 

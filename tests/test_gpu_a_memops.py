@@ -351,6 +351,23 @@ def test_conv_backward_bias(g, N, C, H, W):
         assert np.all(np.abs(g.host(db).astype(np.float64) - want) <= 1e-5 * l1)
 
 
+def test_add_n_is_the_chained_add(g):
+    """mnv_add_n: ((a0 + a1) + a2) + ... -- bit-identical to the reference's chain of Add ops, aligned and unaligned."""
+    import ctypes
+    for n in (1, 7, 4096, 100003):
+        for count in (1, 2, 4, 8):
+            srcs = [rng.normal(0, 1, n + 1).astype(np.float32) for _ in range(count)]
+            want = srcs[0].copy()
+            for v in srcs[1:]:
+                want = (want + v).astype(np.float32)
+            for off in (0, 1):
+                devs = [g.dev(v) for v in srcs]
+                out = g.empty(n + 1)
+                ptrs = (ctypes.c_void_p * count)(*[d[off:].data_ptr() for d in devs])
+                g.run("mnv_add_n", ptrs, count, out[off:], n)
+                g.assert_bits_equal(g.host(out)[off:off + n], want[off:off + n], "add_n %d x %d" % (count, n))
+
+
 def test_generators_and_fill(g):
     for n in (1, 5, 1000, 100003):
         out = g.empty(n + 1)
