@@ -2086,14 +2086,24 @@ static void plan_splits(GemmParams& p, size_t ws_bytes_for_partials) {
   p.splits = (p.k_stages + p.stages_per_split - 1) / p.stages_per_split;  // no empty split
 }
 // fraction of the machine's CTA slots the tile grid keeps busy over its whole run
-static double wave_fill(const GemmParams& p) {
+MNV_OPT g_opt_no_tail{0};    // 1: no tail split (tuning)
+// tail_ok: the caller K-splits a thin last wave over the idle CTAs (plan_tail), so that wave costs 1 / S of a wave plus
+// the partial round trip (taken as a tenth of a wave)
+static double wave_fill(const GemmParams& p, bool tail_ok = false) {
   long long ctas = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
   const int sms = p.tall == 2 ? sm_budget() / 2 : sm_budget();
   long long waves = (ctas + sms - 1) / sms;
+  const int rem = static_cast<int>(ctas % sms);
+  if (tail_ok && p.splits == 1 && ctas >= sms && rem > 0 && rem * 2 <= sms && !g_opt_no_tail.load()) {
+    int S = sms / rem;
+    if (S > 8) S = 8;
+    if (S > p.k_stages / 8) S = p.k_stages / 8;
+    if (S >= 2) return (static_cast<double>(ctas) / sms) / (static_cast<double>(ctas / sms) + 1.0 / S + 0.1);
+  }
   return static_cast<double>(ctas) / static_cast<double>(waves * sms);
 }
 
-static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_wide = false, bool allow_tall = false) {
+static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_wide = false, bool allow_tall = false, bool tail_ok = false) {
   p.m_tiles = (p.M + BM - 1) / BM;
   p.wide = 0; p.tall = 0; p.stages = kStages; p.stage_bytes = kStageBytes;
   int n_tiles, bn;
@@ -2118,7 +2128,7 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
   plan_splits(p, ws_bytes_for_partials);
   // The wide tile has a single TMEM accumulator, so its epilogue is not hidden behind the next tile's
   // mainloop: worth it only when a tile's mainloop is long (measured break-even ~70 k-stages).
-  if (p.wide && p.stages_per_split < 96) plan_tiles(p, ws_bytes_for_partials, false, allow_tall);
+  if (p.wide && p.stages_per_split < 96) plan_tiles(p, ws_bytes_for_partials, false, allow_tall, tail_ok);
   if (allow_tall && !g_opt_no_tall.load()) {
     // 256-row tile (all-TMA path): halves the B traffic per flop.  Like the wide tile it has no second accumulator
     // set, so it wants a long mainloop, and it must not cost machine fill.
@@ -2130,7 +2140,7 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
     if (q.bn < 16) q.bn = 16;
     q.n_tiles = (p.N + q.bn - 1) / q.bn;
     plan_splits(q, ws_bytes_for_partials);
-    if (q.stages_per_split >= g_opt_tall_min_stages.load() && (wave_fill(q) >= 0.85 || wave_fill(q) >= wave_fill(p))) {
+    if (q.stages_per_split >= g_opt_tall_min_stages.load() && (wave_fill(q, tail_ok) >= 0.85 || wave_fill(q, tail_ok) >= wave_fill(p, tail_ok))) {
       p = q;
       // the same 256-row tile on a CTA pair (cta_group::2): each CTA stages half of B, so bn is a multiple of 32
       if (g_opt_pair.load() && sm_budget() % 2 == 0) {
@@ -2150,7 +2160,6 @@ static void plan_tiles(GemmParams& p, size_t ws_bytes_for_partials, bool allow_w
 // Tail split (see GemmParams): when the tile grid ends in a last wave that fills at most half the machine, the tiles of
 // that wave are K-split over the idle CTAs.  Partials use the split-K layout partial[split][n][m] (only the tail tiles'
 // entries are touched); splitk_tail_reduce_kernel folds them.
-MNV_OPT g_opt_no_tail{0};    // 1: no tail split (tuning)
 static void plan_tail(GemmParams& p, void* ws, size_t ws_bytes) {
   p.tail_splits = 0;
   if (g_opt_no_tail.load() || p.splits != 1 || !ws) return;
@@ -2382,7 +2391,7 @@ static int conv_tma_fprop(const float* x, const float* w, long long w_sn, long l
     if (w_sc == 1 && w_sn == Ci && Ci % 4 == 0) b_direct = 1;
     else if (w_sn == 1 && w_sc == Co && Co % 32 == 0 && !g_opt_no_mn3.load()) b_direct = 2;
   }
-  plan_tiles(p, ws2_bytes, b_direct != 2, true);
+  plan_tiles(p, ws2_bytes, b_direct != 2, true, true);
   if (b_direct == 2) {      // MN-major B: boxes of 32 columns per CTA
     p.bn = (p.bn + 31) / 32 * 32;
     if (p.bn > BN_MAX) p.bn = BN_MAX;
