@@ -1790,29 +1790,41 @@ static bool make_im2col_tmap(CUtensorMap* tm, const float* x, int Cp, int W, int
 // TF32 is done by the TFLOAT32-typed tensor map).  Tiles go through shared memory so both sides stay coalesced.
 // RELU: the source is ReLU backward's result computed on the fly, v = act > 0 ? x : 0, also written in NCHW to `dx` (the
 // reference op's output): one pass (8 B read + 8 B written per element) instead of ReLU backward (12 B) plus this copy (8 B).
-template <bool RELU>
+// Pixels per tile = 32 * TWJ, chosen per plane size (nhwc_tile_j) so that the last tile of a plane is not mostly padding:
+// 13 x 13 = 169 pixels are one tile of 192 (88 % useful) instead of 128 + 41 (66 %), 14 x 14 one of 224, 28 x 28 five of 160.
+static int nhwc_tile_j(int HW) {
+  int best = 4;
+  long long best_cover = -1;
+  for (int j = 2; j <= 8; ++j) {
+    const long long tw = 32 * j, cover = (HW + tw - 1) / tw * tw;
+    if (best_cover < 0 || cover < best_cover || (cover == best_cover && j > best)) { best = j; best_cover = cover; }
+  }
+  return best;
+}
+template <bool RELU, int TWJ>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cp, int HW,
                                                            int tiles_c, int tiles_hw, long long total_tiles, float* __restrict__ tilesum,
-                                                           const float* __restrict__ act = nullptr, float* __restrict__ dx = nullptr) {
+                                                           const float* __restrict__ act, float* __restrict__ dx) {
   pdl_enter();
-  // tile = 32 channels x 128 pixels: 16 independent 128-byte-per-warp loads per thread before the barrier.
+  // tile = 32 channels x 32 * TWJ pixels: 4 * TWJ independent 128-byte-per-warp loads per thread before the barrier.
   // tilesum != null: the pass also leaves the sum of every (image, pixel tile, channel) in tilesum[(n * tiles_hw + th) * C + c]
   // -- for a top_diff that is ConvBackwardBias's per-tile partial, folded over (n, th) by rowsum_fold_kernel in a fixed order.
-  __shared__ float tile[32][129];
+  constexpr int TW = 32 * TWJ;
+  __shared__ float tile[32][TW + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
     const int tc = static_cast<int>(t % tiles_c);
     const long long r = t / tiles_c;
     const int th = static_cast<int>(r % tiles_hw);
     const size_t n = static_cast<size_t>(r / tiles_hw);
-    const int c0 = tc * 32, h0 = th * 128;
+    const int c0 = tc * 32, h0 = th * TW;
     const float* src = x + (n * C + c0) * HW + h0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = wid + 8 * i;
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < TWJ; ++j) {
         const int hw = lane + 32 * j;
         float v = 0.f;
         if (c0 + c < C && h0 + hw < HW) {
@@ -1837,13 +1849,23 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
     if (c0 + lane < Cp) {
       float* dst = y + (n * HW + h0) * Cp + c0 + lane;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 4 * TWJ; ++i) {
         const int hw = wid + 8 * i;
         if (h0 + hw < HW) dst[static_cast<size_t>(hw) * Cp] = tile[lane][hw];
       }
     }
     __syncthreads();
   }
+}
+template <bool RELU>
+static int launch_nhwc_t(const float* x, float* y, int N, int C, int Cp, int HW, cudaStream_t s, float* tilesum, const float* act, float* dx) {
+  const int twj = nhwc_tile_j(HW), tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 32 * twj - 1) / (32 * twj);
+  const long long total = static_cast<long long>(N) * tiles_c * tiles_hw, cap = static_cast<long long>(kNumSMs) * 16;
+  const dim3 grid(static_cast<unsigned>(total < cap ? total : cap));
+#define MNV_NHWC(J) case J: launch_pdl((nchw_to_nhwc_kernel<RELU, J>), grid, dim3(256), 0, s, x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum, act, dx); break;
+  switch (twj) { MNV_NHWC(2) MNV_NHWC(3) MNV_NHWC(4) MNV_NHWC(5) MNV_NHWC(6) MNV_NHWC(7) default: MNV_NHWC(8) }
+#undef MNV_NHWC
+  return finish_launch();
 }
 // B operand of the TMA-im2col convolutions: out[n][tap][c] (c < Kc = 32-channel chunks per tap, zero past C)
 //   = w[n*sn + c*sc + (flip ? ff-1-tap : tap)], TF32-rounded.
@@ -2320,12 +2342,9 @@ static bool fits_int(long long v) { return v > 0 && v < 0x7fffffffLL; }
 
 static size_t round256(size_t v) { return (v + 255) / 256 * 256; }
 static int launch_nhwc(const float* x, float* y, int N, int C, int Cp, int HW, cudaStream_t s, float* tilesum = nullptr) {
-  const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
-  const long long total = static_cast<long long>(N) * tiles_c * tiles_hw;
-  const long long cap = static_cast<long long>(kNumSMs) * 16;
-  launch_pdl((nchw_to_nhwc_kernel<false>), dim3(static_cast<unsigned>(total < cap ? total : cap)), dim3(256), 0, s, x, y, C, Cp, HW, tiles_c, tiles_hw, total, tilesum, nullptr, nullptr);
-  return finish_launch();
+  return launch_nhwc_t<false>(x, y, N, C, Cp, HW, s, tilesum, nullptr, nullptr);
 }
+static int nhwc_tiles_hw(int HW) { const int tw = 32 * nhwc_tile_j(HW); return (HW + tw - 1) / tw; }
 
 // Channels-last "twin" of an NCHW activation, owned by the CALLER (mnv_conv_twin_bytes): several calls of one training
 // step want the same copy (forward and backward-filter read x, backward-data and backward-filter read top_diff), so the
@@ -2339,9 +2358,9 @@ struct Twin {
   bool has_sums() const { return valid() && (*state & 2) != 0; }   // the per-tile channel sums behind the copy are filled too
 };
 // Layout of a twin buffer of mnv_conv_twin_bytes(): [n][hw][Cp] floats, then (256-byte aligned) the per-(image, pixel tile, channel)
-// sums a filling pass may leave for ConvBackwardBias: tilesum[(n * tiles_hw + th) * C + c], tiles of 128 pixels.
+// sums a filling pass may leave for ConvBackwardBias: tilesum[(n * tiles_hw + th) * C + c], tiles of 32 * nhwc_tile_j(HW) pixels.
 static size_t twin_copy_bytes(int N, int C, int HW) { return round256(static_cast<size_t>(N) * HW * ((C + 3) / 4 * 4) * sizeof(float)); }
-static size_t twin_sums_bytes(int N, int C, int HW) { return round256(static_cast<size_t>(N) * ((HW + 127) / 128) * C * sizeof(float)); }
+static size_t twin_sums_bytes(int N, int C, int HW) { return round256(static_cast<size_t>(N) * nhwc_tiles_hw(HW) * C * sizeof(float)); }
 
 // Cross-correlation of x[N][Ci][H][W] with `ff` taps as a GEMM whose two operands both arrive through TMA:
 //   A[m = (n,oh,ow)][k = (tap, c)]  channels-last copy of x through an im2col tensor map (no gather warps, padding
@@ -2668,12 +2687,8 @@ int mnv_relu_backward_tw(const float* top, const float* top_diff, float* bottom_
   const int Cp = (C + 3) / 4 * 4, HW = H * W;
   if (!twin || !twin_state || !fits_int(static_cast<long long>(N) * HW * Cp))    // no twin wanted: the plain op
     return mnv_relu_backward(top, top, top_diff, bottom_diff, N, C, H, W, stream);
-  const int tiles_c = (Cp + 31) / 32, tiles_hw = (HW + 127) / 128;
-  const long long total = static_cast<long long>(N) * tiles_c * tiles_hw, cap = static_cast<long long>(kNumSMs) * 16;
   float* tilesum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(twin) + twin_copy_bytes(N, C, HW));
-  launch_pdl((nchw_to_nhwc_kernel<true>), dim3(static_cast<unsigned>(total < cap ? total : cap)), dim3(256), 0, as_stream(stream), 
-      top_diff, twin, C, Cp, HW, tiles_c, tiles_hw, total, tilesum, top, bottom_diff);
-  int rc = finish_launch();
+  int rc = launch_nhwc_t<true>(top_diff, twin, N, C, Cp, HW, as_stream(stream), tilesum, top, bottom_diff);
   if (!rc) *twin_state = 3;     // copy + per-tile channel sums
   return rc;
 }
@@ -2877,7 +2892,7 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
      // 32 pixels).  The im2col walk and the rows of B wrap from one image into the next identically, so nothing is padded
      // per image, top_diff needs no re-pitch, and the two copies are the ones forward / backward-data use (twins).
     const int cpt = (Ci + BK - 1) / BK, Cp = (Ci + 3) / 4 * 4, Cop = (Co + 3) / 4 * 4;
-    const int tiles_hw = (P + 127) / 128;
+    const int tiles_hw = nhwc_tiles_hw(P);
     const bool geom_ok = cpt * BK * 2 <= Ci * 3 && ph <= 127 && pw <= 127 && fh - 1 - ph <= 128 && fw - 1 - pw <= 128 && sv <= 8 && sh <= 8 &&
                          fits_int(static_cast<long long>(N) * H * W * Cp) && fits_int(static_cast<long long>(N) * P * Cop);
     if (geom_ok && !(g_opt_no_tma_a.load() & 4) && !g_opt_no_nhwc_wgrad.load() && get_im2col_fn() && get_encode_fn()) {

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-for n in 8; do
+for n in ${NG:-8}; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02_bench_${n}gpu.json 2> gpurun_out/r02_bench_${n}gpu.err; echo rc=$?; tail -c 600 gpurun_out/r02_bench_${n}gpu.err
 python - <<PY
 import json
