@@ -63,7 +63,8 @@ int mnv_set_dependent_launch(int enabled);
 int mnv_add(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
 int mnv_sub(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
 /* dst = ((srcs[0] + srcs[1]) + srcs[2]) + ... : the bits of count - 1 chained mnv_add calls, in one pass.  `srcs` is a HOST
- * array of 1..8 device pointers.  owl.net sums the sensitivities of a blob with several consumers with it (net.py:1102-1114). */
+ * array of 1..8 device pointers; dst may be srcs[0] (the one sanctioned alias: an accumulation that continues a sum), no
+ * other overlap.  owl.net sums the sensitivities of a blob with several consumers with it (net.py:1102-1114). */
 int mnv_add_n(const float* const* srcs, int count, float* dst, size_t n, mnv_stream_t stream);
 int mnv_dot_mult(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);
 int mnv_dot_div(const float* a, const float* b, float* c, size_t n, mnv_stream_t stream);

@@ -113,12 +113,12 @@ int launch_ew(const float* a, const float* b, const float* c, float* out, size_t
 // 3 * (count - 1)).  owl.net sums the sensitivities a blob receives from its consumers with it (an inception input has four).
 struct AddNArgs { const float* src[8]; int count; };
 template <bool VEC>
-__global__ void __launch_bounds__(kBlock) add_n_kernel(const AddNArgs a, float* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(kBlock) add_n_kernel(const AddNArgs a, float* out, size_t n) {   // out may be src[0] (plain loads, no restrict)
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   if (VEC) {
     const size_t n4 = n / 4;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      float4 acc = __ldg(reinterpret_cast<const float4*>(a.src[0]) + i);
+      float4 acc = reinterpret_cast<const float4*>(a.src[0])[i];
 #pragma unroll 8
       for (int j = 1; j < a.count; ++j) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.src[j]) + i);
