@@ -76,6 +76,9 @@ class NetTrainer(object):
         if self.peer is not None:
             try:
                 self.peer.finish_step()
+                if self.peer.small and "one all-reduce" not in self.merge_kind:
+                    self.merge_kind = ("gradients produced in place in one flat buffer, merged by one all-reduce after backward "
+                                       "(whole gradient <= %d MB: the bucketed peer exchange costs more than the step)" % (self.peer.SMALL_BYTES >> 20))
             except Exception as ex:
                 if self.peer.flat is not None:
                     raise
