@@ -364,6 +364,10 @@ __global__ void __launch_bounds__(kBlock) avgpool_bwd_smem_kernel(const float* _
     float* sdy = sm + misalign4(dysrc);
     stage_in(sdy, dysrc, cnt * HoWo);
     __syncthreads();
+    // each term of a bottom element's sum is dy / (wh * ww), rounded: divide every pooled element once here (an IEEE
+    // division is ~25 instructions) instead of once per window that contains a bottom element -- the same terms, the same bits
+    for (int e = threadIdx.x; e < cnt * HoWo; e += blockDim.x) sdy[e] = __fdiv_rn(sdy[e], div);
+    __syncthreads();
     float* dxp = dx + static_cast<size_t>(p0) * HW;
     for (int e = threadIdx.x; e < cnt * HW; e += blockDim.x) {
       int gq = fdiv(e, d_hw), r = e - gq * HW, h = fdiv(r, d_w), w = r - h * g.W;
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(kBlock) avgpool_bwd_smem_kernel(const float* _
       int j_hi = min(static_cast<int>(fdiv(w + g.pw, d_sh)), g.Wo - 1);
       float acc = 0.f;
       for (int i = i_lo; i <= i_hi; ++i)
-        for (int j = j_lo; j <= j_hi; ++j) acc = __fadd_rn(acc, __fdiv_rn(dyp[i * g.Wo + j], div));
+        for (int j = j_lo; j <= j_hi; ++j) acc = __fadd_rn(acc, dyp[i * g.Wo + j]);
       dxp[e] = acc;
     }
     __syncthreads();
