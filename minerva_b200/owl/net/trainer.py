@@ -12,6 +12,8 @@ import time
 
 
 class NetTrainer(object):
+    BOUND_GRAPHS = 2     # graph mode: recordings bound to recurring input arrays (a double-buffered feed has two)
+
     def __init__(self, net, dist=None, fused_update=True, merge="auto", graph=False):
         """dist: an initialised torch.distributed module (or None for 1 GPU).
         graph: record the whole step (forward, backward, loss reduction, update) into a CUDA graph once and replay it
@@ -28,7 +30,10 @@ class NetTrainer(object):
         self.peer = None
         self.merge_kind = "none (1 GPU)"
         self.graph = bool(graph)
-        self._g = None                   # recorded step: dict(graph, key, seeds, data, label, launches, loss)
+        self._g = None                   # recorded step: dict(graph, key, seeds, data, label, loss), input copied in
+        self._bound = []                 # recordings bound to recurring input arrays (no input copy)
+        self._seen = []                  # the last few (data, label) pairs that went through the copying recording
+        self._bound_made = 0
         self.graph_replays = 0           # replays so far; launches they stand for = graph_launches_per_step each
         self.graph_launches_per_step = 0
         self.loss_device = None          # graph mode: (1-element NArray of sum(ln(y) o label), batch) of the last step
@@ -102,7 +107,10 @@ class NetTrainer(object):
         What varies between steps stays outside the recording: the input batch is copied into the recorded input arrays,
         the dropout keys are read from a device word stored before every replay (_runtime.GraphSeeds), and a change of the
         learning rate / momentum / weight decay / batch size records a new graph.  Same kernels, same order, same bits as
-        the eager step."""
+        the eager step.
+        Input arrays that come back (the two device slots of a double-buffered feed) get a recording of their own the second
+        time they are seen -- bound to those arrays, so their steps need no input copy (158 MB per AlexNet step, 0.11 ms); at
+        most BOUND_GRAPHS of them.  Every recording updates the same weights; `loss_device` is the replayed recording's."""
         import torch
         import minerva_b200.owl._runtime as rt
         net = self.net
@@ -120,7 +128,29 @@ class NetTrainer(object):
         else:
             data, label = du.data, du.label
         key = (net.current_lr, net.base_weight_decay, net.momentum, net.batch_size, tuple(data.shape), tuple(label.shape), id(dev))
-        if self._g is None or self._g["key"] != key:
+        if self._g is not None and self._g["key"] != key:
+            self._g, self._bound, self._seen, self._bound_made = None, [], [], 0     # hyper-parameters changed: every recording is stale
+        for b in self._bound:                                        # a recording bound to exactly these input arrays
+            if b["data"] is data and b["label"] is label:
+                b["seeds"].arm()
+                b["graph"].replay()
+                self.loss_device = b["loss"]
+                self.graph_replays += 1
+                return
+        if self._g is not None and data is not self._g["data"] and self._bound_made < 4 * self.BOUND_GRAPHS:
+            if any(d is data and l is label for d, l in self._seen):
+                if len(self._bound) >= self.BOUND_GRAPHS:            # a new feed took over: its slots replace the oldest ones
+                    self._bound.pop(0)
+                self._bound_made += 1                                # (bounded: rotating arrays must not re-record forever)
+                self._bound.append(self._record(key, data, label, dev, bind=True))
+                b = self._bound[-1]
+                b["seeds"].arm()
+                b["graph"].replay()
+                self.loss_device = b["loss"]
+                self.graph_replays += 1
+                return
+            self._seen = (self._seen + [(data, label)])[-4:]
+        if self._g is None:
             if any(net.units[uid].weight is None for uid in net.get_weighted_unit_ids()):
                 # the very first step runs eagerly: lazy initialisation (weight fillers, kernel attributes, driver entry
                 # points) is not recordable; the next call records
@@ -135,8 +165,9 @@ class NetTrainer(object):
                     if feed is not None:
                         du.feed = feed
                 return
-            self._record(key, data, label, dev)
+            self._g = self._record(key, data, label, dev)
         g = self._g
+        self.loss_device = g["loss"]
         if data is not g["data"]:
             g["data"].as_torch().copy_(data.as_torch(), non_blocking=True)
         if label is not g["label"]:
@@ -145,15 +176,15 @@ class NetTrainer(object):
         g["graph"].replay()
         self.graph_replays += 1
 
-    def _record(self, key, data, label, dev):
+    def _record(self, key, data, label, dev, bind=False):
+        """-> the recording (dict).  bind: the graph reads `data` / `label` themselves instead of arrays of its own."""
         import torch
         import minerva_b200.owl._runtime as rt
         from minerva_b200 import _lib
         net = self.net
         du = net.get_data_unit()
         owl = net.B.owl
-        self._g = None                   # drop the previous recording (and its pool) first
-        static_data, static_label = owl.zeros(list(data.shape)), owl.zeros(list(label.shape))
+        static_data, static_label = (data, label) if bind else (owl.zeros(list(data.shape)), owl.zeros(list(label.shape)))
         seeds = rt.GraphSeeds(dev)
         feed = getattr(du, "feed", None)
         dev.stream.synchronize()
@@ -178,8 +209,7 @@ class NetTrainer(object):
                 du.feed = feed
         rt.set_device(rt._devices.index(dev))      # torch.cuda.graph restores ITS entry stream; make the device's current again
         self.graph_launches_per_step = int(lib.mnv_launch_count() - n0)
-        self.loss_device = loss
-        self._g = dict(graph=graph, key=key, seeds=seeds, data=static_data, label=static_label)
+        return dict(graph=graph, key=key, seeds=seeds, data=static_data, label=static_label, loss=loss)
 
     def _eager_step(self):
         net = self.net

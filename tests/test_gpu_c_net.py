@@ -201,9 +201,11 @@ def test_graph_step_with_feed(gpu_owl):
         fu.B = old.B
         net.units[0] = fu
         tr = NetTrainer(net, None, graph=graph)
-        for _ in range(4):
+        for _ in range(9):
             tr.step()
         fu.close()
+        if graph:      # step 1 eager, 2-3 through the copying recording, then one recording bound to each of the feed's two device slots
+            assert len(tr._bound) == 2 and tr.graph_replays == 8
         res.append([net.units[uid].weight.to_numpy() for uid in net.get_weighted_unit_ids()])
     for a, b in zip(*res):
         np.testing.assert_array_equal(a, b)
