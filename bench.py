@@ -174,6 +174,8 @@ def op_work(name, a):
         return "hbm", 12.0 * a[3]
     if name == "mnv_accumulate":
         return "hbm", 12.0 * a[2]
+    if name == "mnv_copy_strided_n":          # prof_args = (count, elements)
+        return "hbm", 8.0 * a[1]
     if name == "mnv_add_n":                   # prof_args = (count, n)
         return "hbm", 4.0 * (a[0] + 1) * a[1]
     if name == "mnv_relu_backward_tw":        # top, top_diff, bottom_diff, N, C, H, W, ...: 8 B read + 8 B written (NCHW result + its channels-last twin)

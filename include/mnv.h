@@ -123,6 +123,14 @@ int mnv_transpose(const float* a, float* c, int m, int n, mnv_stream_t stream);
  * src + b*src_stride to dst + b*dst_stride (strides in floats). */
 int mnv_copy_strided(const float* src, float* dst, size_t inner, size_t outer,
                      size_t src_stride, size_t dst_stride, mnv_stream_t stream);
+/* up to 8 such copies that share `outer`, in one launch: Concat of up to 8 arrays (cuda.cpp:75-108 issues one copy per
+ * input) and the Slices that take a concatenated gradient apart (host array of segments). */
+typedef struct mnv_copy_seg_t {
+  const float* src;
+  float* dst;
+  size_t inner, src_stride, dst_stride;
+} mnv_copy_seg_t;
+int mnv_copy_strided_n(const mnv_copy_seg_t* segs, int count, size_t outer, mnv_stream_t stream);
 /* Select (cuda_perform.h:74): dst{rows,n_idx} = columns `indices` of src{rows,cols}.  The
  * reference passes a host pointer to the device (cuda_perform.cu:676); here `indices` is a
  * device array of n_idx ints. */

@@ -186,6 +186,31 @@ __global__ void __launch_bounds__(kBlock) copy_strided_kernel(const float* __res
   }
 }
 
+// up to 8 strided block copies that share `outer` in one launch (blockIdx.y = the copy): the four inputs of an inception
+// concat, or the four slices of its gradient, are one kernel instead of four
+struct CopySegs { const float* src[8]; float* dst[8]; size_t inner[8], src_stride[8], dst_stride[8]; int vec[8]; };
+__global__ void __launch_bounds__(kBlock) copy_strided_n_kernel(const CopySegs sg, size_t outer) {
+  const int j = blockIdx.y;
+  const float* __restrict__ src = sg.src[j];
+  float* __restrict__ dst = sg.dst[j];
+  const size_t inner = sg.inner[j], ss = sg.src_stride[j], ds = sg.dst_stride[j];
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (sg.vec[j]) {
+    const size_t inner4 = inner / 4, total = inner4 * outer;
+    for (size_t e = tid; e < total; e += stride) {
+      const size_t b = e / inner4, k = e - b * inner4;
+      reinterpret_cast<float4*>(dst + b * ds)[k] = __ldg(reinterpret_cast<const float4*>(src + b * ss) + k);
+    }
+  } else {
+    const size_t total = inner * outer;
+    for (size_t e = tid; e < total; e += stride) {
+      const size_t b = e / inner, k = e - b * inner;
+      dst[b * ds + k] = __ldg(src + b * ss + k);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) select_kernel(float* __restrict__ dst, const float* __restrict__ src, const int* __restrict__ indices,
                                                         size_t n_idx, size_t rows) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -252,6 +277,30 @@ int mnv_copy_strided(const float* src, float* dst, size_t inner, size_t outer, s
   int vec = aligned16(src) && aligned16(dst) && inner % 4 == 0 && src_stride % 4 == 0 && dst_stride % 4 == 0;
   size_t work = vec ? inner / 4 * outer : inner * outer;
   copy_strided_kernel<<<stream_grid(work), kBlock, 0, as_stream(s)>>>(src, dst, inner, outer, src_stride, dst_stride, vec);
+  return finish_launch();
+}
+
+int mnv_copy_strided_n(const mnv_copy_seg_t* segs, int count, size_t outer, mnv_stream_t s) {
+  if (count < 0 || count > 8) return MNV_EINVAL;
+  if (count == 0 || outer == 0) return MNV_OK;
+  if (!segs) return MNV_EINVAL;
+  CopySegs sg;
+  size_t max_work = 0;
+  int n = 0;
+  for (int j = 0; j < count; ++j) {
+    const mnv_copy_seg_t& g = segs[j];
+    if (g.inner == 0) continue;
+    if (!g.src || !g.dst) return MNV_EINVAL;
+    sg.src[n] = g.src; sg.dst[n] = g.dst; sg.inner[n] = g.inner; sg.src_stride[n] = g.src_stride; sg.dst_stride[n] = g.dst_stride;
+    sg.vec[n] = aligned16(g.src) && aligned16(g.dst) && g.inner % 4 == 0 && g.src_stride % 4 == 0 && g.dst_stride % 4 == 0;
+    const size_t work = sg.vec[n] ? g.inner / 4 * outer : g.inner * outer;
+    if (work > max_work) max_work = work;
+    ++n;
+  }
+  if (n == 0) return MNV_OK;
+  int gx = stream_grid(max_work);
+  if (gx * n > kNumSMs * kBlocksPerSM) gx = (kNumSMs * kBlocksPerSM + n - 1) / n;     // one wave over all the copies together
+  copy_strided_n_kernel<<<dim3(gx, n), kBlock, 0, as_stream(s)>>>(sg, outer);
   return finish_launch();
 }
 

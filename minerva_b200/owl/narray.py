@@ -706,13 +706,50 @@ class NArray:
         inner_unit = _prod(oshape[:dim])
         outer = _prod(oshape[dim + 1:])
         dst_stride = inner_unit * oshape[dim]
-        off = 0
+        off, segs = 0, []
         for a in arrays:
             inner = inner_unit * a._shape[dim]
-            NArray._call("mnv_copy_strided", dev, a._on(dev).data_ptr(), out._t.data_ptr() + 4 * off, inner, outer,
-                         inner, dst_stride)
+            segs.append((a._on(dev).data_ptr(), out._t.data_ptr() + 4 * off, inner, inner, dst_stride))
             off += inner
+        NArray._copy_segs(dev, segs, outer)
         return out
+
+    class _CopySeg(ctypes.Structure):      # mnv_copy_seg_t (include/mnv.h)
+        _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("inner", ctypes.c_size_t), ("src_stride", ctypes.c_size_t),
+                    ("dst_stride", ctypes.c_size_t)]
+
+    @staticmethod
+    def _copy_segs(dev, segs, outer):
+        """Strided block copies sharing `outer`, eight per launch (mnv_copy_strided_n)."""
+        for i in range(0, len(segs), 8):
+            chunk = segs[i:i + 8]
+            if len(chunk) == 1:
+                src, dst, inner, ss, ds = chunk[0]
+                NArray._call("mnv_copy_strided", dev, src, dst, inner, outer, ss, ds)
+                continue
+            tab = (NArray._CopySeg * len(chunk))(*[NArray._CopySeg(*c) for c in chunk])
+            NArray._call("mnv_copy_strided_n", dev, tab, len(chunk), outer, prof_args=(len(chunk), sum(c[2] for c in chunk) * outer))
+
+    @staticmethod
+    def split(src, dim, counts):
+        """The consecutive slices of `src` along `dim` with the given extents (the pieces a Concat put together), in one launch."""
+        nd = len(src._shape)
+        _check(nd - dim <= 2, "Currently only support slice on the last two dims!")
+        _check(sum(counts) == src._shape[dim], "split extents must cover the dimension")
+        dev = _rt.current_device()
+        inner_unit = _prod(src._shape[:dim])
+        outer = _prod(src._shape[dim + 1:])
+        outs, segs, st = [], [], 0
+        base = src._on(dev).data_ptr()
+        for cnt in counts:
+            oshape = list(src._shape)
+            oshape[dim] = cnt
+            o = NArray._new(oshape, dev)
+            segs.append((base + 4 * inner_unit * st, o._t.data_ptr(), inner_unit * cnt, inner_unit * src._shape[dim], inner_unit * cnt))
+            outs.append(o)
+            st += cnt
+        NArray._copy_segs(dev, segs, outer)
+        return outs
 
     @staticmethod
     def slice(src, slice_dim, st_off, slice_count):

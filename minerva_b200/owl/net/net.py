@@ -247,9 +247,15 @@ class ConcatUnit(ComputeUnit):
         self.out = to_top[self.top_names[0]]
 
     def backward(self, from_top, to_btm, phase):
+        top = from_top[self.top_names[0]]
+        split = getattr(getattr(self.B.owl, "NArray", None), "split", None)
+        if split is not None:            # every slice in one launch (mnv_copy_strided_n)
+            for b, piece in zip(self.btm_names, split(top, self.dim, self.slice_count)):
+                to_btm[b] = piece
+            return
         st = 0
         for b, cnt in zip(self.btm_names, self.slice_count):
-            to_btm[b] = self.B.owl.slice(from_top[self.top_names[0]], self.dim, st, cnt)
+            to_btm[b] = self.B.owl.slice(top, self.dim, st, cnt)
             st += cnt
 
 

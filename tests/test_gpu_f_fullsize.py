@@ -213,6 +213,14 @@ def test_concat_slice_full_size(gpu_owl_f):
     for p, c in zip(parts, chans):
         np.testing.assert_array_equal(owl.slice(cat, 2, off, c).to_numpy(), p)
         off += c
+    # all four slices in one launch (mnv_copy_strided_n), what ConcatUnit.backward uses; odd extents take the scalar path
+    for piece, p in zip(owl.NArray.split(cat, 2, list(chans)), parts):
+        np.testing.assert_array_equal(piece.to_numpy(), p)
+    odd = [rs.standard_normal((3, c, 5, 7)).astype(np.float32) for c in (3, 1, 6)]
+    cat2 = owl.concat([owl.from_numpy(p) for p in odd], 2)
+    np.testing.assert_array_equal(cat2.to_numpy(), np.concatenate(odd, 1))
+    for piece, p in zip(owl.NArray.split(cat2, 2, [3, 1, 6]), odd):
+        np.testing.assert_array_equal(piece.to_numpy(), p)
 
 
 @pytest.fixture(scope="module")
