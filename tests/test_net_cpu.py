@@ -283,3 +283,42 @@ def test_xavier_seeds_and_rank_salt():
     owl_cpu.set_rank_salt(0)
     np.testing.assert_array_equal(weights[0], weights[1])
     assert not np.array_equal(masks[0], masks[1])
+
+
+def test_graph_seeds_reproduce_next_seed():
+    """_runtime.GraphSeeds (keys of a step recorded into a CUDA graph): word + k * stride, xor salt == what next_seed() hands
+    the k-th generator call of that step; arm() leaves the host counter where the eager step would have left it."""
+    import torch
+    from minerva_b200.owl import _runtime as rt
+
+    class Dev:
+        device = torch.device("cpu")
+    saved = list(rt._seed)
+    try:
+        for salt in (0, 5):
+            rt.set_seed(0xC0FFEE)
+            rt.set_rank_salt(salt)
+            rt._seed[1] = 0xFFFFFFF0            # the 32-bit products wrap inside the step
+            eager = [rt.next_seed(salted=True) for _ in range(6)]
+            after = rt._seed[1]
+            rt._seed[1] = 0xFFFFFFF0
+            gs = rt.GraphSeeds(Dev())
+            recorded = [gs.next(salted=True) for _ in range(6)]     # what the recording bakes in: (add, xor) per call
+            gs.arm()
+            word = int(gs.word[0]) & 0xFFFFFFFF
+            assert [((word + add) & 0xFFFFFFFF) ^ xor for add, xor in recorded] == eager
+            assert rt._seed[1] == after
+    finally:
+        rt._seed[:] = saved
+
+
+def test_small_nets_merge_with_one_all_reduce():
+    """merge.plan_layout + the SMALL_BYTES rule: LeNet / the MLP (1-2 MB of gradient) take the single all-reduce, AlexNet the
+    bucketed peer exchange."""
+    from minerva_b200.owl.net.merge import plan_layout, PeerGradMerge
+    lenet = [("ip2", 5000, 10), ("ip1", 400000, 500), ("conv2", 25000, 50), ("conv1", 500, 20)]
+    _, _, total = plan_layout(lenet, 8, 1)
+    assert total * 4 <= PeerGradMerge.SMALL_BYTES
+    alex = [("fc8", 4096000, 1000), ("fc7", 16777216, 4096), ("fc6", 37748736, 4096), ("conv5", 884736, 256), ("conv1", 34848, 96)]
+    _, buckets, total = plan_layout(alex, 8, 2)
+    assert total * 4 > PeerGradMerge.SMALL_BYTES and len(buckets) == 3
