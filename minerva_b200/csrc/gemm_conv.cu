@@ -1022,7 +1022,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
     if (BTMA && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       // the whole box(es), OOB rows/cols arrive as zeros
-      const uint32_t bytes = static_cast<uint32_t>(bn_cta) * BK * 4 + (AM == A_TMA ? kATile : 0);
+#ifdef MNV_TUNING
+      // diagnostic (tuning build only): pf_dist = -1 / -2 / -3 skips the A / B / both copies -- results are garbage, the time
+      // says which operand stream bounds the mainloop
+      const int dbg_skip = p.pf_dist < 0 ? -p.pf_dist : 0;
+#else
+      constexpr int dbg_skip = 0;
+#endif
+      const uint32_t bytes = ((dbg_skip & 2) ? 0u : static_cast<uint32_t>(bn_cta) * BK * 4) + ((AM == A_TMA && !(dbg_skip & 1)) ? kATile : 0);
       // CTA pair: where this CTA's copies count their bytes -- the leader's barrier (cta_group::2 copy forms) or its own
       const bool remote_bar = PAIR && p.pair_remote;
       const uint32_t full_ld0 = remote_bar ? mapa_u32(full0, 0) : full0;
@@ -1084,7 +1091,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           if (!remote_bar) mbar_arrive_expect_tx(full0 + 8 * stage, bytes);
           else if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * bytes);      // both CTAs' copies land on the leader's barrier
           const uint32_t fbar = full_ld0 + 8 * stage;
-          if (AM == A_TMA) {
+          if (AM == A_TMA && !(dbg_skip & 1)) {
             const uint32_t a_dst = smem_base + stage * kSBytes, bar = fbar;
             if (p.a_mode == TMA_A_IM2COL_K) {
               const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
@@ -1113,6 +1120,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
           }
           const uint32_t dst = smem_base + stage * kSBytes + kATile;
           const int halves = WIDE ? 2 : 1, rows = WIDE ? p.bn / 2 : p.bn;   // a TMA box has at most 256 rows
+          if (dbg_skip & 2) {
+          } else
           if (AM == A_TMA && p.b_im2col) {   // transposed orientation: the n-tile's bn pixels x 32 channels of tap (kh, kw)
             const int n_first = t.nt * p.bn, img = n_first / p.P, pix = n_first - img * p.P, oh = pix / p.Wo;
             const int tap = ks / p.cpt, cc = ks - tap * p.cpt, kh = tap / p.fw;
