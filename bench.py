@@ -484,9 +484,23 @@ def measure(C, args, wl_key, headline):
         launches = lib.mnv_launch_count() - l0 + (trainer.graph_replays - r0) * trainer.graph_launches_per_step
         return C.max_over_ranks(e0.elapsed_time(e1)), t_host, int(launches)
 
-    for _ in range(max(3, args.warmup)):
-        trainer.step()
-    C.sync_all()
+    try:
+        for _ in range(max(3, args.warmup)):
+            trainer.step()
+        C.sync_all()
+    except Exception as ex:
+        if not use_graph:
+            raise
+        # the recording is an optimisation of the launch path, not the product: report why it failed and time the
+        # call-by-call step (same kernels, same results)
+        print("bench.py: CUDA-graph recording failed (%r); timing the call-by-call step" % (ex,), file=sys.stderr)
+        res["cuda_graph"] = "failed: %r" % (ex,)
+        use_graph = False
+        trainer.graph = False
+        torch.cuda.synchronize()
+        for _ in range(max(3, args.warmup)):
+            trainer.step()
+        C.sync_all()
     if world > 1:
         res["merge_check"] = merge_check(C, net, trainer)
         C.sync_all()
@@ -760,11 +774,11 @@ def main():
                        "gradient_merge": head["gradient_merge"],
                        "launch": ("the whole step (forward, backward, loss reduction, update: %d kernel launches) recorded once into a CUDA "
                                   "graph and replayed; `eager` = the same steps launched call by call" % head.get("launches_per_graph_replay", 0))
-                                 if head.get("cuda_graph") else "every C-ABI call launched from Python",
+                                 if head.get("cuda_graph") is True else "every C-ABI call launched from Python",
                        **({"gradient_merge_note": head["gradient_merge_note"]} if "gradient_merge_note" in head else {}),
                        **({"tuning": args.mnv_opt} if args.mnv_opt else {})},
             "clocks": head.get("clocks"), "gpu_launches": head["gpu_launches"], "host_enqueue_ms_per_step": head["host_enqueue_ms_per_step"], "loss": head["loss"],
-            "cuda_graph": head.get("cuda_graph", False), "eager": head.get("eager"),
+            "cuda_graph": head.get("cuda_graph", False), "eager": head.get("eager"),   # cuda_graph: True, False, or "failed: ..." (then timed call by call)
             "e2e": head.get("e2e"), "roofline": roofline, "cpu_baseline": cpu_baseline, "op_table": optable,
             "other_configs": others, "cpu_reference_ops": cpu_ops,
             "peaks": {k: pk.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
