@@ -9,6 +9,11 @@ import minerva_b200.owl as owl
 import minerva_b200.owl.net as onet
 from minerva_b200.owl import _runtime as rt
 name = sys.argv[1] if len(sys.argv) > 1 else "googlenet"
+if len(sys.argv) > 2:      # KEY=INT tuning options: the whole process runs on the tuning build of the library
+    from minerva_b200 import _lib
+    lib = _lib.use_tuning()
+    for kv in sys.argv[2:]:
+        lib.mnv_debug_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1]))
 wl = bench.WORKLOADS[name]
 owl.set_device(owl.create_gpu_device(0))
 owl.set_seed(1)
