@@ -983,7 +983,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_kernel(const __grid_con
             if (PAIR) umma_tf32_2sm(tmem_d, adesc, bdesc, idesc, acc);
             else umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
             if (WIDE)   // second half of the columns: same A tile, B rows bnh.., TMEM columns bnh..
-              umma_tf32(tmem_d + bnh, adesc, make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
+              umma_tf32(tmem_d + bnh, adesc, b_mn ? make_sw128_desc_mn(b_addr + bnh * 128 + kk * 1024) : make_sw128_desc(b_addr + bnh * 128 + kk * 32), idesc, acc);
             if (TALL)   // rows 128..255: second A half, same B tile, second accumulator
               umma_tf32(tmem_d + BN_MAX, a_mn ? make_sw128_desc_mn(a_addr + kABytes + kk * 1024) : make_sw128_desc(a_addr + kABytes + kk * 32),
                         bdesc, idesc, acc);
@@ -1684,6 +1684,7 @@ MNV_OPT g_opt_no_transposed{0};  // 1: narrow-output convolutions keep the D[pix
 // signalling the leader's barrier, the CUTLASS protocol) vs 686 (local barriers + a forwarded arrive); conv4 forward 0.233 ms vs
 // 0.314; conv4 backward-filter 0.315 vs 0.534.  With tf32 an instruction covers K = 8 (32 bytes), so a k-stage is four paired
 // instructions plus per-copy / per-stage cross-SM signalling; the halved B bytes do not buy that back.  DESIGN.md 5.1d.
+MNV_OPT g_opt_wgrad_wide{1};    // 0: channels-last backward-filter never takes the wide (128 x 384) tile (tuning)
 MNV_OPT g_opt_no_pointwise{0};  // 1: 1x1 convolutions through the im2col map and the packed filter like every other geometry (tuning)
 MNV_OPT g_opt_pair_remote{1};   // CTA pair: 1 = the peer's copies count their bytes on the leader's barrier (cta_group::2 copy forms),
                                 // 0 = every copy signals its own CTA's barrier and the peer forwards one arrive per stage
@@ -1746,7 +1747,7 @@ static bool make_a_mn_tmap(CUtensorMap* tm, const float* a, int M, int K, int ld
 // columns are read without a bound on m, so the caller guarantees round32(M) <= ld (rows past M are never stored).
 static bool make_mn3_tmap(CUtensorMap* tm, const float* a, int M, int K, int ld, int groups) {
   EncodeTiledFn fn = get_encode_fn();
-  if (!fn || groups < 1 || groups > 8 || (M + 31) / 32 * 32 > ld) return false;
+  if (!fn || groups < 1 || groups > 12 || (M + 31) / 32 * 32 > ld) return false;
   cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(K), static_cast<cuuint64_t>((M + 31) / 32)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * sizeof(float), 32 * sizeof(float)};
   cuuint32_t box[3] = {32, BK, static_cast<cuuint32_t>(groups)};
@@ -2565,6 +2566,7 @@ __attribute__((visibility("default"))) int mnv_debug_set_option(const char* key,
   if (k == "no_mn3") return g_opt_no_mn3.exchange(value);
   if (k == "pair") return g_opt_pair.exchange(value);
   if (k == "no_pointwise") return g_opt_no_pointwise.exchange(value);
+  if (k == "wgrad_wide") return g_opt_wgrad_wide.exchange(value);
   if (k == "pair_remote") return g_opt_pair_remote.exchange(value);
   if (k == "no_transposed") return g_opt_no_transposed.exchange(value);
   return -1;
@@ -2919,9 +2921,14 @@ static int conv_backward_filter_impl(const float* bottom, const float* top_diff,
         GemmParams q = p;
         q.a = xh; q.b = dyh; q.M = fh * fw * cpt * BK; q.a_mode = TMA_A_IM2COL_MN; q.b_mn = 1; q.cpt = cpt; q.out_mode = 1; q.spi = 0;
         q.P = q.M; q.col_stride = static_cast<long long>(Ci) * fh * fw; q.ldb = Cop; q.b_vec = 1;
-        plan_tiles(q, ws_left, false, true);
+        // More than 256 filters (conv3 / conv4: 384): the wide 128 x 384 tile (two UMMA halves share the A tile, B = one 3-D box
+        // of 12 slabs) issues 4 im2col boxes per 128 x 384 x 32 of MMA work where the tall 256 x 192 tile issues 8 -- this path
+        // is bound by its A boxes: conv3 backward-filter 0.175 -> 0.137 ms, conv4 0.268 -> 0.210.
+        const bool try_wide = g_opt_wgrad_wide.load() && !g_opt_no_mn3.load() && Co > BN_MAX && Cop % 32 == 0;
+        plan_tiles(q, ws_left, try_wide, !try_wide);
+        if (try_wide && !q.wide) plan_tiles(q, ws_left, false, true);     // mainloop too short for the single-accumulator wide tile
         q.bn = q.tall == 2 ? (q.bn + 63) / 64 * 64 : (q.bn + 31) / 32 * 32;   // MN-major B: boxes of 32 columns (per CTA of a pair)
-        if (q.bn > BN_MAX) q.bn = BN_MAX;
+        if (q.bn > BN_MAX && !q.wide) q.bn = BN_MAX;
         q.n_tiles = (q.N + q.bn - 1) / q.bn;
         plan_splits(q, ws_left);
         q.partial = q.splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;

@@ -24,7 +24,7 @@ def stream():
 
 # Alternate kernel paths are forced through the TUNING build (include/mnv_debug.h); while any option is off its
 # default, run() routes calls there, otherwise through the product library.
-_OPT_DEFAULTS = {"tall_min_stages": 32, "tma_tf32": 1, "wait_hint": 100, "sm_budget": 148, "pair_remote": 1}
+_OPT_DEFAULTS = {"tall_min_stages": 32, "tma_tf32": 1, "wait_hint": 100, "sm_budget": 148, "pair_remote": 1, "wgrad_wide": 1}
 _nondefault = {}
 
 

@@ -150,6 +150,7 @@ TMA_CASES = [
     (2, 96, 64, 27, 27, 2, 2, 1, 1, 5, 5),      # AlexNet conv2 channels: 256-row tiles for backward-data (Co <= 128)
     (2, 384, 384, 13, 13, 1, 1, 1, 1, 3, 3),    # AlexNet conv4: 108 k-stages, wide (384-column) tile
     (5, 160, 300, 7, 7, 1, 1, 1, 1, 3, 3),
+    (20, 64, 320, 14, 14, 1, 1, 1, 1, 3, 3),    # 320 filters, 122 k-stages of backward-filter: the wide MN-major tile when asked for
     # 80..128 filters with enough pixel tiles: the transposed orientation D[co][pixel] (im2col operand as B)
     (40, 64, 96, 28, 28, 1, 1, 1, 1, 3, 3),     # forward transposed (Co = 96); 31360 pixels = 123 tiles, image boundaries inside tiles
     (33, 32, 128, 27, 25, 0, 0, 1, 1, 1, 1),    # 1x1, Co = 128, odd plane size
@@ -167,6 +168,7 @@ OPERAND_PATHS = [("gather", {"no_tma_a": 7}), ("tma", {"force_tma_a": 1, "no_tal
                  # the CTA pair (tcgen05.mma.cta_group::2; built, measured slower, off by default), both hand-over protocols
                  ("tma+pair", {"force_tma_a": 1, "pair": 1, "tall_min_stages": 4}),
                  ("tma+pair, forwarded arrive", {"force_tma_a": 1, "pair": 1, "pair_remote": 0, "tall_min_stages": 4}),
+                 ("tma, wide backward-filter tile", {"force_tma_a": 1, "max_splits": 1}), ("tma, no wide backward-filter tile", {"force_tma_a": 1, "wgrad_wide": 0}),
                  ("default", {})]
 
 
@@ -183,7 +185,7 @@ def test_conv_operand_paths(g, case):
     wy = orc.conv_forward(x, w, b, *geo)
     wdx = orc.conv_backward_data(dy, w, *geo)
     wdw = orc.conv_backward_filter(x, dy, *geo)
-    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1, "pair": 0, "pair_remote": 1, "tall_min_stages": 32, "no_pointwise": 0}
+    defaults = {"no_tma_a": 0, "force_tma_a": 0, "no_tall": 0, "tma_tf32": 1, "pair": 0, "pair_remote": 1, "tall_min_stages": 32, "no_pointwise": 0, "wgrad_wide": 1, "max_splits": 0}
     for name, opts in OPERAND_PATHS:
         try:
             for k, v in {**defaults, **opts}.items():

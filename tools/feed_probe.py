@@ -7,6 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from minerva_b200 import _lib
 lib = _lib.use_tuning()
+for kv in sys.argv[1:]:      # extra KEY=INT tuning options
+    lib.mnv_debug_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1]))
 st = torch.cuda.current_stream().cuda_stream
 ws = torch.empty(lib.mnv_workspace_bytes_hint(), dtype=torch.uint8, device="cuda")
 B = 256
