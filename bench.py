@@ -506,6 +506,9 @@ def measure(C, args, wl_key, headline):
         C.sync_all()
         if not res["merge_check"]["ok"]:
             return res, net, trainer, du, (x, onehot)
+        for _ in range(3):               # back to the steady state of the training loop (the check re-seeds, syncs and reads back)
+            trainer.step()
+        C.sync_all()
     sampler = ClockSampler(C.local) if headline else None
     if sampler:
         sampler.start()
