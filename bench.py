@@ -138,7 +138,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)      # a few samples per timed region: every NVML query takes driver locks the launching thread also wants
+            time.sleep(0.03)      # a few samples per timed region: every NVML query takes driver locks the launching thread also wants
 
     def summary(self):
         s = sorted(self.samples)
